@@ -1,0 +1,229 @@
+"""Structure-of-arrays packing of colliders (host side).
+
+The reference keeps one Python object per collider (distance3d/colliders.py:17-646)
+and calls its `support_function` thousands of times per pair.  Here a set of N
+colliders is ONE record of flat arrays (see include/d3d_types.h) that lives in
+HBM and is indexed by the kernels:
+
+    type      int32[N]     type tag
+    pose      f64[N,4,4]   row-major collider2origin
+    param     f64[N,3]     radius / height / size / radii ...
+    vert_off  int32[N]     range into the shared vertex pool
+    vert_len  int32[N]
+    verts     f64[M,3]     box: 8 world vertices (written on the device by
+                           d3d_prepare); hull: world frame; mesh: local frame
+    margin    f64[N]       optional Margin wrapper
+
+`ColliderSet` holds the host copy (numpy) and, lazily, the device copy (torch
+tensors on the current CUDA device).
+"""
+import ctypes
+
+import numpy as np
+
+SPHERE, CAPSULE, BOX, ELLIPSOID, CYLINDER, HULL, MESH, DISK, ELLIPSE, CONE = range(10)
+TYPE_NAMES = ["sphere", "capsule", "box", "ellipsoid", "cylinder", "hull", "mesh",
+              "disk", "ellipse", "cone"]
+
+
+class CColliders(ctypes.Structure):
+    """ctypes mirror of `struct d3d_colliders` (include/d3d_types.h)."""
+    _fields_ = [
+        ("n", ctypes.c_int64),
+        ("type", ctypes.c_void_p),
+        ("pose", ctypes.c_void_p),
+        ("param", ctypes.c_void_p),
+        ("vert_off", ctypes.c_void_p),
+        ("vert_len", ctypes.c_void_p),
+        ("verts", ctypes.c_void_p),
+        ("margin", ctypes.c_void_p),
+    ]
+
+
+class ColliderSet:
+    """Packed set of colliders.
+
+    Build it with :func:`pack_colliders` (from collider objects) or
+    :meth:`from_arrays`.  Host arrays are the source of truth until
+    :meth:`device` is called; device tensors are cached per CUDA device.
+    """
+
+    def __init__(self, type_, pose, param, vert_off, vert_len, verts, margin=None,
+                 boxes_prepared=False):
+        n = len(type_)
+        self.type = np.ascontiguousarray(type_, dtype=np.int32)
+        self.pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(n, 4, 4)
+        self.param = np.ascontiguousarray(param, dtype=np.float64).reshape(n, 3)
+        self.vert_off = np.ascontiguousarray(vert_off, dtype=np.int32)
+        self.vert_len = np.ascontiguousarray(vert_len, dtype=np.int32)
+        self.verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 3)
+        if len(self.verts) == 0:
+            self.verts = np.zeros((1, 3))  # never hand out a null pool pointer
+        self.margin = None if margin is None else np.ascontiguousarray(margin, dtype=np.float64)
+        self.boxes_prepared = boxes_prepared
+        self._device = {}
+
+    from_arrays = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def __len__(self):
+        return len(self.type)
+
+    @property
+    def n_vertices(self):
+        return len(self.verts)
+
+    def host_struct(self):
+        """`d3d_colliders` over the HOST arrays (for the CPU oracle in tests)."""
+        s = CColliders()
+        s.n = len(self)
+        s.type = self.type.ctypes.data
+        s.pose = self.pose.ctypes.data
+        s.param = self.param.ctypes.data
+        s.vert_off = self.vert_off.ctypes.data
+        s.vert_len = self.vert_len.ctypes.data
+        s.verts = self.verts.ctypes.data
+        s.margin = None if self.margin is None else self.margin.ctypes.data
+        return s
+
+    def device(self, device=None):
+        """Upload (once) and return the device-resident buffers."""
+        import torch
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        key = (device.type, device.index)
+        if key not in self._device:
+            self._device[key] = DeviceColliders(self, device)
+        return self._device[key]
+
+    def invalidate_device(self):
+        self._device = {}
+
+    def subset(self, idx):
+        """New set with the colliders `idx` (vertex pool is re-packed)."""
+        idx = np.asarray(idx)
+        vert_len = self.vert_len[idx]
+        vert_off = np.zeros(len(idx), dtype=np.int64)
+        if len(idx):
+            vert_off[1:] = np.cumsum(vert_len[:-1])
+        total = int(vert_len.sum())
+        verts = np.zeros((total, 3))
+        for k, i in enumerate(idx):
+            o, l = int(self.vert_off[i]), int(self.vert_len[i])
+            verts[vert_off[k]:vert_off[k] + l] = self.verts[o:o + l]
+        return ColliderSet(self.type[idx], self.pose[idx], self.param[idx], vert_off, vert_len,
+                           verts, None if self.margin is None else self.margin[idx],
+                           boxes_prepared=self.boxes_prepared)
+
+
+class DeviceColliders:
+    """Device copy of a ColliderSet + the `d3d_colliders` struct pointing at it."""
+
+    def __init__(self, cs, device):
+        import torch
+        from . import _lib
+        self.device = device
+        self.n = len(cs)
+        to = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+        self.type = to(cs.type)
+        self.pose = to(cs.pose)
+        self.param = to(cs.param)
+        self.vert_off = to(cs.vert_off)
+        self.vert_len = to(cs.vert_len)
+        self.verts = to(cs.verts)
+        self.margin = None if cs.margin is None else to(cs.margin)
+        self.struct = CColliders()
+        self.struct.n = self.n
+        self.struct.type = self.type.data_ptr()
+        self.struct.pose = self.pose.data_ptr()
+        self.struct.param = self.param.data_ptr()
+        self.struct.vert_off = self.vert_off.data_ptr()
+        self.struct.vert_len = self.vert_len.data_ptr()
+        self.struct.verts = self.verts.data_ptr()
+        self.struct.margin = None if self.margin is None else self.margin.data_ptr()
+        # box vertices are generated on the device (geometry.py:138-157)
+        _lib.prepare(self)
+
+
+def _pose_from_center(center):
+    T = np.eye(4)
+    T[:3, 3] = center
+    return T
+
+
+def pack_colliders(colliders):
+    """Pack a sequence of collider objects into a :class:`ColliderSet`."""
+    from . import colliders as C
+    n = len(colliders)
+    type_ = np.zeros(n, dtype=np.int32)
+    pose = np.zeros((n, 4, 4))
+    pose[:] = np.eye(4)
+    param = np.zeros((n, 3))
+    vert_off = np.zeros(n, dtype=np.int32)
+    vert_len = np.zeros(n, dtype=np.int32)
+    margin = np.zeros(n)
+    any_margin = False
+    chunks = []
+    n_verts = 0
+
+    def add_vertices(i, V):
+        nonlocal n_verts
+        V = np.asarray(V, dtype=np.float64).reshape(-1, 3)
+        vert_off[i] = n_verts
+        vert_len[i] = len(V)
+        chunks.append(V)
+        n_verts += len(V)
+
+    for i, c in enumerate(colliders):
+        while isinstance(c, C.Margin):
+            margin[i] += c.margin
+            any_margin = True
+            c = c.collider
+        if isinstance(c, C.Box):
+            type_[i] = BOX
+            pose[i] = c.box2origin
+            param[i] = c.size
+            add_vertices(i, np.zeros((8, 3)))
+        elif isinstance(c, C.ConvexHullVertices):
+            type_[i] = HULL
+            add_vertices(i, c.vertices)
+        elif isinstance(c, C.MeshGraph):
+            type_[i] = MESH
+            pose[i] = c.mesh2origin
+            add_vertices(i, c.vertices)
+        elif isinstance(c, C.Sphere):
+            type_[i] = SPHERE
+            pose[i] = _pose_from_center(c.c)
+            param[i, 0] = c.radius
+        elif isinstance(c, C.Capsule):
+            type_[i] = CAPSULE
+            pose[i] = c.capsule2origin
+            param[i, :2] = (c.radius, c.height)
+        elif isinstance(c, C.Ellipsoid):
+            type_[i] = ELLIPSOID
+            pose[i] = c.ellipsoid2origin
+            param[i] = c.radii
+        elif isinstance(c, C.Cylinder):
+            type_[i] = CYLINDER
+            pose[i] = c.cylinder2origin
+            param[i, :2] = (c.radius, c.length)
+        elif isinstance(c, C.Disk):
+            type_[i] = DISK
+            pose[i, :3, 3] = c.c
+            pose[i, :3, 2] = c.normal
+            param[i, 0] = c.radius
+        elif isinstance(c, C.Ellipse):
+            type_[i] = ELLIPSE
+            pose[i, :3, 3] = c.c
+            pose[i, :3, 0] = c.axes[0]
+            pose[i, :3, 1] = c.axes[1]
+            param[i, :2] = c.radii
+        elif isinstance(c, C.Cone):
+            type_[i] = CONE
+            pose[i] = c.cone2origin
+            param[i, :2] = (c.radius, c.height)
+        else:
+            raise TypeError("Unsupported collider type %r" % type(c))
+    verts = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 3))
+    return ColliderSet(type_, pose, param, vert_off, vert_len, verts,
+                       margin if any_margin else None)
