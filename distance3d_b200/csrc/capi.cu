@@ -1,0 +1,230 @@
+// C-ABI plumbing (errors, device info) and the small per-collider kernels:
+// box vertex generation, batched support map evaluation, bounding boxes.
+#include <stdarg.h>
+#include <string.h>
+
+#include "d3d_common.cuh"
+#include "d3d_support.cuh"
+
+static thread_local char g_error[512] = "";
+
+int d3d_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+int d3d_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+namespace {
+
+// geometry.py:138-157 convert_box_to_vertices for every box of the set
+__global__ void k_prepare(d3d_colliders c, double *verts_out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t i = t >> 3;
+    int v = (int)(t & 7);
+    if (i >= c.n || c.type[i] != D3D_BOX) return;
+    Collider col = load_collider(c, i);
+    st3(verts_out + 3 * ((int64_t)c.vert_off[i] + v), box_vertex(col, v));
+}
+
+__global__ void k_support(d3d_colliders c, const int32_t *idx, const double *dirs, int64_t n,
+                          double *out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    Collider col = load_collider(c, idx[t]);
+    st3(out + 3 * t, support<1>(col, ld3(dirs + 3 * t), 0));
+}
+
+__global__ void k_center(d3d_colliders c, double *out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= c.n) return;
+    Collider col = load_collider(c, t);
+    st3(out + 3 * t, center_of(col));
+}
+
+// colliders.py aabb() -> containment.py:6-229.  One thread per collider; hull
+// and mesh vertex scans are serial here (the LBVH path uses k_aabb only once per
+// pose update, the narrow phase dominates).
+__global__ void k_aabb(d3d_colliders c, double *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    Collider col = load_collider(c, i);
+    double lo[3], hi[3];
+    double t[3] = {col.tx, col.ty, col.tz};
+    double e[3] = {0.0, 0.0, 0.0};
+    bool have_extent = true;
+    const double R[3][3] = {{col.r00, col.r01, col.r02}, {col.r10, col.r11, col.r12},
+                            {col.r20, col.r21, col.r22}};
+    const double p[3] = {col.p0, col.p1, col.p2};
+    switch (col.type) {
+    case D3D_SPHERE:  // containment.py:44
+        e[0] = e[1] = e[2] = col.p0;
+        break;
+    case D3D_CAPSULE:  // containment.py:121
+        for (int k = 0; k < 3; ++k) e[k] = 0.5 * col.p1 * fabs(R[k][2]) + col.p0;
+        break;
+    case D3D_CYLINDER:  // containment.py:94-95
+        for (int k = 0; k < 3; ++k) {
+            double a = R[k][2];
+            e[k] = 0.5 * col.p1 * fabs(a) + col.p0 * sqrt(1.0 - a * a);
+        }
+        break;
+    case D3D_ELLIPSOID: {  // containment.py:144-147 (reproduced as is)
+        double E[3][3];
+        for (int k = 0; k < 3; ++k) {
+            double col_[3];
+            for (int j = 0; j < 3; ++j) col_[j] = R[j][k] * p[k];
+            double nrm = sqrt((col_[0] * col_[0] + col_[1] * col_[1]) + col_[2] * col_[2]);
+            for (int j = 0; j < 3; ++j) E[j][k] = col_[j] / nrm * p[k];
+        }
+        for (int j = 0; j < 3; ++j) {
+            double best = 0.0;
+            for (int r = 0; r < 3; ++r) {
+                double val = dot_blas(V3(R[r][0], R[r][1], R[r][2]), V3(E[j][0], E[j][1], E[j][2]));
+                if (r == 0 || val > best) best = val;
+            }
+            e[j] = best;
+        }
+        break;
+    }
+    case D3D_BOX: {  // containment.py:66-67
+        for (int v = 0; v < 8; ++v) {
+            v3 x = box_vertex(col, v);
+            double xs[3] = {x.x, x.y, x.z};
+            for (int k = 0; k < 3; ++k) {
+                if (v == 0 || xs[k] < lo[k]) lo[k] = xs[k];
+                if (v == 0 || xs[k] > hi[k]) hi[k] = xs[k];
+            }
+        }
+        have_extent = false;
+        break;
+    }
+    case D3D_HULL:  // containment.py:22
+    case D3D_MESH: {  // colliders.py:234-237
+        for (int v = 0; v < col.nv; ++v) {
+            v3 x = ld3(col.V + 3 * v);
+            if (col.type == D3D_MESH)
+                x = V3(col.tx + dot_blas(x, V3(col.r00, col.r01, col.r02)),
+                       col.ty + dot_blas(x, V3(col.r10, col.r11, col.r12)),
+                       col.tz + dot_blas(x, V3(col.r20, col.r21, col.r22)));
+            double xs[3] = {x.x, x.y, x.z};
+            for (int k = 0; k < 3; ++k) {
+                if (v == 0 || xs[k] < lo[k]) lo[k] = xs[k];
+                if (v == 0 || xs[k] > hi[k]) hi[k] = xs[k];
+            }
+        }
+        have_extent = false;
+        break;
+    }
+    case D3D_DISK:  // containment.py:173
+        for (int k = 0; k < 3; ++k) e[k] = col.p0 * sqrt(1.0 - R[k][2] * R[k][2]);
+        break;
+    case D3D_ELLIPSE:  // containment.py:228
+        for (int k = 0; k < 3; ++k) {
+            double u = col.p0 * R[k][0], w = col.p1 * R[k][1];
+            e[k] = sqrt(u * u + w * w);
+        }
+        break;
+    case D3D_CONE:  // containment.py:199-203
+        for (int k = 0; k < 3; ++k) {
+            double pa = t[k];
+            double pb = t[k] + col.p1 * R[k][2];
+            double a = pb - pa;
+            double ee = sqrt(1.0 - a * a / (col.p1 * col.p1));
+            double l = pa - ee * col.p0, h = pa + ee * col.p0;
+            lo[k] = l < pb ? l : pb;
+            hi[k] = h > pb ? h : pb;
+        }
+        have_extent = false;
+        break;
+    }
+    if (have_extent)
+        for (int k = 0; k < 3; ++k) { lo[k] = t[k] - e[k]; hi[k] = t[k] + e[k]; }
+    if (col.margin != 0.0)  // colliders.py:639-643
+        for (int k = 0; k < 3; ++k) { lo[k] -= col.margin; hi[k] += col.margin; }
+    double2 *o = reinterpret_cast<double2 *>(out + 6 * i);
+    o[0] = make_double2(lo[0], hi[0]);
+    o[1] = make_double2(lo[1], hi[1]);
+    o[2] = make_double2(lo[2], hi[2]);
+}
+
+__global__ void k_debug_norm(const double *v, int64_t n, double *out, int mode) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double x = v[3 * t], y = v[3 * t + 1], z = v[3 * t + 2];
+    out[t] = mode == 0 ? norm_x87(x, y, z) : norm_x87_exact(x, y, z);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *d3d_last_error_string(void) { return g_error; }
+
+int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream) {
+    if (!c || !verts_out) return d3d_set_error("d3d_prepare: null argument");
+    if (c->n == 0) return 0;
+    int64_t threads = c->n * 8;
+    k_prepare<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*c, verts_out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_support(const d3d_colliders *c, const int32_t *idx, const double *dirs, int64_t n,
+                double *out, void *stream) {
+    if (!c || !idx || !dirs || !out) return d3d_set_error("d3d_support: null argument");
+    if (n == 0) return 0;
+    k_support<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*c, idx, dirs, n, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_center(const d3d_colliders *c, double *out, void *stream) {
+    if (!c || !out) return d3d_set_error("d3d_center: null argument");
+    if (c->n == 0) return 0;
+    k_center<<<(unsigned)((c->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*c, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_aabb(const d3d_colliders *c, double *out, void *stream) {
+    if (!c || !out) return d3d_set_error("d3d_aabb: null argument");
+    if (c->n == 0) return 0;
+    k_aabb<<<(unsigned)((c->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*c, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* test hook: out[k] = norm of v[k,:] with the dnrm2 (x87) semantics of d3d_math.cuh;
+ * mode 0 = production path, 1 = exact integer emulation only */
+int d3d_debug_norm(const double *v, int64_t n, double *out, int mode, void *stream) {
+    if (n == 0) return 0;
+    k_debug_norm<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, n, out, mode);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    D3D_CUDA_CHECK(cudaGetDevice(&dev));
+    if (sm_count) *sm_count = d3d_sm_count();
+    if (cc_major) D3D_CUDA_CHECK(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) D3D_CUDA_CHECK(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// Jolt closest-point-to-origin simplex solver, all state in registers.
+// Restates distance3d/gjk/_gjk_jolt.py:291-711 (cited per function) with the
+// reference's evaluation order so that results are bit-identical.
+#pragma once
+#include "d3d_math.cuh"
+
+// _gjk_jolt.py:291-312
+D3D_DEV void bary_line(v3 a, v3 b, double &u, double &v) {
+    v3 ab = b - a;
+    double denominator = dot_blas(ab, ab);
+    if (denominator < D3D_EPS_SQR) {
+        if (dot_blas(a, a) < dot_blas(b, b)) { u = 1.0; v = 0.0; }
+        else { u = 0.0; v = 1.0; }
+    } else {
+        v = -dot_blas(a, ab) / denominator;
+        u = 1.0 - v;
+    }
+}
+
+// _gjk_jolt.py:315-372
+D3D_DEV void bary_plane(v3 a, v3 b, v3 c, double &u, double &v, double &w) {
+    v3 v0 = b - a, v1 = c - a, v2 = c - b;
+    double d00 = dot_blas(v0, v0), d11 = dot_blas(v1, v1), d22 = dot_blas(v2, v2);
+    if (d00 <= d22) {
+        double d01 = dot_blas(v0, v1);
+        double denominator = d00 * d11 - d01 * d01;
+        if (fabs(denominator) < D3D_EPS) {
+            if (d00 > d11) { bary_line(a, b, u, v); w = 0.0; }
+            else { bary_line(a, c, u, w); v = 0.0; }
+        } else {
+            double a0 = dot_blas(a, v0), a1 = dot_blas(a, v1);
+            v = (d01 * a1 - d11 * a0) / denominator;
+            w = (d01 * a0 - d00 * a1) / denominator;
+            u = 1.0 - v - w;
+        }
+    } else {
+        double d12 = dot_blas(v1, v2);
+        double denominator = d11 * d22 - d12 * d12;
+        if (fabs(denominator) < D3D_EPS) {
+            if (d11 > d22) { bary_line(a, c, u, w); v = 0.0; }
+            else { bary_line(b, c, v, w); u = 0.0; }
+        } else {
+            double c1 = dot_blas(c, v1), c2 = dot_blas(c, v2);
+            u = (d22 * c1 - d12 * c2) / denominator;
+            v = (d11 * c2 - d12 * c1) / denominator;
+            w = 1.0 - u - v;
+        }
+    }
+}
+
+// utils.py:73
+D3D_DEV double triple(v3 a, v3 b, v3 c) { return dot_blas(a, cross(b, c)); }
+
+// _gjk_jolt.py:375-390
+D3D_DEV void bary_tetra(v3 a, v3 b, v3 c, v3 d, double &u, double &v, double &w, double &x) {
+    v3 vab = b - a, vac = c - a, vad = d - a;
+    double va6 = -triple(b, d - b, c - b);
+    double vb6 = -triple(a, vac, vad);
+    double vc6 = -triple(a, vad, vab);
+    double vd6 = -triple(a, vab, vac);
+    double v6 = 1.0 / triple(vab, vac, vad);
+    u = va6 * v6; v = vb6 * v6; w = vc6 * v6; x = vd6 * v6;
+}
+
+// _gjk_jolt.py:393-412
+D3D_DEV v3 closest_line(v3 a, v3 b, int &set) {
+    double u, v;
+    bary_line(a, b, u, v);
+    if (v <= 0.0) { set = 1; return a; }
+    if (u <= 0.0) { set = 2; return b; }
+    set = 3;
+    return a * u + b * v;
+}
+
+// _gjk_jolt.py:415-523.  Not force-inlined: it is instantiated for the
+// triangle case and inside the per-face loop of the tetrahedron case.
+static __device__ __noinline__ v3 closest_triangle(v3 a, v3 b, v3 c, int &set) {
+    v3 ab = b - a, ac = c - a, bc = c - b;
+    bool bc_shorter_than_ac = dot_blas(bc, bc) < dot_blas(ac, ac);
+    v3 n = bc_shorter_than_ac ? cross(ab, bc) : cross(ab, ac);
+    double n_len_sq = dot_blas(n, n);
+
+    if (n_len_sq < D3D_EPS_SQR) {  // degenerate: best of the three edges
+        int closest_set, new_set;
+        v3 closest_point = closest_line(a, b, closest_set);
+        double best_dist_sq = dot_blas(closest_point, closest_point);
+        v3 q = closest_line(a, c, new_set);
+        double dist_sq = dot_blas(q, q);
+        if (dist_sq < best_dist_sq) {
+            closest_point = q;
+            best_dist_sq = dist_sq;
+            closest_set = (new_set & 1) + ((new_set & 2) << 1);
+        }
+        q = closest_line(b, c, new_set);
+        dist_sq = dot_blas(q, q);
+        if (dist_sq < best_dist_sq) {
+            closest_point = q;
+            closest_set = new_set << 1;
+        }
+        set = closest_set;
+        return closest_point;
+    }
+
+    v3 ap = -a;
+    double d1 = dot_blas(ab, ap), d2 = dot_blas(ac, ap);
+    if (d1 <= 0.0 && d2 <= 0.0) { set = 1; return a; }
+
+    v3 bp = -b;
+    double d3 = dot_blas(ab, bp), d4 = dot_blas(ac, bp);
+    if (d3 >= 0.0 && d4 <= d3) { set = 2; return b; }
+
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0 && 0.0 <= d1 && d3 <= 0.0) {
+        double v = d1 / (d1 - d3);
+        set = 3;
+        return a + ab * v;
+    }
+
+    v3 cp = -c;
+    double d5 = dot_blas(ab, cp), d6 = dot_blas(ac, cp);
+    if (d6 >= 0.0 && d5 <= d6) { set = 4; return c; }
+
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0 && 0.0 <= d2 && d6 <= 0.0) {
+        double w = d2 / (d2 - d6);
+        set = 5;
+        return a + ac * w;
+    }
+
+    double va = d3 * d6 - d5 * d4;
+    double d4_d3 = d4 - d3, d5_d6 = d5 - d6;
+    if (va <= 0.0 && 0.0 <= d4_d3 && d5_d6 >= 0.0) {
+        double w = d4_d3 / (d4_d3 + d5_d6);
+        set = 6;
+        return b + bc * w;
+    }
+
+    set = 7;
+    double s = dot_blas((a + b) + c, n);
+    return (n * s) / (3.0 * n_len_sq);
+}
+
+// _gjk_jolt.py:526-570: bit i set = origin outside plane i
+D3D_DEV int origin_outside_planes(v3 a, v3 b, v3 c, v3 d) {
+    v3 ab = b - a, ac = c - a, ad = d - a, bd = d - b, bc = c - b;
+    v3 ab_x_ac = cross(ab, ac), ac_x_ad = cross(ac, ad), ad_x_ab = cross(ad, ab),
+       bd_x_bc = cross(bd, bc);
+    double p0 = dot_blas(a, ab_x_ac), p1 = dot_blas(a, ac_x_ad), p2 = dot_blas(a, ad_x_ab),
+           p3 = dot_blas(b, bd_x_bc);
+    double s0 = dot_blas(ad, ab_x_ac), s1 = dot_blas(ab, ac_x_ad), s2 = dot_blas(ac, ad_x_ab),
+           s3 = -dot_blas(ab, bd_x_bc);
+    if (s0 > 0.0 && s1 > 0.0 && s2 > 0.0 && s3 > 0.0)
+        return (p0 >= -D3D_EPS ? 1 : 0) | (p1 >= -D3D_EPS ? 2 : 0) | (p2 >= -D3D_EPS ? 4 : 0) |
+               (p3 >= -D3D_EPS ? 8 : 0);
+    if (s0 < 0.0 && s1 < 0.0 && s2 < 0.0 && s3 < 0.0)
+        return (p0 <= D3D_EPS ? 1 : 0) | (p1 <= D3D_EPS ? 2 : 0) | (p2 <= D3D_EPS ? 4 : 0) |
+               (p3 <= D3D_EPS ? 8 : 0);
+    return 0xf;
+}
+
+// _gjk_jolt.py:573-631
+D3D_DEV v3 closest_tetrahedron(v3 a, v3 b, v3 c, v3 d, int &set) {
+    int closest_set = 0xf;
+    v3 closest_point = V3(0.0, 0.0, 0.0);
+    double best_dist_sq = D3D_MAX_FLOAT;
+    int out = origin_outside_planes(a, b, c, d);
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        if (!(out & (1 << f))) continue;
+        // faces: abc, acd, adb, bdc
+        v3 fa = (f == 3) ? b : a;
+        v3 fb = (f == 0) ? b : ((f == 1) ? c : d);
+        v3 fc = (f == 0) ? c : ((f == 1) ? d : ((f == 2) ? b : c));
+        int s;
+        v3 q = closest_triangle(fa, fb, fc, s);
+        double dist_sq = dot_blas(q, q);
+        if (f == 0 || dist_sq < best_dist_sq) {
+            best_dist_sq = dist_sq;
+            closest_point = q;
+            if (f == 0) closest_set = s;
+            else if (f == 1) closest_set = (s & 1) + ((s & 6) << 1);
+            else if (f == 2) closest_set = (s & 1) + ((s & 2) << 2) + ((s & 4) >> 1);
+            else closest_set = ((s & 1) << 1) + ((s & 2) << 2) + (s & 4);
+        }
+    }
+    set = closest_set;
+    return closest_point;
+}
+
+// _gjk_jolt.py:690-711
+D3D_DEV bool closest_point_to_origin(v3 y0, v3 y1, v3 y2, v3 y3, int n_points,
+                                     double prev_v_len_sq, v3 &v_out, double &v_len_sq_out,
+                                     int &set_out) {
+    v3 v;
+    int set;
+    if (n_points == 1) { set = 1; v = y0; }
+    else if (n_points == 2) v = closest_line(y0, y1, set);
+    else if (n_points == 3) v = closest_triangle(y0, y1, y2, set);
+    else v = closest_tetrahedron(y0, y1, y2, y3, set);
+    double v_len_sq = dot_blas(v, v);
+    if (v_len_sq < prev_v_len_sq) {
+        v_out = v; v_len_sq_out = v_len_sq; set_out = set;
+        return true;
+    }
+    return false;
+}

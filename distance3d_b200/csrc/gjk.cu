@@ -1,0 +1,444 @@
+// Batched Jolt-variant GJK (distance + closest points, and boolean intersection).
+//
+// Replaces the Python driver loops gjk_distance_jolt / gjk_intersection_jolt and
+// their numba step functions (distance3d/gjk/_gjk_jolt.py:29-288) for MANY pairs
+// per call.  Pipeline, all on the caller's stream, no host synchronisation:
+//
+//   k_pair_keys   key = (typeA, typeB) bin, or the "wide" bin when a collider has
+//                 more than D3D_THREAD_HULL_MAX vertices; warp-aggregated histogram
+//   k_bin_scan    exclusive scan of the 101 bins
+//   k_bin_scatter counting-sort permutation (warp-aggregated cursors)
+//   k_gjk<MODE,1>  persistent, one THREAD per pair over the sorted order, lanes
+//                 refill from a warp-private chunk so a warp never idles on its
+//                 slowest pair; analytic supports in registers, simplex in
+//                 shared memory ([slot][component][thread], conflict free)
+//   k_gjk<MODE,32> one WARP per pair for wide hulls: vertex max-dot by strided
+//                 scan + __shfl_xor reduction (lowest index wins ties), the
+//                 simplex solve is replicated on all lanes
+#include "d3d_common.cuh"
+#include "d3d_simplex.cuh"
+#include "d3d_support.cuh"
+
+#define D3D_THREAD_HULL_MAX 16
+#define D3D_NBINS (D3D_NUM_TYPES * D3D_NUM_TYPES + 1)
+#define D3D_WIDE_BIN (D3D_NUM_TYPES * D3D_NUM_TYPES)
+
+namespace {
+
+struct GjkWorkspace {
+    int *counters;  // [0] next sorted index (thread kernel), [1] next (warp kernel),
+                    // [2] #pairs handled by the thread kernel, [3] total
+    int *hist;      // [128]
+    int *cursor;    // [128]
+    uint8_t *keys;  // [P]
+    int *perm;      // [P]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline size_t gjk_ws_bytes(int64_t n) {
+    return 4096 + align_up((size_t)n, 256) + align_up((size_t)n * 4, 256);
+}
+
+inline GjkWorkspace carve(void *ws, int64_t n) {
+    GjkWorkspace w;
+    char *p = reinterpret_cast<char *>(ws);
+    w.counters = reinterpret_cast<int *>(p);
+    w.hist = reinterpret_cast<int *>(p + 1024);
+    w.cursor = reinterpret_cast<int *>(p + 2048);
+    w.keys = reinterpret_cast<uint8_t *>(p + 4096);
+    w.perm = reinterpret_cast<int *>(p + 4096 + align_up((size_t)n, 256));
+    return w;
+}
+
+__device__ __forceinline__ bool is_wide(const d3d_colliders &c, int i) {
+    int t = __ldg(c.type + i);
+    return (t == D3D_HULL || t == D3D_MESH) && __ldg(c.vert_len + i) > D3D_THREAD_HULL_MAX;
+}
+
+__global__ void k_pair_keys(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n,
+                            GjkWorkspace w) {
+    __shared__ int sh[D3D_NBINS];
+    for (int i = threadIdx.x; i < D3D_NBINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
+        int key;
+        if (is_wide(c, pr.x) || is_wide(c, pr.y)) key = D3D_WIDE_BIN;
+        else key = __ldg(c.type + pr.x) * D3D_NUM_TYPES + __ldg(c.type + pr.y);
+        w.keys[k] = (uint8_t)key;
+        atomicAdd(&sh[key], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D3D_NBINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&w.hist[i], sh[i]);
+}
+
+__global__ void k_bin_scan(GjkWorkspace w, int64_t n) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < D3D_NBINS; ++i) {
+            int h = w.hist[i];
+            w.cursor[i] = acc;
+            if (i == D3D_WIDE_BIN) w.counters[2] = acc;
+            acc += h;
+        }
+        w.counters[0] = 0;
+        w.counters[1] = 0;
+        w.counters[3] = acc;
+    }
+}
+
+__global__ void k_bin_scatter(int64_t n, GjkWorkspace w) {
+    for (int64_t k0 = blockIdx.x * (int64_t)blockDim.x; k0 < n; k0 += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = k0 + threadIdx.x;
+        bool valid = k < n;
+        int key = valid ? w.keys[k] : -1;
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            unsigned peers = __match_any_sync(active, key);
+            int leader = __ffs(peers) - 1;
+            int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&w.cursor[key], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            w.perm[base + __popc(peers & ((1u << lane) - 1))] = (int)k;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Simplex storage: element (array a, slot s, component c) lives at
+// base[((a * 4 + s) * 3 + c) * stride].  a: 0 = Y (A - B), 1 = P (on A), 2 = Q (on B).
+struct Simplex {
+    double *base;
+    int stride;
+    D3D_DEV double &at(int a, int s, int c) const { return base[((a * 4 + s) * 3 + c) * stride]; }
+    D3D_DEV v3 get(int a, int s) const { return V3(at(a, s, 0), at(a, s, 1), at(a, s, 2)); }
+    D3D_DEV void set(int a, int s, v3 v) const { at(a, s, 0) = v.x; at(a, s, 1) = v.y; at(a, s, 2) = v.z; }
+};
+
+struct GjkParams {
+    double tolerance_sq;
+    double max_distance_squared;
+    double sanity_check;
+    double *out_dist;
+    double *out_a;
+    double *out_b;
+    double *out_Y;
+    int32_t *out_npoints;
+    int32_t *out_iters;
+    int32_t *out_status;
+    uint8_t *out_hit;
+};
+
+struct PairState {
+    Collider A, B;
+    v3 sd;
+    double v_len_sq, prev_v_len_sq;
+    int n_points, iters, k, state;
+};
+
+template <int G>
+D3D_DEV void init_pair(PairState &s, const d3d_colliders &c, const int32_t *pairs, int k) {
+    int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
+    s.A = load_collider(c, pr.x);
+    s.B = load_collider(c, pr.y);
+    s.sd = V3(1.0, 0.0, 0.0);
+    s.v_len_sq = 1.0;  // np.dot(sd, sd), _gjk_jolt.py:197
+    s.prev_v_len_sq = D3D_MAX_FLOAT;
+    s.n_points = 0;
+    s.iters = 0;
+    s.k = k;
+    s.state = D3D_UNKNOWN;
+}
+
+// max(|Y_i|^2) over the slots selected by mask (_gjk_jolt.py:634-640)
+D3D_DEV double max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
+    double m = dot_blas(y0, y0);  // slot 0 is always part of a non-empty prefix mask
+    if (!(mask & 1)) m = -1.0;
+    if (mask & 2) m = fmax(m, dot_blas(y1, y1));
+    if (mask & 4) m = fmax(m, dot_blas(y2, y2));
+    if (mask & 8) m = fmax(m, dot_blas(y3, y3));
+    return m;
+}
+
+// One iteration of _distance_loop (MODE 0, _gjk_jolt.py:224-288) or
+// _intersection_loop (MODE 1, _gjk_jolt.py:83-135).
+template <int MODE, int G>
+D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int lane) {
+    if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return; }
+    ++s.iters;
+    v3 p = support<G>(s.A, s.sd, lane);
+    v3 q = support<G>(s.B, -s.sd, lane);
+    v3 w = p - q;
+    double dot = dot_blas(s.sd, w);
+    if (MODE == 0) {
+        if (dot < 0.0 && dot * dot > s.v_len_sq * prm.max_distance_squared) {
+            s.state = D3D_CLIPPED;
+            return;
+        }
+    } else {
+        if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return; }
+    }
+    S.set(0, s.n_points, w);
+    if (MODE == 0) { S.set(1, s.n_points, p); S.set(2, s.n_points, q); }
+    ++s.n_points;
+
+    v3 y0 = S.get(0, 0), y1 = S.get(0, 1), y2 = S.get(0, 2), y3 = S.get(0, 3);
+    v3 v_new;
+    double v_len_sq_new;
+    int simplex;
+    bool ok = closest_point_to_origin(y0, y1, y2, y3, s.n_points, s.prev_v_len_sq, v_new,
+                                      v_len_sq_new, simplex);
+    if (ok) {
+        s.sd = v_new;
+        s.v_len_sq = v_len_sq_new;
+    } else {
+        if (MODE == 1) { s.state = D3D_NO_INTERSECTION; return; }
+        --s.n_points;  // undo add, keep all old points (_gjk_jolt.py:248-252)
+        simplex = (1 << s.n_points) - 1;
+    }
+    if (simplex == 0xf) {
+        if (MODE == 0) s.v_len_sq = 0.0;
+        s.state = D3D_INTERSECTION;
+        return;
+    }
+    if (MODE == 1) {
+        if (s.v_len_sq <= prm.tolerance_sq) { s.state = D3D_INTERSECTION; return; }
+        if (s.v_len_sq <= D3D_EPS * max_y_len_sq(y0, y1, y2, y3, (1 << s.n_points) - 1)) {
+            s.state = D3D_INTERSECTION;
+            return;
+        }
+    }
+    if (MODE == 0) {
+        // update_simplex_ypq (_gjk_jolt.py:654-664)
+        int nn = 0;
+        for (int i = 0; i < s.n_points; ++i)
+            if (simplex & (1 << i)) {
+                if (nn != i) { S.set(0, nn, S.get(0, i)); S.set(1, nn, S.get(1, i)); S.set(2, nn, S.get(2, i)); }
+                ++nn;
+            }
+        s.n_points = nn;
+        if (s.v_len_sq <= prm.tolerance_sq) { s.v_len_sq = 0.0; s.state = D3D_INTERSECTION; return; }
+        if (s.v_len_sq <= D3D_EPS * max_y_len_sq(y0, y1, y2, y3, simplex)) {
+            s.v_len_sq = 0.0;
+            s.state = D3D_INTERSECTION;
+            return;
+        }
+    }
+    s.sd = s.sd * -1.0;
+    if (!(s.prev_v_len_sq >= s.v_len_sq)) { s.state = D3D_MONOTONICITY; return; }
+    if (s.prev_v_len_sq - s.v_len_sq <= D3D_EPS * s.prev_v_len_sq) {
+        s.state = D3D_NO_INTERSECTION;
+        return;
+    }
+    s.prev_v_len_sq = s.v_len_sq;
+    if (MODE == 1) {
+        // update_simplex_y (_gjk_jolt.py:643-651)
+        int nn = 0;
+        for (int i = 0; i < s.n_points; ++i)
+            if (simplex & (1 << i)) {
+                if (nn != i) S.set(0, nn, S.get(0, i));
+                ++nn;
+            }
+        s.n_points = nn;
+    }
+}
+
+// Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).
+template <int MODE>
+D3D_DEV void gjk_finish(const PairState &s, const Simplex &S, const GjkParams &prm, bool writer) {
+    int64_t k = s.k;
+    int state = s.state;
+    if (MODE == 1) {
+        if (writer) {
+            prm.out_hit[k] = (state == D3D_INTERSECTION) ? 1 : 0;
+            if (prm.out_iters) prm.out_iters[k] = s.iters;
+            if (prm.out_status) prm.out_status[k] = state;
+        }
+        return;
+    }
+    v3 a = V3(0.0, 0.0, 0.0), b = a;
+    double dist = D3D_MAX_FLOAT;
+    if (state == D3D_NO_INTERSECTION || state == D3D_INTERSECTION) {
+        int n = s.n_points;
+        if (n == 1) { a = S.get(1, 0); b = S.get(2, 0); }
+        else if (n == 2) {
+            double u, v;
+            bary_line(S.get(0, 0), S.get(0, 1), u, v);
+            a = S.get(1, 0) * u + S.get(1, 1) * v;
+            b = S.get(2, 0) * u + S.get(2, 1) * v;
+        } else if (n == 3) {
+            double u, v, w;
+            bary_plane(S.get(0, 0), S.get(0, 1), S.get(0, 2), u, v, w);
+            a = (S.get(1, 0) * u + S.get(1, 1) * v) + S.get(1, 2) * w;
+            b = (S.get(2, 0) * u + S.get(2, 1) * v) + S.get(2, 2) * w;
+        } else if (n == 4) {
+            double u, v, w, x;
+            bary_tetra(S.get(0, 0), S.get(0, 1), S.get(0, 2), S.get(0, 3), u, v, w, x);
+            a = ((S.get(1, 0) * u + S.get(1, 1) * v) + S.get(1, 2) * w) + S.get(1, 3) * x;
+            b = ((S.get(2, 0) * u + S.get(2, 1) * v) + S.get(2, 2) * w) + S.get(2, 3) * x;
+        }
+        double check_value = fabs(dot_blas(s.sd, s.sd) - s.v_len_sq);
+        if (!(check_value < prm.sanity_check)) state = D3D_SANITY_FAILED;
+        dist = sqrt(s.v_len_sq);
+        if (dist < D3D_EPS) { a = (a + b) * 0.5; b = a; }
+    }
+    if (!writer) return;
+    prm.out_dist[k] = dist;
+    if (prm.out_a) st3(prm.out_a + 3 * k, a);
+    if (prm.out_b) st3(prm.out_b + 3 * k, b);
+    if (prm.out_Y) {
+        for (int i = 0; i < 4; ++i) st3(prm.out_Y + 12 * k + 3 * i, i < s.n_points ? S.get(0, i) : V3(0.0, 0.0, 0.0));
+    }
+    if (prm.out_npoints) prm.out_npoints[k] = s.n_points;
+    if (prm.out_iters) prm.out_iters[k] = s.iters;
+    if (prm.out_status) prm.out_status[k] = state;
+}
+
+#define GJK_THREADS 128
+#define GJK_CHUNK 256
+#define GJK_REFILL_MIN 8  // refill when at least this many lanes of the warp are idle
+
+// One thread per pair, persistent, lanes refill from a warp-private chunk.
+template <int MODE>
+__global__ void __launch_bounds__(GJK_THREADS, 3)
+k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
+    extern __shared__ double smem[];
+    Simplex S;
+    S.base = smem + threadIdx.x;
+    S.stride = GJK_THREADS;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int total = w.counters[2];
+    int chunk_begin = 0, chunk_end = 0;
+    bool exhausted = false;
+    PairState s;
+    s.state = D3D_UNKNOWN;
+    bool running = false;   // lane owns a pair that still iterates
+    bool finished = false;  // lane owns a pair whose result is not written yet
+
+    for (;;) {
+        unsigned run_mask = __ballot_sync(0xffffffffu, running);
+        int idle = 32 - __popc(run_mask);
+        if (idle >= GJK_REFILL_MIN || run_mask == 0) {
+            if (finished) { gjk_finish<MODE>(s, S, prm, true); finished = false; }
+            if (!exhausted) {
+                unsigned need = ~run_mask;
+                int rank = __popc(need & lt_mask);
+                int want = __popc(need);
+                int handed = 0;
+                while (handed < want && !exhausted) {
+                    if (chunk_begin == chunk_end) {
+                        int start = 0;
+                        if (lane == 0) start = atomicAdd(&w.counters[0], GJK_CHUNK);
+                        start = __shfl_sync(0xffffffffu, start, 0);
+                        if (start >= total) { exhausted = true; break; }
+                        chunk_begin = start;
+                        chunk_end = min(start + GJK_CHUNK, total);
+                    }
+                    int avail = chunk_end - chunk_begin;
+                    int give = min(avail, want - handed);
+                    if (!running && rank >= handed && rank < handed + give) {
+                        init_pair<1>(s, c, pairs, __ldg(w.perm + chunk_begin + (rank - handed)));
+                        running = true;
+                    }
+                    chunk_begin += give;
+                    handed += give;
+                }
+            }
+            run_mask = __ballot_sync(0xffffffffu, running);
+            if (run_mask == 0) break;
+        }
+        if (running) {
+            gjk_step<MODE, 1>(s, S, prm, 0);
+            if (s.state != D3D_UNKNOWN) { running = false; finished = true; }
+        }
+    }
+}
+
+// One warp per pair (wide hulls); every lane holds the same state.
+template <int MODE>
+__global__ void __launch_bounds__(GJK_THREADS, 3)
+k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
+    __shared__ double smem[(GJK_THREADS / 32) * 36];
+    const int lane = threadIdx.x & 31;
+    Simplex S;
+    S.base = smem + (threadIdx.x >> 5) * 36;
+    S.stride = 1;
+    const int first = w.counters[2], total = w.counters[3];
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&w.counters[1], 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0) + first;
+        if (idx >= total) break;
+        PairState s;
+        init_pair<32>(s, c, pairs, __ldg(w.perm + idx));
+        while (s.state == D3D_UNKNOWN) {
+            gjk_step<MODE, 32>(s, S, prm, lane);
+            __syncwarp();
+        }
+        gjk_finish<MODE>(s, S, prm, lane == 0);
+        __syncwarp();
+    }
+}
+
+template <int MODE>
+int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const GjkParams &prm,
+               void *workspace, size_t ws_bytes, cudaStream_t stream) {
+    if (n_pairs == 0) return 0;
+    if (n_pairs > 0x7fffffff) return d3d_set_error("d3d_gjk: more than 2^31-1 pairs in one call");
+    if (ws_bytes < gjk_ws_bytes(n_pairs)) return d3d_set_error("d3d_gjk: workspace too small");
+    GjkWorkspace w = carve(workspace, n_pairs);
+    D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 4096, stream));
+    int sms = d3d_sm_count();
+    int bin_blocks = (int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8);
+    k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w);
+    k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
+    k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
+    size_t smem = sizeof(double) * 36 * GJK_THREADS;
+    int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * 3);
+    k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    int wblocks = (int)d3d_min64((n_pairs + 3) / 4, (int64_t)sms * 3);
+    k_gjk_warp<MODE><<<wblocks, GJK_THREADS, 0, stream>>>(*c, pairs, w, prm);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t d3d_gjk_workspace_bytes(int64_t n_pairs) { return gjk_ws_bytes(n_pairs); }
+
+int d3d_gjk_distance(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                     double tolerance, double max_distance_squared, double sanity_check,
+                     double *out_dist, double *out_a, double *out_b, double *out_Y,
+                     int32_t *out_npoints, int32_t *out_iters, int32_t *out_status,
+                     void *workspace, size_t ws_bytes, void *stream) {
+    if (n_pairs == 0) return 0;
+    if (!c || !pairs || !out_dist) return d3d_set_error("d3d_gjk_distance: null argument");
+    GjkParams prm;
+    prm.tolerance_sq = tolerance * tolerance;
+    prm.max_distance_squared = max_distance_squared;
+    prm.sanity_check = sanity_check;
+    prm.out_dist = out_dist; prm.out_a = out_a; prm.out_b = out_b; prm.out_Y = out_Y;
+    prm.out_npoints = out_npoints; prm.out_iters = out_iters; prm.out_status = out_status;
+    prm.out_hit = nullptr;
+    return launch_gjk<0>(c, pairs, n_pairs, prm, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                         double tolerance, uint8_t *out_hit, int32_t *out_iters,
+                         int32_t *out_status, void *workspace, size_t ws_bytes, void *stream) {
+    if (n_pairs == 0) return 0;
+    if (!c || !pairs || !out_hit) return d3d_set_error("d3d_gjk_intersection: null argument");
+    GjkParams prm = {};
+    prm.tolerance_sq = tolerance * tolerance;
+    prm.out_hit = out_hit; prm.out_iters = out_iters; prm.out_status = out_status;
+    return launch_gjk<1>(c, pairs, n_pairs, prm, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

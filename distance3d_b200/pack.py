@@ -97,7 +97,9 @@ class ColliderSet:
         return self._device[key]
 
     def invalidate_device(self):
+        """Call after editing the host arrays in place (poses, parameters)."""
         self._device = {}
+        self.boxes_prepared = False
 
     def subset(self, idx):
         """New set with the colliders `idx` (vertex pool is re-packed)."""

@@ -1,0 +1,73 @@
+/* distance3d_b200 -- C ABI of the CUDA library (libd3d_b200.so).
+ *
+ * The reference (AlexanderFabisch/distance3d, pure Python + numba) has no FFI
+ * seam; the seam a maintainer would bind is its Python API.  Each entry point
+ * below names the reference function it replaces (file:line relative to the
+ * reference repository).  Conventions:
+ *   - every pointer is a DEVICE pointer unless marked "host";
+ *   - the caller owns all buffers (inputs, outputs, workspaces);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *     host synchronisation happens inside a call;
+ *   - return value 0 = ok, < 0 = API misuse / CUDA error, text available from
+ *     d3d_last_error_string(); data-dependent outcomes are per-pair status
+ *     codes (include/d3d_types.h).
+ * INTEGRATION.md shows the ctypes binding used by distance3d_b200/_lib.py.
+ */
+#ifndef D3D_B200_H
+#define D3D_B200_H
+
+#include <stddef.h>
+#include "d3d_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* host: message of the last failing call on this host thread */
+const char *d3d_last_error_string(void);
+/* host: SM count and compute capability of the current device */
+int d3d_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* geometry.py:138-157 convert_box_to_vertices (called from colliders.py:161-176 on
+ * construction and update_pose): writes the 8 world-frame vertices of every BOX of
+ * `c` into verts_out[vert_off .. vert_off+8). */
+int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream);
+
+/* colliders.py:131,221,272,326,374,426,479,533,590,629 <collider>.support_function(d):
+ * out[k,:] = support of collider idx[k] in direction dirs[k,:]. */
+int d3d_support(const d3d_colliders *c, const int32_t *idx, const double *dirs, int64_t n,
+                double *out, void *stream);
+
+/* colliders.py:134,171,224,266,319,367,419,472,527,582 <collider>.center(): out[n,3] */
+int d3d_center(const d3d_colliders *c, double *out, void *stream);
+
+/* colliders.py:140,180,234,281,335,383,435,489,543,599,639 <collider>.aabb()
+ * (containment.py:6-229): out[n,3,2] = [[xmin,xmax],[ymin,ymax],[zmin,zmax]]. */
+int d3d_aabb(const d3d_colliders *c, double *out, void *stream);
+
+/* Workspace size for d3d_gjk_distance / d3d_gjk_intersection over n_pairs pairs. */
+size_t d3d_gjk_workspace_bytes(int64_t n_pairs);
+
+/* gjk/_gjk_jolt.py:138-221 gjk_distance_jolt (= gjk.gjk, gjk/__init__.py:27) for
+ * pairs[k] = (index of collider 1, index of collider 2):
+ *   out_dist[k]      distance (MAX_FLOAT when status is CLIPPED)
+ *   out_a/out_b[k,3] closest points on collider 1 / 2          (may be NULL)
+ *   out_Y[k,4,3]     simplex of Minkowski-difference points    (may be NULL)
+ *   out_npoints[k]   number of valid rows of out_Y             (may be NULL)
+ *   out_iters[k]     GJK iterations (gjk_distance_jolt_iterations, :714-785; may be NULL)
+ *   out_status[k]    D3D_NO_INTERSECTION / D3D_INTERSECTION / D3D_CLIPPED / ... (may be NULL) */
+int d3d_gjk_distance(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                     double tolerance, double max_distance_squared, double sanity_check,
+                     double *out_dist, double *out_a, double *out_b, double *out_Y,
+                     int32_t *out_npoints, int32_t *out_iters, int32_t *out_status,
+                     void *workspace, size_t ws_bytes, void *stream);
+
+/* gjk/_gjk_jolt.py:29-135 gjk_intersection_jolt (= gjk.gjk_intersection): out_hit[k] in {0,1} */
+int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                         double tolerance, uint8_t *out_hit, int32_t *out_iters,
+                         int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -209,3 +209,11 @@ class Tree:
                                 c_i64(other.root), _p(other.nodes), _p(other.aabbs),
                                 _p(pairs), c_i64(n))
         return pairs[:n]
+
+
+def norm(v):
+    """BLAS dnrm2 (x87) of each row of v[n,3]."""
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(len(v))
+    lib().d3do_norm(_p(v), c_i64(len(v)), _p(out))
+    return out

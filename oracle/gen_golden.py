@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the REAL reference.
+
+Runs only in the build container (imports /root/reference through
+oracle/refshim).  The fixtures store the packed inputs (ColliderSet arrays)
+and the outputs of the reference's own functions:
+
+  gjk.npz      gjk.gjk / gjk.gjk_intersection / gjk_distance_jolt_iterations
+  epa.npz      epa.epa on the GJK simplices of intersecting pairs
+  mpr.npz      mpr.mpr_penetration / mpr_intersection
+  aabb.npz     collider.aabb(), AabbTree.overlaps_aabb_tree, all_aabbs_overlap
+  support.npz  collider.support_function on random directions
+  hulls.npz    ConvexHullVertices with 64-256 vertices (config C3 shape)
+
+Usage: python oracle/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import refbridge  # noqa: E402
+
+refbridge.setup()
+from distance3d import gjk, epa, mpr, aabb_tree  # noqa: E402
+from distance3d.gjk._gjk_jolt import gjk_distance_jolt_iterations  # noqa: E402
+
+OUT = os.path.join(refbridge.REPO, "tests", "golden")
+MAX_FLOAT = np.finfo(float).max
+ALL = ["sphere", "ellipsoid", "capsule", "cylinder", "box", "mesh", "cone", "disk", "ellipse"]
+
+
+def set_arrays(cs, prefix="cs_"):
+    d = {prefix + k: getattr(cs, k) for k in ("type", "pose", "param", "vert_off", "vert_len", "verts")}
+    if cs.margin is not None:
+        d[prefix + "margin"] = cs.margin
+    return d
+
+
+def run_gjk(cols, pairs):
+    n = len(pairs)
+    dist = np.zeros(n); a = np.zeros((n, 3)); b = np.zeros((n, 3)); Y = np.zeros((n, 4, 3))
+    status = np.zeros(n, dtype=np.int32); iters = np.zeros(n, dtype=np.int32)
+    hit = np.zeros(n, dtype=np.uint8)
+    for k, (i, j) in enumerate(pairs):
+        try:
+            d, pa, pb, yy = gjk.gjk(cols[i], cols[j])
+        except AssertionError:
+            status[k] = 4
+            continue
+        iters[k] = gjk_distance_jolt_iterations(cols[i], cols[j])
+        if pa is None:
+            dist[k] = MAX_FLOAT; status[k] = 3
+        else:
+            dist[k] = d; a[k] = pa; b[k] = pb; Y[k] = yy
+            status[k] = 1 if d == 0.0 else 0
+        hit[k] = gjk.gjk_intersection(cols[i], cols[j])
+    return dict(dist=dist, a=a, b=b, Y=Y, status=status, iters=iters, hit=hit)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rs = np.random.RandomState(2024)
+
+    # ---- GJK on all 9 collider types (+ Margin) ---------------------------
+    from distance3d import colliders as RC
+    cols = refbridge.random_reference_colliders(rs, 240, ALL)
+    for k in range(0, 240, 12):
+        cols[k] = RC.Margin(cols[k], 0.1 * rs.rand())
+    cs = refbridge.to_set(cols)
+    pairs = rs.randint(0, len(cols), size=(600, 2)).astype(np.int32)
+    res = run_gjk(cols, pairs)
+    # n_points is not returned by the reference; the oracle provides it and the
+    # test only compares the first n_points rows of Y
+    np.savez_compressed(os.path.join(OUT, "gjk.npz"), pairs=pairs, **set_arrays(cs), **res)
+
+    # support + aabb + center on the same set
+    dirs = rs.randn(len(cols), 4, 3)
+    dirs[:, 3] = [1.0, 0.0, 0.0]
+    sup = np.array([[c.support_function(np.ascontiguousarray(d)) for d in dirs[i]]
+                    for i, c in enumerate(cols)])
+    aabbs = np.array([c.aabb() for c in cols])
+    centers = np.array([c.center() for c in cols])
+    np.savez_compressed(os.path.join(OUT, "support.npz"), dirs=dirs, support=sup, aabb=aabbs,
+                        center=centers, **set_arrays(cs))
+
+    # ---- close-together shapes: EPA + MPR ---------------------------------
+    names = ["sphere", "ellipsoid", "capsule", "cylinder", "box", "mesh", "cone"]
+    cols2 = refbridge.random_reference_colliders(
+        rs, 160, names, **{n: dict(center_scale=0.3) for n in names})
+    cs2 = refbridge.to_set(cols2)
+    pairs2 = rs.randint(0, len(cols2), size=(400, 2)).astype(np.int32)
+    g2 = run_gjk(cols2, pairs2)
+    n = len(pairs2)
+    mtv = np.zeros((n, 3)); success = np.zeros(n, dtype=np.uint8); nfaces = np.zeros(n, dtype=np.int32)
+    estatus = np.full(n, -1, dtype=np.int32)
+    faces_all = np.zeros((n, 64, 4, 3))
+    for k, (i, j) in enumerate(pairs2):
+        if g2["dist"][k] != 0.0 or g2["status"][k] != 1:
+            continue
+        try:
+            m, faces, ok = epa.epa(g2["Y"][k].copy(), cols2[i], cols2[j])
+        except AssertionError:
+            estatus[k] = 7
+            continue
+        estatus[k] = 1
+        mtv[k] = m; success[k] = ok; nfaces[k] = len(faces); faces_all[k, :len(faces)] = faces
+    np.savez_compressed(os.path.join(OUT, "epa.npz"), pairs=pairs2, Y=g2["Y"], gjk_dist=g2["dist"],
+                        mtv=mtv, success=success, n_faces=nfaces, status=estatus,
+                        faces=faces_all.astype(np.float64), **set_arrays(cs2))
+    hit = np.zeros(n, dtype=np.uint8); hit_i = np.zeros(n, dtype=np.uint8)
+    depth = np.zeros(n); pdir = np.zeros((n, 3)); pos = np.zeros((n, 3))
+    for k, (i, j) in enumerate(pairs2):
+        h, dpt, dr, ps = mpr.mpr_penetration(cols2[i], cols2[j])
+        hit[k] = h
+        hit_i[k] = mpr.mpr_intersection(cols2[i], cols2[j])
+        if h:
+            depth[k] = dpt; pdir[k] = dr; pos[k] = ps
+    np.savez_compressed(os.path.join(OUT, "mpr.npz"), pairs=pairs2, hit=hit, hit_intersection=hit_i,
+                        depth=depth, dir=pdir, pos=pos, gjk_hit=g2["hit"], **set_arrays(cs2))
+
+    # ---- hulls with 64-256 vertices (config C3 shape) ----------------------
+    cols3 = []
+    for _ in range(24):
+        nv = rs.randint(64, 257)
+        cols3.extend(refbridge.random_reference_colliders(
+            rs, 1, ["mesh"], mesh=dict(n_vertices=nv, center_scale=0.8)))
+    cs3 = refbridge.to_set(cols3)
+    pairs3 = np.array([(i, j) for i in range(24) for j in range(24) if i < j][:120], dtype=np.int32)
+    g3 = run_gjk(cols3, pairs3)
+    n = len(pairs3)
+    mtv = np.zeros((n, 3)); success = np.zeros(n, dtype=np.uint8); nfaces = np.zeros(n, dtype=np.int32)
+    estatus = np.full(n, -1, dtype=np.int32)
+    for k, (i, j) in enumerate(pairs3):
+        if g3["dist"][k] != 0.0:
+            continue
+        try:
+            m, faces, ok = epa.epa(g3["Y"][k].copy(), cols3[i], cols3[j])
+        except AssertionError:
+            estatus[k] = 7
+            continue
+        estatus[k] = 1; mtv[k] = m; success[k] = ok; nfaces[k] = len(faces)
+    np.savez_compressed(os.path.join(OUT, "hulls.npz"), pairs=pairs3, epa_mtv=mtv, epa_success=success,
+                        epa_n_faces=nfaces, epa_status=estatus, **set_arrays(cs3), **g3)
+
+    # ---- broad phase -------------------------------------------------------
+    from distance3d.random import rand_capsule
+    rs32 = np.random.RandomState(32)
+    caps = []
+    for _ in range(1500):
+        caps.append(RC.Capsule(*rand_capsule(rs32, center_scale=2.0, radius_scale=0.1, height_scale=0.5)))
+    cs4 = refbridge.to_set(caps)
+    A = np.array([c.aabb() for c in caps])
+    tree = aabb_tree.AabbTree()
+    tree.insert_aabbs(A)
+    _, _, _, tpairs = tree.overlaps_aabb_tree(tree)
+    tpairs = np.array(tpairs, dtype=np.int32).reshape(-1, 2)
+    _, _, bpairs = aabb_tree.all_aabbs_overlap(A[:300], A[300:700])
+    bpairs = np.array(bpairs, dtype=np.int32).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "aabb.npz"), aabb=A, tree_pairs=tpairs, brute_pairs=bpairs,
+                        tree_nodes=tree.nodes, tree_root=tree.root, **set_arrays(cs4))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

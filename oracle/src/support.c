@@ -299,3 +299,8 @@ void d3do_aabb(const d3d_colliders *c, double *out) {
             }
     }
 }
+
+/* dnrm2 semantics (x87) for n 3-vectors: test hook for the device emulation */
+void d3do_norm(const double *v, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = vnorm_blas(vload(v + 3 * i));
+}

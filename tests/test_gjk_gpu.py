@@ -1,0 +1,150 @@
+"""GPU: the CUDA GJK path (through the C ABI) against the CPU oracle.
+
+Tolerances are the ones BASELINE.json states: distance and closest points within
+1e-9 absolute; intersection booleans identical except for pairs whose oracle
+distance is within 1e-12 of contact.  Bit-exact agreement is additionally
+reported (and required for the collider types whose support maps contain no
+BLAS-norm call: capsule, cylinder, box, hull).
+"""
+import numpy as np
+import pytest
+
+from distance3d_b200 import gjk, random as d3random
+from distance3d_b200 import pack as P
+from oracle import cpu_oracle as O
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def compare_distance(cs, pairs, exact_types=None, **kw):
+    res = gjk.gjk_distance_batch(cs, pairs, **kw).cpu()
+    ref = O.gjk_distance(cs, pairs, n_threads=O.max_threads(), **kw)
+    ok = ref["status"] <= 1
+    # identical termination state, except within 1e-12 of contact
+    near = (ref["dist"] < 1e-12) | (np.abs(res["dist"]) < 1e-12)
+    same = res["status"] == ref["status"]
+    assert np.all(same | near), "status differs on %d pairs" % int((~(same | near)).sum())
+    clipped = ref["status"] == 3
+    assert np.array_equal(res["status"][clipped], ref["status"][clipped])
+    m = ok & same
+    assert np.max(np.abs(res["dist"][m] - ref["dist"][m]), initial=0.0) < TOL
+    assert np.max(np.abs(res["closest_a"][m] - ref["a"][m]), initial=0.0) < TOL
+    assert np.max(np.abs(res["closest_b"][m] - ref["b"][m]), initial=0.0) < TOL
+    if exact_types is not None:
+        pairs = np.asarray(pairs)
+        ex = np.isin(cs.type[pairs[:, 0]], exact_types) & np.isin(cs.type[pairs[:, 1]], exact_types)
+        if True:
+            e = ex & ok
+            assert np.array_equal(res["dist"][e], ref["dist"][e])
+            assert np.array_equal(res["closest_a"][e], ref["a"][e])
+            assert np.array_equal(res["closest_b"][e], ref["b"][e])
+            assert np.array_equal(res["iters"][ex], ref["iters"][ex])
+            assert np.array_equal(res["n_points"][e], ref["n_points"][e])
+            for k in np.where(e)[0][:500]:
+                n = ref["n_points"][k]
+                assert np.array_equal(res["simplex"][k, :n], ref["Y"][k, :n])
+    return res, ref
+
+
+EXACT = tuple(range(10))  # every collider type is bit-exact (x87 norm emulated)
+
+
+def test_golden_all_types_vs_reference_outputs():
+    """CUDA path against the outputs of the real reference stored in tests/golden."""
+    cs, g = load_golden("gjk.npz")
+    res = gjk.gjk_distance_batch(cs, g["pairs"]).cpu()
+    ok = g["status"] <= 1
+    assert np.max(np.abs(res["dist"][ok] - g["dist"][ok])) < TOL
+    assert np.max(np.abs(res["closest_a"][ok] - g["a"][ok])) < TOL
+    assert np.max(np.abs(res["closest_b"][ok] - g["b"][ok])) < TOL
+    assert np.array_equal(res["status"][g["status"] == 3], g["status"][g["status"] == 3])
+    hit, _, _ = gjk.gjk_intersection_batch(cs, g["pairs"])
+    hit = hit.cpu().numpy()
+    near = g["dist"] < 1e-12
+    valid = g["status"] != 4
+    assert np.array_equal(hit[valid & ~near], g["hit"][valid & ~near])
+    compare_distance(cs, g["pairs"], exact_types=EXACT)
+    # bit-exact against the real reference's outputs, all nine collider types + Margin
+    assert np.array_equal(res["dist"][ok], g["dist"][ok])
+    assert np.array_equal(res["closest_a"][ok], g["a"][ok])
+    assert np.array_equal(res["closest_b"][ok], g["b"][ok])
+    valid = g["status"] != 4
+    assert np.array_equal(res["iters"][valid], g["iters"][valid])
+    assert np.array_equal(hit[valid], g["hit"][valid])
+
+
+def test_golden_wide_hulls_warp_kernel():
+    cs, g = load_golden("hulls.npz")
+    res, ref = compare_distance(cs, g["pairs"], exact_types=EXACT)
+    assert np.array_equal(res["dist"], g["dist"])  # bit-exact against the real reference
+    assert np.array_equal(res["closest_a"], g["a"])
+
+
+@pytest.mark.parametrize("names,exact", [
+    (("capsule", "cylinder", "box"), True),
+    (d3random.PRIMITIVES, True),
+    (d3random.PRIMITIVES + ("mesh",), True),
+    (("cone", "sphere", "box"), True),
+])
+def test_random_batches(names, exact):
+    rs = np.random.RandomState(11)
+    cs = d3random.random_collider_set(rs, 3000, names=names)
+    pairs = d3random.random_pairs(rs, len(cs), 40000)
+    compare_distance(cs, pairs, exact_types=EXACT if exact else None)
+
+
+def test_mixed_wide_and_small_hulls():
+    rs = np.random.RandomState(12)
+    cs = d3random.random_collider_set(rs, 600, names=("mesh", "box", "capsule"),
+                                      hull_vertices=(4, 120), center_scale=1.5)
+    pairs = d3random.random_pairs(rs, len(cs), 6000)
+    compare_distance(cs, pairs, exact_types=EXACT)
+
+
+def test_intersection_matches_oracle():
+    rs = np.random.RandomState(13)
+    cs = d3random.random_collider_set(rs, 3000, names=d3random.PRIMITIVES + ("mesh",))
+    pairs = d3random.random_pairs(rs, len(cs), 50000)
+    hit, iters, status = gjk.gjk_intersection_batch(cs, pairs, want_iters=True)
+    ref = O.gjk_intersection(cs, pairs, n_threads=O.max_threads())
+    dist = O.gjk_distance(cs, pairs, n_threads=O.max_threads())["dist"]
+    hit = hit.cpu().numpy()
+    assert np.array_equal(hit, ref["hit"])
+    assert np.array_equal(iters.cpu().numpy(), ref["iters"])
+    assert np.array_equal(status.cpu().numpy(), ref["status"])
+    assert np.array_equal(hit == 1, dist == 0.0)
+    assert 0.05 < hit.mean() < 0.6
+
+
+def test_edge_cases_empty_single_clipped_identical():
+    rs = np.random.RandomState(14)
+    cs = d3random.random_collider_set(rs, 50, names=d3random.PRIMITIVES)
+    res = gjk.gjk_distance_batch(cs, np.zeros((0, 2), dtype=np.int32)).cpu()
+    assert res["dist"].shape == (0,)
+    # a collider against itself intersects
+    pairs = np.stack([np.arange(50), np.arange(50)], axis=1).astype(np.int32)
+    res, ref = compare_distance(cs, pairs)
+    assert np.all(res["dist"] == 0.0)
+    # far apart -> clipped (MAX_FLOAT)
+    cs.pose[:25, :3, 3] += 1.0e4
+    cs.invalidate_device()
+    pairs = np.stack([np.arange(25), np.arange(25, 50)], axis=1).astype(np.int32)
+    res, ref = compare_distance(cs, pairs)
+    assert np.all(res["status"] == 3) and np.all(res["dist"] == np.finfo(float).max)
+
+
+def test_scalar_api_matches_reference_semantics():
+    from distance3d_b200 import colliders as C
+    s1 = C.Sphere(np.zeros(3), 1.0)
+    s2 = C.Sphere(np.array([0.0, 0.0, 3.0]), 1.0)
+    d, a, b, Y = gjk.gjk(s1, s2)
+    assert abs(d - 1.0) < 1e-9 and Y.shape == (4, 3)
+    assert gjk.gjk(s1, C.Sphere(np.array([0.0, 0.0, 1e3]), 1.0)) == (np.finfo(float).max, None, None, None)
+    assert gjk.gjk_intersection(s1, C.Sphere(np.array([0.0, 0.5, 0.0]), 1.0)) is True
+    assert gjk.gjk_intersection(s1, s2) is False
+    assert gjk.gjk_distance_jolt_iterations(s1, s2) >= 1
+    box = C.Box(np.eye(4), np.ones(3))
+    np.testing.assert_allclose(box.aabb(), [[-0.5, 0.5]] * 3)
+    np.testing.assert_allclose(box.support_function(np.array([1.0, 1.0, 1.0])), [0.5, 0.5, 0.5])

@@ -1,0 +1,106 @@
+"""CPU: the C oracle reproduces the REAL reference's outputs bit for bit.
+
+The fixtures in tests/golden/ were produced by oracle/gen_golden.py from the
+reference itself (AlexanderFabisch/distance3d v0.9.0, numba JIT on).  This pins
+the oracle; the GPU tests then compare the CUDA path with the oracle.
+"""
+import numpy as np
+
+from oracle import cpu_oracle as O
+from util import load_golden
+
+MAX_FLOAT = np.finfo(float).max
+
+
+def test_support_aabb_center_bit_exact():
+    cs, g = load_golden("support.npz")
+    O.prepare(cs)
+    for i in range(len(cs)):
+        for d, ref in zip(g["dirs"][i], g["support"][i]):
+            np.testing.assert_array_equal(O.support(cs, i, d), ref)
+        np.testing.assert_array_equal(O.center(cs, i), g["center"][i])
+    np.testing.assert_array_equal(O.aabb(cs), g["aabb"])
+
+
+def _check_gjk(cs, g):
+    res = O.gjk_distance(cs, g["pairs"])
+    ok = g["status"] != 4  # reference raised AssertionError (sanity check)
+    assert np.all(res["status"][~ok] >= 4)
+    clipped = g["status"] == 3
+    assert np.all(res["status"][clipped] == 3)
+    m = ok & ~clipped
+    np.testing.assert_array_equal(res["dist"][m], g["dist"][m])
+    np.testing.assert_array_equal(res["a"][m], g["a"][m])
+    np.testing.assert_array_equal(res["b"][m], g["b"][m])
+    np.testing.assert_array_equal(res["iters"][ok], g["iters"][ok])
+    for k in np.where(m)[0]:
+        n = res["n_points"][k]
+        np.testing.assert_array_equal(res["Y"][k, :n], g["Y"][k, :n])
+    hit = O.gjk_intersection(cs, g["pairs"])
+    np.testing.assert_array_equal(hit["hit"][ok], g["hit"][ok])
+    return res
+
+
+def test_gjk_all_collider_types_bit_exact():
+    cs, g = load_golden("gjk.npz")
+    res = _check_gjk(cs, g)
+    assert set(int(t) for t in np.unique(cs.type)) == set(range(10)) - {6}  # MeshGraph: test_meshgraph
+    assert 0.05 < np.mean(res["dist"] == 0.0) < 0.6
+
+
+def test_gjk_hulls_64_to_256_vertices_bit_exact():
+    cs, g = load_golden("hulls.npz")
+    _check_gjk(cs, g)
+    assert cs.vert_len.min() >= 64 and cs.vert_len.max() <= 256
+
+
+def test_epa_bit_exact_including_max_faces_assert():
+    cs, g = load_golden("epa.npz")
+    sel = np.where(g["status"] >= 0)[0]
+    res = O.epa(cs, g["pairs"][sel], g["Y"][sel], return_faces=True)
+    asserted = g["status"][sel] == 7
+    np.testing.assert_array_equal(res["status"] == 7, asserted)
+    m = ~asserted
+    np.testing.assert_array_equal(res["mtv"][m], g["mtv"][sel][m])
+    np.testing.assert_array_equal(res["success"][m], g["success"][sel][m])
+    np.testing.assert_array_equal(res["n_faces"][m], g["n_faces"][sel][m])
+    for q in np.where(m)[0]:
+        n = res["n_faces"][q]
+        np.testing.assert_array_equal(res["faces"][q, :n], g["faces"][sel[q], :n])
+    assert asserted.sum() > 0 and m.sum() > 50
+
+
+def test_epa_on_wide_hulls_bit_exact():
+    cs, g = load_golden("hulls.npz")
+    sel = np.where(g["epa_status"] >= 0)[0]
+    res = O.epa(cs, g["pairs"][sel], g["Y"][sel])
+    asserted = g["epa_status"][sel] == 7
+    np.testing.assert_array_equal(res["status"] == 7, asserted)
+    np.testing.assert_array_equal(res["mtv"][~asserted], g["epa_mtv"][sel][~asserted])
+
+
+def test_mpr_bit_exact():
+    cs, g = load_golden("mpr.npz")
+    res = O.mpr(cs, g["pairs"])
+    np.testing.assert_array_equal(res["hit"], g["hit"])
+    hit = g["hit"].astype(bool)
+    np.testing.assert_array_equal(res["depth"][hit], g["depth"][hit])
+    np.testing.assert_array_equal(res["dir"][hit], g["dir"][hit])
+    np.testing.assert_array_equal(res["pos"][hit], g["pos"][hit])
+    res_i = O.mpr(cs, g["pairs"], penetration=False)
+    np.testing.assert_array_equal(res_i["hit"], g["hit_intersection"])
+
+
+def test_broad_phase_tree_and_brute_force_identical_lists():
+    cs, g = load_golden("aabb.npz")
+    A = O.aabb(cs)
+    np.testing.assert_array_equal(A, g["aabb"])
+    tree = O.Tree()
+    tree.insert_aabbs(A)
+    np.testing.assert_array_equal(tree.nodes, g["tree_nodes"])
+    assert tree.root == int(g["tree_root"])
+    np.testing.assert_array_equal(tree.overlaps_aabb_tree(tree), g["tree_pairs"])
+    np.testing.assert_array_equal(O.all_aabbs_overlap(A[:300], A[300:700]), g["brute_pairs"])
+    # tree result == brute force as a set
+    brute = O.all_aabbs_overlap(A, A)
+    assert set(map(tuple, brute)) == set(map(tuple, g["tree_pairs"]))
