@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched GJK distance on random primitive pairs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[0] tiled, SURVEY.md section 8d "C1"): every pair
+owns two fresh random colliders drawn uniformly from {sphere, ellipsoid, capsule,
+cylinder, box} with the default scales of the reference's generators
+(benchmarks/benchmark_gjk.py:7-20, distance3d/random.py:200-362); PAIRS pairs per
+GPU (weak scaling: pairs are independent, every rank owns its shard, no
+data-path collective).  A step = one d3d_gjk_distance pass over the rank's shard.
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FLOP_PER_ITER = 350.0  # algorithmic flop per GJK iteration (primitives)
+BYTES_PER_PAIR = 496.0  # 336 B in + 160 B out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4 * 1024 * 1024, help="pairs per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=2 * 1024 * 1024,
+                    help="pairs timed on the host cores for cpu_baseline")
+    ap.add_argument("--seed", type=int, default=84)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(seed, n_pairs):
+    """2 * n_pairs random primitives; pair k = (2k, 2k + 1)."""
+    from distance3d_b200 import random as d3random
+    rs = np.random.RandomState(seed)
+    cs = d3random.random_collider_set(rs, 2 * n_pairs, names=d3random.PRIMITIVES)
+    pairs = np.arange(2 * n_pairs, dtype=np.int32).reshape(n_pairs, 2)
+    return cs, pairs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak(torch, _lib):
+    """Dependent-free FP64 FMA loop -> TFLOP/s (roofline denominator, measured live)."""
+    L = _lib.lib()
+    scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+    sm = ctypes.c_int(0)
+    L.d3d_device_info(ctypes.byref(sm), None, None)
+    blocks, iters = sm.value * 8, 1 << 15
+    s = _lib.stream_ptr()
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.d3d_fp64_peak_probe(_lib.ptr(scratch), ctypes.c_int(blocks), ctypes.c_int(iters), s)
+        e1.record()
+        torch.cuda.synchronize()
+        flop = blocks * 256 * 8.0 * iters * 2.0
+        best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def cpu_baseline(cs, pairs, sample):
+    """The C oracle (port of the reference algorithm) on all host threads, bounded sample."""
+    from oracle import cpu_oracle
+    n = min(sample, len(pairs))
+    threads = cpu_oracle.max_threads()
+    cpu_oracle.prepare(cs)
+    cpu_oracle.gjk_distance(cs, pairs[:min(n, 20000)], n_threads=threads)  # warm
+    t0 = time.perf_counter()
+    res = cpu_oracle.gjk_distance(cs, pairs[:n], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, threads, n, res
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU port on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    n = min(args.cpu_sample, args.pairs)
+    cs, pairs = make_workload(args.seed, n)
+    from oracle import cpu_oracle
+    threads = cpu_oracle.max_threads()
+    cpu_oracle.prepare(cs)
+    for _ in range(args.warmup):
+        cpu_oracle.gjk_distance(cs, pairs[:min(n, 50000)], n_threads=threads)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu_oracle.gjk_distance(cs, pairs, n_threads=threads)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = n / (ms * 1e-3)
+    sample = "%d of %d pairs per step, %d host threads" % (n, args.pairs, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "gjk_distance_pairs_per_s", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, pairs_per_gpu):
+    return {"workload": "C1 tiled: Jolt GJK distance + closest points, uniform mix of "
+                        "{sphere, ellipsoid, capsule, cylinder, box}, default generator scales, "
+                        "two fresh colliders per pair (benchmarks/benchmark_gjk.py shape)",
+            "pairs_per_gpu": pairs_per_gpu, "seed": args.seed,
+            "l2_policy": "inputs (%.0f MB per pass) larger than the 126 MB L2"
+                         % (pairs_per_gpu * BYTES_PER_PAIR / 1e6)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from distance3d_b200 import _lib, gjk
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic shard of this rank --------------------------------------
+    cs, pairs = make_workload(args.seed + 1000 * rank, args.pairs)
+    dc = cs.device(dev)
+    pairs_d = torch.from_numpy(pairs).to(dev)
+    n = len(pairs)
+    out = None
+
+    def step():
+        nonlocal out
+        out = gjk.gjk_distance_batch(dc, pairs_d, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # mean iterations (must equal the oracle's on the same inputs, checked below)
+    res = out.cpu()
+    mean_iters = float(res["iters"].mean())
+    hit_frac = float((res["dist"] == 0.0).mean())
+
+    # ---- end to end through the public API with HOST buffers ---------------
+    host = {k: torch.from_numpy(getattr(cs, k)).pin_memory()
+            for k in ("type", "pose", "param", "vert_off", "vert_len", "verts")}
+    host_pairs = torch.from_numpy(pairs).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_pairs.numel() * 4
+    host_out = {k: torch.empty_like(getattr(out, k), device="cpu").pin_memory()
+                for k in ("dist", "closest_a", "closest_b", "status")}
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    def e2e_step():
+        for k, v in host.items():
+            getattr(dc, k).copy_(v.reshape(getattr(dc, k).shape), non_blocking=True)
+        pairs_d.copy_(host_pairs, non_blocking=True)
+        _lib.prepare(dc)
+        r = gjk.gjk_distance_batch(dc, pairs_d, out=out)
+        for k, v in host_out.items():
+            v.copy_(getattr(r, k), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        fp64_peak = measure_fp64_peak(torch, _lib)
+        per_gpu = value / world
+        achieved = per_gpu * mean_iters * FLOP_PER_ITER / 1e12
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "gjk_distance_pairs_per_s", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n),
+            "mean_gjk_iterations": mean_iters, "intersecting_fraction": hit_frac,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                "kernel": "k_gjk_thread<0>",
+                "note": "algorithmic flop = pairs x mean_iters x 350 (SURVEY 8d); peak = FP64 FMA "
+                        "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "hbm_achieved_gbs": per_gpu * BYTES_PER_PAIR / 1e9,
+                "hbm_peak_gbs": hbm_peak,
+                "hbm_peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                "hbm_frac": per_gpu * BYTES_PER_PAIR / 1e9 / hbm_peak,
+            },
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": 5 * args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            cpu_value, threads, sample_n, ref = cpu_baseline(cs, pairs, args.cpu_sample)
+            line["cpu_baseline"] = {
+                "value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                "sample": "first %d of %d pairs of rank 0's shard, C oracle with OpenMP" % (sample_n, n)}
+            # the timed output must be the right answer: compare with the oracle sample
+            m = ref["status"] <= 1
+            line["parity_on_cpu_sample"] = {
+                "pairs": int(sample_n),
+                "bit_exact_dist": bool(np.array_equal(res["dist"][:sample_n], ref["dist"])),
+                "bit_exact_points": bool(np.array_equal(res["closest_a"][:sample_n][m], ref["a"][m])
+                                         and np.array_equal(res["closest_b"][:sample_n][m], ref["b"][m])),
+                "iters_equal": bool(np.array_equal(res["iters"][:sample_n], ref["iters"])),
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

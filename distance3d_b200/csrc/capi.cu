@@ -162,6 +162,19 @@ __global__ void k_aabb(d3d_colliders c, double *out) {
     o[2] = make_double2(lo[2], hi[2]);
 }
 
+// Dependent-free FP64 FMA loop: 8 independent accumulator chains per thread.
+__global__ void k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0,
+           a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void k_debug_norm(const double *v, int64_t n, double *out, int mode) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -214,6 +227,14 @@ int d3d_aabb(const d3d_colliders *c, double *out, void *stream) {
 int d3d_debug_norm(const double *v, int64_t n, double *out, int mode, void *stream) {
     if (n == 0) return 0;
     k_debug_norm<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, n, out, mode);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* FP64 roofline probe: launches `blocks` x 256 threads doing 8*iters FMAs each
+ * (2 flop per FMA); time it with CUDA events on `stream`. */
+int d3d_fp64_peak_probe(double *scratch, int blocks, int iters, void *stream) {
+    k_fp64_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, iters);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

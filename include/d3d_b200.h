@@ -28,6 +28,14 @@ const char *d3d_last_error_string(void);
 /* host: SM count and compute capability of the current device */
 int d3d_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Measurement / test hooks (no reference counterpart):
+ * d3d_fp64_peak_probe runs blocks x 256 threads x 8*iters dependent-free FP64 FMAs
+ * (roofline denominator for the narrow phase, timed by the caller with CUDA events);
+ * d3d_debug_norm evaluates the device emulation of the reference's np.linalg.norm
+ * (BLAS dnrm2 on the x87 FPU; mode 0 = production path, 1 = integer emulation only). */
+int d3d_fp64_peak_probe(double *scratch, int blocks, int iters, void *stream);
+int d3d_debug_norm(const double *v, int64_t n, double *out, int mode, void *stream);
+
 /* geometry.py:138-157 convert_box_to_vertices (called from colliders.py:161-176 on
  * construction and update_pose): writes the 8 world-frame vertices of every BOX of
  * `c` into verts_out[vert_off .. vert_off+8). */
