@@ -72,72 +72,72 @@ D3D_DEV v3 closest_line(v3 a, v3 b, int &set) {
     return a * u + b * v;
 }
 
-// _gjk_jolt.py:415-523.  Not force-inlined: it is instantiated for the
-// triangle case and inside the per-face loop of the tetrahedron case.
-static __device__ __noinline__ v3 closest_triangle(v3 a, v3 b, v3 c, int &set) {
+// Degenerate triangle (_gjk_jolt.py:450-472): best of the three edges.
+static __device__ __noinline__ v3 closest_triangle_degenerate(v3 a, v3 b, v3 c, int &set) {
+    int closest_set, new_set;
+    v3 closest_point = closest_line(a, b, closest_set);
+    double best_dist_sq = dot_blas(closest_point, closest_point);
+    v3 q = closest_line(a, c, new_set);
+    double dist_sq = dot_blas(q, q);
+    if (dist_sq < best_dist_sq) {
+        closest_point = q;
+        best_dist_sq = dist_sq;
+        closest_set = (new_set & 1) + ((new_set & 2) << 1);
+    }
+    q = closest_line(b, c, new_set);
+    dist_sq = dot_blas(q, q);
+    if (dist_sq < best_dist_sq) {
+        closest_point = q;
+        closest_set = new_set << 1;
+    }
+    set = closest_set;
+    return closest_point;
+}
+
+// _gjk_jolt.py:415-523.  The reference walks the Voronoi regions with early
+// returns; here every lane computes all region predicates (same expressions,
+// same order of evaluation of the tests) and only the short tails that build the
+// result diverge, so lanes of a warp that sit in different regions stay together.
+D3D_DEV v3 closest_triangle(v3 a, v3 b, v3 c, int &set) {
     v3 ab = b - a, ac = c - a, bc = c - b;
     bool bc_shorter_than_ac = dot_blas(bc, bc) < dot_blas(ac, ac);
-    v3 n = bc_shorter_than_ac ? cross(ab, bc) : cross(ab, ac);
+    v3 second = bc_shorter_than_ac ? bc : ac;
+    v3 n = cross(ab, second);
     double n_len_sq = dot_blas(n, n);
+    if (n_len_sq < D3D_EPS_SQR) return closest_triangle_degenerate(a, b, c, set);
 
-    if (n_len_sq < D3D_EPS_SQR) {  // degenerate: best of the three edges
-        int closest_set, new_set;
-        v3 closest_point = closest_line(a, b, closest_set);
-        double best_dist_sq = dot_blas(closest_point, closest_point);
-        v3 q = closest_line(a, c, new_set);
-        double dist_sq = dot_blas(q, q);
-        if (dist_sq < best_dist_sq) {
-            closest_point = q;
-            best_dist_sq = dist_sq;
-            closest_set = (new_set & 1) + ((new_set & 2) << 1);
-        }
-        q = closest_line(b, c, new_set);
-        dist_sq = dot_blas(q, q);
-        if (dist_sq < best_dist_sq) {
-            closest_point = q;
-            closest_set = new_set << 1;
-        }
-        set = closest_set;
-        return closest_point;
-    }
-
-    v3 ap = -a;
-    double d1 = dot_blas(ab, ap), d2 = dot_blas(ac, ap);
-    if (d1 <= 0.0 && d2 <= 0.0) { set = 1; return a; }
-
-    v3 bp = -b;
-    double d3 = dot_blas(ab, bp), d4 = dot_blas(ac, bp);
-    if (d3 >= 0.0 && d4 <= d3) { set = 2; return b; }
-
+    double d1 = dot_blas(ab, -a), d2 = dot_blas(ac, -a);
+    double d3 = dot_blas(ab, -b), d4 = dot_blas(ac, -b);
+    double d5 = dot_blas(ab, -c), d6 = dot_blas(ac, -c);
     double vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.0 && 0.0 <= d1 && d3 <= 0.0) {
-        double v = d1 / (d1 - d3);
-        set = 3;
-        return a + ab * v;
-    }
-
-    v3 cp = -c;
-    double d5 = dot_blas(ab, cp), d6 = dot_blas(ac, cp);
-    if (d6 >= 0.0 && d5 <= d6) { set = 4; return c; }
-
     double vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.0 && 0.0 <= d2 && d6 <= 0.0) {
-        double w = d2 / (d2 - d6);
-        set = 5;
-        return a + ac * w;
-    }
-
     double va = d3 * d6 - d5 * d4;
     double d4_d3 = d4 - d3, d5_d6 = d5 - d6;
-    if (va <= 0.0 && 0.0 <= d4_d3 && d5_d6 >= 0.0) {
-        double w = d4_d3 / (d4_d3 + d5_d6);
-        set = 6;
-        return b + bc * w;
-    }
 
-    set = 7;
-    double s = dot_blas((a + b) + c, n);
-    return (n * s) / (3.0 * n_len_sq);
+    int region;
+    if (d1 <= 0.0 && d2 <= 0.0) region = 1;
+    else if (d3 >= 0.0 && d4 <= d3) region = 2;
+    else if (vc <= 0.0 && 0.0 <= d1 && d3 <= 0.0) region = 3;
+    else if (d6 >= 0.0 && d5 <= d6) region = 4;
+    else if (vb <= 0.0 && 0.0 <= d2 && d6 <= 0.0) region = 5;
+    else if (va <= 0.0 && 0.0 <= d4_d3 && d5_d6 >= 0.0) region = 6;
+    else region = 7;
+    set = region;
+
+    if (region == 7) {
+        double s = dot_blas((a + b) + c, n);
+        return (n * s) / (3.0 * n_len_sq);
+    }
+    if (region == 3 || region == 5 || region == 6) {
+        // a + v*ab | a + w*ac | b + w*bc
+        v3 base = (region == 6) ? b : a;
+        v3 dir = (region == 3) ? ab : ((region == 5) ? ac : bc);
+        double num = (region == 3) ? d1 : ((region == 5) ? d2 : d4_d3);
+        double den = (region == 3) ? (d1 - d3) : ((region == 5) ? (d2 - d6) : (d4_d3 + d5_d6));
+        double t = num / den;
+        return base + dir * t;
+    }
+    return (region == 1) ? a : ((region == 2) ? b : c);
 }
 
 // _gjk_jolt.py:526-570: bit i set = origin outside plane i
@@ -158,45 +158,48 @@ D3D_DEV int origin_outside_planes(v3 a, v3 b, v3 c, v3 d) {
     return 0xf;
 }
 
-// _gjk_jolt.py:573-631
-D3D_DEV v3 closest_tetrahedron(v3 a, v3 b, v3 c, v3 d, int &set) {
-    int closest_set = 0xf;
-    v3 closest_point = V3(0.0, 0.0, 0.0);
-    double best_dist_sq = D3D_MAX_FLOAT;
-    int out = origin_outside_planes(a, b, c, d);
-#pragma unroll 1
-    for (int f = 0; f < 4; ++f) {
-        if (!(out & (1 << f))) continue;
-        // faces: abc, acd, adb, bdc
-        v3 fa = (f == 3) ? b : a;
-        v3 fb = (f == 0) ? b : ((f == 1) ? c : d);
-        v3 fc = (f == 0) ? c : ((f == 1) ? d : ((f == 2) ? b : c));
-        int s;
-        v3 q = closest_triangle(fa, fb, fc, s);
-        double dist_sq = dot_blas(q, q);
-        if (f == 0 || dist_sq < best_dist_sq) {
-            best_dist_sq = dist_sq;
-            closest_point = q;
-            if (f == 0) closest_set = s;
-            else if (f == 1) closest_set = (s & 1) + ((s & 6) << 1);
-            else if (f == 2) closest_set = (s & 1) + ((s & 2) << 2) + ((s & 4) >> 1);
-            else closest_set = ((s & 1) << 1) + ((s & 2) << 2) + (s & 4);
-        }
-    }
-    set = closest_set;
-    return closest_point;
-}
-
-// _gjk_jolt.py:690-711
+// _gjk_jolt.py:690-711 with closest_point_tetrahedron (:573-631) folded in.
+//
+// Triangle (3 points) and tetrahedron (4 points) lanes share ONE instance of
+// closest_triangle: a 3-point simplex is treated as a tetrahedron whose only
+// candidate face is (y0, y1, y2).  Each lane walks its own candidate faces in
+// ascending order (the order matters for the strict '<' tie-break), the loop
+// trip count is the number of candidate faces, not 4.
 D3D_DEV bool closest_point_to_origin(v3 y0, v3 y1, v3 y2, v3 y3, int n_points,
                                      double prev_v_len_sq, v3 &v_out, double &v_len_sq_out,
                                      int &set_out) {
-    v3 v;
-    int set;
-    if (n_points == 1) { set = 1; v = y0; }
-    else if (n_points == 2) v = closest_line(y0, y1, set);
-    else if (n_points == 3) v = closest_triangle(y0, y1, y2, set);
-    else v = closest_tetrahedron(y0, y1, y2, y3, set);
+    v3 v = y0;
+    int set = 1;
+    if (n_points == 2) {
+        v = closest_line(y0, y1, set);
+    } else if (n_points >= 3) {
+        int out = 1;
+        if (n_points == 4) out = origin_outside_planes(y0, y1, y2, y3);
+        set = 0xf;
+        v = V3(0.0, 0.0, 0.0);
+        double best_dist_sq = D3D_MAX_FLOAT;
+        int todo = out;
+#pragma unroll 1
+        while (todo) {
+            int f = __ffs(todo) - 1;
+            todo &= todo - 1;
+            // faces: abc, acd, adb, bdc
+            v3 fa = (f == 3) ? y1 : y0;
+            v3 fb = (f == 0) ? y1 : ((f == 1) ? y2 : y3);
+            v3 fc = (f == 0) ? y2 : ((f == 1) ? y3 : ((f == 2) ? y1 : y2));
+            int s;
+            v3 q = closest_triangle(fa, fb, fc, s);
+            double dist_sq = dot_blas(q, q);
+            if (f == 0 || dist_sq < best_dist_sq) {
+                best_dist_sq = dist_sq;
+                v = q;
+                if (f == 0) set = s;
+                else if (f == 1) set = (s & 1) + ((s & 6) << 1);
+                else if (f == 2) set = (s & 1) + ((s & 2) << 2) + ((s & 4) >> 1);
+                else set = ((s & 1) << 1) + ((s & 2) << 2) + (s & 4);
+            }
+        }
+    }
     double v_len_sq = dot_blas(v, v);
     if (v_len_sq < prev_v_len_sq) {
         v_out = v; v_len_sq_out = v_len_sq; set_out = set;

@@ -9,15 +9,60 @@
 #include "../../include/d3d_types.h"
 #include "d3d_math.cuh"
 
+// Register-resident collider record.  All support / centre code below is written
+// against the accessor interface (r00() .. tz(), p0() .. p2(), margin(), type, nv, V)
+// so the same code also runs on a record staged in shared memory (ColliderSmem).
 struct Collider {
     int type;
     int nv;
     const double *V;  // vertex range in the pool (box / hull: world frame, mesh: local)
-    double margin;
-    double r00, r01, r02, tx;
-    double r10, r11, r12, ty;
-    double r20, r21, r22, tz;
-    double p0, p1, p2;
+    double m_margin;
+    double m[15];     // r00 r01 r02 tx  r10 r11 r12 ty  r20 r21 r22 tz  p0 p1 p2
+    D3D_DEV double r00() const { return m[0]; }
+    D3D_DEV double r01() const { return m[1]; }
+    D3D_DEV double r02() const { return m[2]; }
+    D3D_DEV double tx() const { return m[3]; }
+    D3D_DEV double r10() const { return m[4]; }
+    D3D_DEV double r11() const { return m[5]; }
+    D3D_DEV double r12() const { return m[6]; }
+    D3D_DEV double ty() const { return m[7]; }
+    D3D_DEV double r20() const { return m[8]; }
+    D3D_DEV double r21() const { return m[9]; }
+    D3D_DEV double r22() const { return m[10]; }
+    D3D_DEV double tz() const { return m[11]; }
+    D3D_DEV double p0() const { return m[12]; }
+    D3D_DEV double p1() const { return m[13]; }
+    D3D_DEV double p2() const { return m[14]; }
+    D3D_DEV double margin() const { return m_margin; }
+};
+
+// The same record staged in shared memory: field f of the owning thread lives at
+// base[f * STRIDE] (STRIDE = threads per block: consecutive threads hit consecutive
+// 8-byte words, conflict free; STRIDE = 1 for a warp-private record).
+#define D3D_COLLIDER_FIELDS 16
+template <int STRIDE>
+struct ColliderSmem {
+    int type;
+    int nv;
+    const double *V;
+    const double *base;
+    D3D_DEV double f(int i) const { return base[i * STRIDE]; }
+    D3D_DEV double r00() const { return f(0); }
+    D3D_DEV double r01() const { return f(1); }
+    D3D_DEV double r02() const { return f(2); }
+    D3D_DEV double tx() const { return f(3); }
+    D3D_DEV double r10() const { return f(4); }
+    D3D_DEV double r11() const { return f(5); }
+    D3D_DEV double r12() const { return f(6); }
+    D3D_DEV double ty() const { return f(7); }
+    D3D_DEV double r20() const { return f(8); }
+    D3D_DEV double r21() const { return f(9); }
+    D3D_DEV double r22() const { return f(10); }
+    D3D_DEV double tz() const { return f(11); }
+    D3D_DEV double p0() const { return f(12); }
+    D3D_DEV double p1() const { return f(13); }
+    D3D_DEV double p2() const { return f(14); }
+    D3D_DEV double margin() const { return f(15); }
 };
 
 // 128-bit vectorised loads of the 4x4 pose (rows 0..2) and the parameters.
@@ -26,35 +71,62 @@ D3D_DEV Collider load_collider(const d3d_colliders &c, int64_t i) {
     o.type = __ldg(c.type + i);
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
-    o.margin = c.margin ? __ldg(c.margin + i) : 0.0;
+    o.m_margin = c.margin ? __ldg(c.margin + i) : 0.0;
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
-    double2 a = __ldg(T + 0), b = __ldg(T + 1), d = __ldg(T + 2), e = __ldg(T + 3),
-            f = __ldg(T + 4), g = __ldg(T + 5);
-    o.r00 = a.x; o.r01 = a.y; o.r02 = b.x; o.tx = b.y;
-    o.r10 = d.x; o.r11 = d.y; o.r12 = e.x; o.ty = e.y;
-    o.r20 = f.x; o.r21 = f.y; o.r22 = g.x; o.tz = g.y;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double2 a = __ldg(T + k);
+        o.m[2 * k] = a.x;
+        o.m[2 * k + 1] = a.y;
+    }
     const double *p = c.param + 3 * i;
-    o.p0 = __ldg(p); o.p1 = __ldg(p + 1); o.p2 = __ldg(p + 2);
+    o.m[12] = __ldg(p); o.m[13] = __ldg(p + 1); o.m[14] = __ldg(p + 2);
+    return o;
+}
+
+// Stage collider i into the calling thread's shared-memory record.
+template <int STRIDE>
+D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, double *base) {
+    ColliderSmem<STRIDE> o;
+    o.type = __ldg(c.type + i);
+    o.nv = __ldg(c.vert_len + i);
+    o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
+    o.base = base;
+    const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double2 a = __ldg(T + k);
+        base[(2 * k) * STRIDE] = a.x;
+        base[(2 * k + 1) * STRIDE] = a.y;
+    }
+    const double *p = c.param + 3 * i;
+    base[12 * STRIDE] = __ldg(p);
+    base[13 * STRIDE] = __ldg(p + 1);
+    base[14 * STRIDE] = __ldg(p + 2);
+    base[15 * STRIDE] = c.margin ? __ldg(c.margin + i) : 0.0;
     return o;
 }
 
 // np.dot(pose[:3,:3].T, d)  (dgemv convention)
-D3D_DEV v3 rot_t(const Collider &c, v3 d) {
-    return V3(gemv_row(c.r00, c.r10, c.r20, d), gemv_row(c.r01, c.r11, c.r21, d),
-              gemv_row(c.r02, c.r12, c.r22, d));
+template <class C>
+D3D_DEV v3 rot_t(const C &c, v3 d) {
+    return V3(gemv_row(c.r00(), c.r10(), c.r20(), d), gemv_row(c.r01(), c.r11(), c.r21(), d),
+              gemv_row(c.r02(), c.r12(), c.r22(), d));
 }
 // utils.py:143 transform_point
-D3D_DEV v3 xform(const Collider &c, v3 v) {
-    return V3(c.tx + gemv_row(c.r00, c.r01, c.r02, v), c.ty + gemv_row(c.r10, c.r11, c.r12, v),
-              c.tz + gemv_row(c.r20, c.r21, c.r22, v));
+template <class C>
+D3D_DEV v3 xform(const C &c, v3 v) {
+    return V3(c.tx() + gemv_row(c.r00(), c.r01(), c.r02(), v), c.ty() + gemv_row(c.r10(), c.r11(), c.r12(), v),
+              c.tz() + gemv_row(c.r20(), c.r21(), c.r22(), v));
 }
 
 // geometry.py:138-157: vertex i of a box, bit k of i selects +0.5 on axis (2-k)
-D3D_DEV v3 box_vertex(const Collider &c, int i) {
-    v3 l = V3((i & 4) ? 0.5 * c.p0 : -0.5 * c.p0, (i & 2) ? 0.5 * c.p1 : -0.5 * c.p1,
-              (i & 1) ? 0.5 * c.p2 : -0.5 * c.p2);
-    return V3(c.tx + dot_blas(l, V3(c.r00, c.r01, c.r02)), c.ty + dot_blas(l, V3(c.r10, c.r11, c.r12)),
-              c.tz + dot_blas(l, V3(c.r20, c.r21, c.r22)));
+template <class C>
+D3D_DEV v3 box_vertex(const C &c, int i) {
+    v3 l = V3((i & 4) ? 0.5 * c.p0() : -0.5 * c.p0(), (i & 2) ? 0.5 * c.p1() : -0.5 * c.p1(),
+              (i & 1) ? 0.5 * c.p2() : -0.5 * c.p2());
+    return V3(c.tx() + dot_blas(l, V3(c.r00(), c.r01(), c.r02())), c.ty() + dot_blas(l, V3(c.r10(), c.r11(), c.r12())),
+              c.tz() + dot_blas(l, V3(c.r20(), c.r21(), c.r22())));
 }
 
 // First arg-max of V.dot(d) (colliders.py:132).  G lanes of a warp cooperate:
@@ -104,36 +176,36 @@ D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
     }
 }
 
-template <int G>
-D3D_DEV v3 support_unmargined(const Collider &c, v3 d, int lane) {
+template <int G, class C>
+D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     switch (c.type) {
     case D3D_SPHERE: {  // geometry.py:341-346
         double s = norm3(d);
-        v3 ctr = V3(c.tx, c.ty, c.tz);
-        if (s == 0.0) return ctr + V3(0.0, 0.0, c.p0);
-        return ctr + (d / s) * c.p0;
+        v3 ctr = V3(c.tx(), c.ty(), c.tz());
+        if (s == 0.0) return ctr + V3(0.0, 0.0, c.p0());
+        return ctr + (d / s) * c.p0();
     }
     case D3D_CAPSULE: {  // geometry.py:243-256
         v3 l = rot_t(c, d);
         double s = sqrt(l.x * l.x + l.y * l.y + l.z * l.z);
         v3 v;
-        if (s == 0.0) v = V3(c.p0, 0.0, 0.0);
-        else v = l * (c.p0 / s);
-        if (l.z > 0.0) v.z += 0.5 * c.p1;
-        else v.z -= 0.5 * c.p1;
+        if (s == 0.0) v = V3(c.p0(), 0.0, 0.0);
+        else v = l * (c.p0() / s);
+        if (l.z > 0.0) v.z += 0.5 * c.p1();
+        else v.z -= 0.5 * c.p1();
         return xform(c, v);
     }
     case D3D_CYLINDER: {  // geometry.py:194-206
         v3 l = rot_t(c, d);
         double s = sqrt(l.x * l.x + l.y * l.y);
-        double z = (l.z < 0.0) ? -0.5 * c.p1 : 0.5 * c.p1;
+        double z = (l.z < 0.0) ? -0.5 * c.p1() : 0.5 * c.p1();
         v3 v;
-        if (s == 0.0) v = V3(c.p0, 0.0, z);
-        else { double k = c.p0 / s; v = V3(l.x * k, l.y * k, z); }
+        if (s == 0.0) v = V3(c.p0(), 0.0, z);
+        else { double k = c.p0() / s; v = V3(l.x * k, l.y * k, z); }
         return xform(c, v);
     }
     case D3D_ELLIPSOID: {  // geometry.py:282-284
-        v3 r = V3(c.p0, c.p1, c.p2);
+        v3 r = V3(c.p0(), c.p1(), c.p2());
         v3 l = rot_t(c, d);
         return xform(c, vmul(normalized(vmul(l, r)), r));
     }
@@ -158,50 +230,51 @@ D3D_DEV v3 support_unmargined(const Collider &c, v3 d, int lane) {
         return xform(c, ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, l, lane)));
     }
     case D3D_DISK: {  // geometry.py:375-383
-        v3 ctr = V3(c.tx, c.ty, c.tz);
-        v3 n = V3(c.r02, c.r12, c.r22);
+        v3 ctr = V3(c.tx(), c.ty(), c.tz());
+        v3 n = V3(c.r02(), c.r12(), c.r22());
         v3 x, y;
         plane_basis(n, x, y);
         v3 pt = V3(dot_blas(x, d), dot_blas(y, d), 0.0);
         double nrm = norm3(pt);
         if (nrm == 0.0) return ctr;
-        pt = pt * (c.p0 / nrm);
+        pt = pt * (c.p0() / nrm);
         return V3(ctr.x + gemv_row(x.x, y.x, n.x, pt), ctr.y + gemv_row(x.y, y.y, n.y, pt),
                   ctr.z + gemv_row(x.z, y.z, n.z, pt));
     }
     case D3D_ELLIPSE: {  // geometry.py:412-414
-        v3 a0 = V3(c.r00, c.r10, c.r20), a1 = V3(c.r01, c.r11, c.r21);
+        v3 a0 = V3(c.r00(), c.r10(), c.r20()), a1 = V3(c.r01(), c.r11(), c.r21());
         double l0 = gemv_row(a0.x, a0.y, a0.z, d), l1 = gemv_row(a1.x, a1.y, a1.z, d);
-        double w0 = c.p0 * l0, w1 = c.p1 * l1;
+        double w0 = c.p0() * l0, w1 = c.p1() * l1;
         double nrm = norm_dd(w0, w1, 0.0);
         if (nrm != 0.0) { w0 = w0 / nrm; w1 = w1 / nrm; }
-        w0 *= c.p0; w1 *= c.p1;
-        return V3(c.tx + fma(w1, a1.x, w0 * a0.x), c.ty + fma(w1, a1.y, w0 * a0.y),
-                  c.tz + fma(w1, a1.z, w0 * a0.z));
+        w0 *= c.p0(); w1 *= c.p1();
+        return V3(c.tx() + fma(w1, a1.x, w0 * a0.x), c.ty() + fma(w1, a1.y, w0 * a0.y),
+                  c.tz() + fma(w1, a1.z, w0 * a0.z));
     }
     case D3D_CONE: {  // geometry.py:443-454
         v3 l = rot_t(c, d);
         v3 dp = V3(l.x, l.y, 0.0);
         double nrm = norm3(dp);
         if (nrm == 0.0) dp = V3(0.0, 0.0, 0.0);
-        else dp = dp * (c.p0 / nrm);
-        v3 pt = (dot_blas(l, dp) >= l.z * c.p1) ? dp : V3(0.0, 0.0, c.p1);
+        else dp = dp * (c.p0() / nrm);
+        v3 pt = (dot_blas(l, dp) >= l.z * c.p1()) ? dp : V3(0.0, 0.0, c.p1());
         return xform(c, pt);
     }
     }
     return V3(0.0, 0.0, 0.0);
 }
 
-template <int G>
-D3D_DEV v3 support(const Collider &c, v3 d, int lane) {
+template <int G, class C>
+D3D_DEV v3 support(const C &c, v3 d, int lane) {
     v3 s = support_unmargined<G>(c, d, lane);
-    if (c.margin != 0.0) s = s + normalized(d) * c.margin;  // colliders.py:629-631
+    if (c.margin() != 0.0) s = s + normalized(d) * c.margin();  // colliders.py:629-631
     return s;
 }
 
 // colliders.py center(); hull / mesh means are sequential column sums (np.mean axis 0)
-D3D_DEV v3 center_of(const Collider &c) {
-    v3 t = V3(c.tx, c.ty, c.tz);
+template <class C>
+D3D_DEV v3 center_of(const C &c) {
+    v3 t = V3(c.tx(), c.ty(), c.tz());
     if (c.type == D3D_HULL || c.type == D3D_MESH) {
         v3 s = V3(0.0, 0.0, 0.0);
         for (int k = 0; k < c.nv; ++k) s = s + ld3(c.V + 3 * k);
@@ -209,6 +282,6 @@ D3D_DEV v3 center_of(const Collider &c) {
         return c.type == D3D_HULL ? s : xform(c, s);
     }
     if (c.type == D3D_CONE)
-        return V3(t.x + 0.5 * c.p1 * c.r02, t.y + 0.5 * c.p1 * c.r12, t.z + 0.5 * c.p1 * c.r22);
+        return V3(t.x + 0.5 * c.p1() * c.r02(), t.y + 0.5 * c.p1() * c.r12(), t.z + 0.5 * c.p1() * c.r22());
     return t;
 }

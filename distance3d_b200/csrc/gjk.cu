@@ -109,14 +109,26 @@ __global__ void k_bin_scatter(int64_t n, GjkWorkspace w) {
 }
 
 // ---------------------------------------------------------------------------
-// Simplex storage: element (array a, slot s, component c) lives at
-// base[((a * 4 + s) * 3 + c) * stride].  a: 0 = Y (A - B), 1 = P (on A), 2 = Q (on B).
+// Per-pair state in shared memory.  Field f of the owning thread (thread kernel:
+// STRIDE = block size) or of the owning warp (warp kernel: STRIDE = 1) lives at
+// base[f * STRIDE]:
+//   [ 0,16)  collider A record (d3d_support.cuh ColliderSmem)
+//   [16,32)  collider B record
+//   [32,44)  Y  simplex points of A - B   (slot s, component c at 32 + 3 s + c)
+//   [44,56)  P  support points on A
+//   [56,68)  Q  support points on B
+#define GJK_FIELDS 68
+#define GJK_OFF_B 16
+#define GJK_OFF_Y 32
+#define GJK_OFF_P 44
+#define GJK_OFF_Q 56
+
+template <int STRIDE>
 struct Simplex {
     double *base;
-    int stride;
-    D3D_DEV double &at(int a, int s, int c) const { return base[((a * 4 + s) * 3 + c) * stride]; }
-    D3D_DEV v3 get(int a, int s) const { return V3(at(a, s, 0), at(a, s, 1), at(a, s, 2)); }
-    D3D_DEV void set(int a, int s, v3 v) const { at(a, s, 0) = v.x; at(a, s, 1) = v.y; at(a, s, 2) = v.z; }
+    D3D_DEV double &at(int off, int s, int c) const { return base[(off + 3 * s + c) * STRIDE]; }
+    D3D_DEV v3 get(int off, int s) const { return V3(at(off, s, 0), at(off, s, 1), at(off, s, 2)); }
+    D3D_DEV void set(int off, int s, v3 v) const { at(off, s, 0) = v.x; at(off, s, 1) = v.y; at(off, s, 2) = v.z; }
 };
 
 struct GjkParams {
@@ -133,18 +145,20 @@ struct GjkParams {
     uint8_t *out_hit;
 };
 
+template <int STRIDE>
 struct PairState {
-    Collider A, B;
+    ColliderSmem<STRIDE> A, B;
     v3 sd;
     double v_len_sq, prev_v_len_sq;
     int n_points, iters, k, state;
 };
 
-template <int G>
-D3D_DEV void init_pair(PairState &s, const d3d_colliders &c, const int32_t *pairs, int k) {
+template <int STRIDE>
+D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32_t *pairs, int k,
+                       double *base) {
     int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
-    s.A = load_collider(c, pr.x);
-    s.B = load_collider(c, pr.y);
+    s.A = stage_collider<STRIDE>(c, pr.x, base);
+    s.B = stage_collider<STRIDE>(c, pr.y, base + GJK_OFF_B * STRIDE);
     s.sd = V3(1.0, 0.0, 0.0);
     s.v_len_sq = 1.0;  // np.dot(sd, sd), _gjk_jolt.py:197
     s.prev_v_len_sq = D3D_MAX_FLOAT;
@@ -154,10 +168,20 @@ D3D_DEV void init_pair(PairState &s, const d3d_colliders &c, const int32_t *pair
     s.state = D3D_UNKNOWN;
 }
 
+// One shared copy of the ten-way support switch per kernel: both colliders of a pair
+// go through it (two calls), and because pairs are processed in (typeA, typeB) order
+// the switch is warp-uniform almost always.
+template <int G, int STRIDE>
+static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const double *base,
+                                               double dx, double dy, double dz, int lane) {
+    ColliderSmem<STRIDE> c;
+    c.type = type; c.nv = nv; c.V = V; c.base = base;
+    return support<G>(c, V3(dx, dy, dz), lane);
+}
+
 // max(|Y_i|^2) over the slots selected by mask (_gjk_jolt.py:634-640)
 D3D_DEV double max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
-    double m = dot_blas(y0, y0);  // slot 0 is always part of a non-empty prefix mask
-    if (!(mask & 1)) m = -1.0;
+    double m = (mask & 1) ? dot_blas(y0, y0) : -1.0;
     if (mask & 2) m = fmax(m, dot_blas(y1, y1));
     if (mask & 4) m = fmax(m, dot_blas(y2, y2));
     if (mask & 8) m = fmax(m, dot_blas(y3, y3));
@@ -166,12 +190,12 @@ D3D_DEV double max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
 
 // One iteration of _distance_loop (MODE 0, _gjk_jolt.py:224-288) or
 // _intersection_loop (MODE 1, _gjk_jolt.py:83-135).
-template <int MODE, int G>
-D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int lane) {
+template <int MODE, int G, int STRIDE>
+D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return; }
     ++s.iters;
-    v3 p = support<G>(s.A, s.sd, lane);
-    v3 q = support<G>(s.B, -s.sd, lane);
+    v3 p = support_call<G, STRIDE>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
+    v3 q = support_call<G, STRIDE>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
     v3 w = p - q;
     double dot = dot_blas(s.sd, w);
     if (MODE == 0) {
@@ -182,11 +206,12 @@ D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int 
     } else {
         if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return; }
     }
-    S.set(0, s.n_points, w);
-    if (MODE == 0) { S.set(1, s.n_points, p); S.set(2, s.n_points, q); }
+    S.set(GJK_OFF_Y, s.n_points, w);
+    if (MODE == 0) { S.set(GJK_OFF_P, s.n_points, p); S.set(GJK_OFF_Q, s.n_points, q); }
     ++s.n_points;
 
-    v3 y0 = S.get(0, 0), y1 = S.get(0, 1), y2 = S.get(0, 2), y3 = S.get(0, 3);
+    v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
+       y3 = S.get(GJK_OFF_Y, 3);
     v3 v_new;
     double v_len_sq_new;
     int simplex;
@@ -217,7 +242,11 @@ D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int 
         int nn = 0;
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
-                if (nn != i) { S.set(0, nn, S.get(0, i)); S.set(1, nn, S.get(1, i)); S.set(2, nn, S.get(2, i)); }
+                if (nn != i) {
+                    S.set(GJK_OFF_Y, nn, S.get(GJK_OFF_Y, i));
+                    S.set(GJK_OFF_P, nn, S.get(GJK_OFF_P, i));
+                    S.set(GJK_OFF_Q, nn, S.get(GJK_OFF_Q, i));
+                }
                 ++nn;
             }
         s.n_points = nn;
@@ -240,7 +269,7 @@ D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int 
         int nn = 0;
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
-                if (nn != i) S.set(0, nn, S.get(0, i));
+                if (nn != i) S.set(GJK_OFF_Y, nn, S.get(GJK_OFF_Y, i));
                 ++nn;
             }
         s.n_points = nn;
@@ -248,8 +277,9 @@ D3D_DEV void gjk_step(PairState &s, const Simplex &S, const GjkParams &prm, int 
 }
 
 // Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).
-template <int MODE>
-D3D_DEV void gjk_finish(const PairState &s, const Simplex &S, const GjkParams &prm, bool writer) {
+template <int MODE, int STRIDE>
+D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm,
+                        bool writer) {
     int64_t k = s.k;
     int state = s.state;
     if (MODE == 1) {
@@ -264,23 +294,22 @@ D3D_DEV void gjk_finish(const PairState &s, const Simplex &S, const GjkParams &p
     double dist = D3D_MAX_FLOAT;
     if (state == D3D_NO_INTERSECTION || state == D3D_INTERSECTION) {
         int n = s.n_points;
-        if (n == 1) { a = S.get(1, 0); b = S.get(2, 0); }
-        else if (n == 2) {
-            double u, v;
-            bary_line(S.get(0, 0), S.get(0, 1), u, v);
-            a = S.get(1, 0) * u + S.get(1, 1) * v;
-            b = S.get(2, 0) * u + S.get(2, 1) * v;
-        } else if (n == 3) {
-            double u, v, w;
-            bary_plane(S.get(0, 0), S.get(0, 1), S.get(0, 2), u, v, w);
-            a = (S.get(1, 0) * u + S.get(1, 1) * v) + S.get(1, 2) * w;
-            b = (S.get(2, 0) * u + S.get(2, 1) * v) + S.get(2, 2) * w;
-        } else if (n == 4) {
-            double u, v, w, x;
-            bary_tetra(S.get(0, 0), S.get(0, 1), S.get(0, 2), S.get(0, 3), u, v, w, x);
-            a = ((S.get(1, 0) * u + S.get(1, 1) * v) + S.get(1, 2) * w) + S.get(1, 3) * x;
-            b = ((S.get(2, 0) * u + S.get(2, 1) * v) + S.get(2, 2) * w) + S.get(2, 3) * x;
+        // barycentric weights of the closest point (zero weight for unused slots)
+        double u = 1.0, v = 0.0, w = 0.0, x = 0.0;
+        v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
+           y3 = S.get(GJK_OFF_Y, 3);
+        if (n == 2) bary_line(y0, y1, u, v);
+        else if (n == 3) bary_plane(y0, y1, y2, u, v, w);
+        else if (n == 4) bary_tetra(y0, y1, y2, y3, u, v, w, x);
+        // u*P0 + v*P1 + w*P2 + x*P3, left to right, only over the valid slots
+        a = S.get(GJK_OFF_P, 0);
+        b = S.get(GJK_OFF_Q, 0);
+        if (n >= 2) {
+            a = a * u + S.get(GJK_OFF_P, 1) * v;
+            b = b * u + S.get(GJK_OFF_Q, 1) * v;
         }
+        if (n >= 3) { a = a + S.get(GJK_OFF_P, 2) * w; b = b + S.get(GJK_OFF_Q, 2) * w; }
+        if (n >= 4) { a = a + S.get(GJK_OFF_P, 3) * x; b = b + S.get(GJK_OFF_Q, 3) * x; }
         double check_value = fabs(dot_blas(s.sd, s.sd) - s.v_len_sq);
         if (!(check_value < prm.sanity_check)) state = D3D_SANITY_FAILED;
         dist = sqrt(s.v_len_sq);
@@ -291,7 +320,8 @@ D3D_DEV void gjk_finish(const PairState &s, const Simplex &S, const GjkParams &p
     if (prm.out_a) st3(prm.out_a + 3 * k, a);
     if (prm.out_b) st3(prm.out_b + 3 * k, b);
     if (prm.out_Y) {
-        for (int i = 0; i < 4; ++i) st3(prm.out_Y + 12 * k + 3 * i, i < s.n_points ? S.get(0, i) : V3(0.0, 0.0, 0.0));
+        for (int i = 0; i < 4; ++i)
+            st3(prm.out_Y + 12 * k + 3 * i, i < s.n_points ? S.get(GJK_OFF_Y, i) : V3(0.0, 0.0, 0.0));
     }
     if (prm.out_npoints) prm.out_npoints[k] = s.n_points;
     if (prm.out_iters) prm.out_iters[k] = s.iters;
@@ -307,15 +337,15 @@ template <int MODE>
 __global__ void __launch_bounds__(GJK_THREADS, 3)
 k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
     extern __shared__ double smem[];
-    Simplex S;
-    S.base = smem + threadIdx.x;
-    S.stride = GJK_THREADS;
+    double *base = smem + threadIdx.x;
+    Simplex<GJK_THREADS> S;
+    S.base = base;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
     const int total = w.counters[2];
     int chunk_begin = 0, chunk_end = 0;
     bool exhausted = false;
-    PairState s;
+    PairState<GJK_THREADS> s;
     s.state = D3D_UNKNOWN;
     bool running = false;   // lane owns a pair that still iterates
     bool finished = false;  // lane owns a pair whose result is not written yet
@@ -324,7 +354,7 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
         unsigned run_mask = __ballot_sync(0xffffffffu, running);
         int idle = 32 - __popc(run_mask);
         if (idle >= GJK_REFILL_MIN || run_mask == 0) {
-            if (finished) { gjk_finish<MODE>(s, S, prm, true); finished = false; }
+            if (finished) { gjk_finish<MODE, GJK_THREADS>(s, S, prm, true); finished = false; }
             if (!exhausted) {
                 unsigned need = ~run_mask;
                 int rank = __popc(need & lt_mask);
@@ -342,7 +372,7 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
                     int avail = chunk_end - chunk_begin;
                     int give = min(avail, want - handed);
                     if (!running && rank >= handed && rank < handed + give) {
-                        init_pair<1>(s, c, pairs, __ldg(w.perm + chunk_begin + (rank - handed)));
+                        init_pair<GJK_THREADS>(s, c, pairs, __ldg(w.perm + chunk_begin + (rank - handed)), base);
                         running = true;
                     }
                     chunk_begin += give;
@@ -353,34 +383,36 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
             if (run_mask == 0) break;
         }
         if (running) {
-            gjk_step<MODE, 1>(s, S, prm, 0);
+            gjk_step<MODE, 1, GJK_THREADS>(s, S, prm, 0);
             if (s.state != D3D_UNKNOWN) { running = false; finished = true; }
         }
     }
 }
 
-// One warp per pair (wide hulls); every lane holds the same state.
+// One warp per pair (wide hulls); every lane holds the same state, the shared
+// record is written redundantly (same values) by all lanes.
 template <int MODE>
-__global__ void __launch_bounds__(GJK_THREADS, 3)
+__global__ void __launch_bounds__(GJK_THREADS, 4)
 k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
-    __shared__ double smem[(GJK_THREADS / 32) * 36];
+    __shared__ double smem[(GJK_THREADS / 32) * GJK_FIELDS];
     const int lane = threadIdx.x & 31;
-    Simplex S;
-    S.base = smem + (threadIdx.x >> 5) * 36;
-    S.stride = 1;
+    double *base = smem + (threadIdx.x >> 5) * GJK_FIELDS;
+    Simplex<1> S;
+    S.base = base;
     const int first = w.counters[2], total = w.counters[3];
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(&w.counters[1], 1);
         idx = __shfl_sync(0xffffffffu, idx, 0) + first;
         if (idx >= total) break;
-        PairState s;
-        init_pair<32>(s, c, pairs, __ldg(w.perm + idx));
+        PairState<1> s;
+        init_pair<1>(s, c, pairs, __ldg(w.perm + idx), base);
+        __syncwarp();
         while (s.state == D3D_UNKNOWN) {
-            gjk_step<MODE, 32>(s, S, prm, lane);
+            gjk_step<MODE, 32, 1>(s, S, prm, lane);
             __syncwarp();
         }
-        gjk_finish<MODE>(s, S, prm, lane == 0);
+        gjk_finish<MODE, 1>(s, S, prm, lane == 0);
         __syncwarp();
     }
 }
@@ -398,7 +430,8 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
-    size_t smem = sizeof(double) * 36 * GJK_THREADS;
+    size_t smem = sizeof(double) * GJK_FIELDS * GJK_THREADS;
+    D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * 3);
     k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     int wblocks = (int)d3d_min64((n_pairs + 3) / 4, (int64_t)sms * 3);
