@@ -1,0 +1,209 @@
+"""AABB tree for broad-phase collision detection, on the GPU.
+
+Drop-in for distance3d/aabb_tree.py: `AabbTree` (:15-191), `all_aabbs_overlap`
+(:465-500) and `aabb_overlap` (:503-527).  The reference grows an incremental
+binary tree on the host; here every `insert_aabbs` rebuilds a linear BVH on the
+device (Morton codes, radix sort, Karras hierarchy, bottom-up refit; see
+csrc/lbvh.cu) and queries run a stackless traversal.  Only overlap SETS are
+contractual: indices returned by the queries are insertion indices
+(0 .. n-1 in the order the boxes were inserted) and index `external_data_list`.
+
+`Lbvh` is the batched device-level interface used by the pipeline.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_i64, c_size, ptr
+
+INDEX_NONE = -1
+
+
+class Lbvh:
+    """Linear BVH over device-resident boxes ``aabbs f64[n,3,2]`` (torch tensor)."""
+
+    def __init__(self, aabbs):
+        torch = _lib.torch_cuda()
+        if not isinstance(aabbs, torch.Tensor):
+            aabbs = torch.from_numpy(np.ascontiguousarray(aabbs, dtype=np.float64)).to(
+                torch.device("cuda", torch.cuda.current_device()))
+        self.aabbs = aabbs.reshape(-1, 3, 2).contiguous()
+        self.n = int(self.aabbs.shape[0])
+        self.device = self.aabbs.device
+        L = _lib.lib()
+        nbytes = L.d3d_bvh_workspace_bytes(c_i64(self.n))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _lib._check(L.d3d_bvh_build(ptr(self.aabbs), c_i64(self.n), ptr(self.workspace),
+                                    c_size(nbytes), _lib.stream_ptr()))
+        self._order = None
+
+    def leaf_order(self):
+        """Object indices in Morton order (int32[n])."""
+        if self._order is None:
+            torch = _lib.torch_cuda()
+            self._order = torch.empty(self.n, dtype=torch.int32, device=self.device)
+            _lib._check(_lib.lib().d3d_bvh_leaf_order(ptr(self.workspace), c_i64(self.n),
+                                                      ptr(self._order), _lib.stream_ptr()))
+        return self._order
+
+    def root_aabb(self):
+        torch = _lib.torch_cuda()
+        out = torch.empty((3, 2), dtype=torch.float64, device=self.device)
+        _lib._check(_lib.lib().d3d_bvh_root_aabb(ptr(self.workspace), c_i64(self.n), ptr(out),
+                                                 _lib.stream_ptr()))
+        return out
+
+    def overlap(self, query, capacity=None, order=None, out=None):
+        """All (tree index, query index) pairs with overlapping boxes.
+
+        Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  When
+        `capacity` is too small the query is re-run once with the exact size.
+        """
+        torch = _lib.torch_cuda()
+        if not isinstance(query, torch.Tensor):
+            query = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float64)).to(self.device)
+        query = query.reshape(-1, 3, 2).contiguous()
+        nq = int(query.shape[0])
+        if capacity is None:
+            capacity = max(1024, 16 * nq)
+        L = _lib.lib()
+        while True:
+            if out is None or out.shape[0] < capacity:
+                out = torch.empty((capacity, 2), dtype=torch.int32, device=self.device)
+            _lib._check(L.d3d_bvh_overlap(
+                ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq), ptr(out),
+                c_i64(out.shape[0]), ptr(self._count), _lib.stream_ptr()))
+            count = int(self._count.item())
+            if count <= out.shape[0]:
+                return out[:count], count
+            capacity = count
+            out = None
+
+    def overlap_self(self, capacity=None):
+        """Tree against its own leaves, queries walked in Morton order."""
+        return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order())
+
+
+def brute_force_pairs(aabbs1, aabbs2, capacity=None):
+    """Device brute force: (pairs int32[count,2] sorted row-major, count)."""
+    torch = _lib.torch_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def dev_boxes(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(dev).reshape(-1, 3, 2).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev).reshape(-1, 3, 2)
+
+    a1, a2 = dev_boxes(aabbs1), dev_boxes(aabbs2)
+    n1, n2 = int(a1.shape[0]), int(a2.shape[0])
+    count_t = torch.zeros(1, dtype=torch.int64, device=dev)
+    capacity = capacity or max(1024, 8 * (n1 + n2))
+    L = _lib.lib()
+    while True:
+        out = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
+        _lib._check(L.d3d_aabb_overlap_brute(ptr(a1), c_i64(n1), ptr(a2), c_i64(n2), ptr(out),
+                                             c_i64(capacity), ptr(count_t), _lib.stream_ptr()))
+        count = int(count_t.item())
+        if count <= capacity:
+            break
+        capacity = count
+    pairs = out[:count]
+    if count:
+        key = pairs[:, 0].to(torch.int64) * max(n2, 1) + pairs[:, 1].to(torch.int64)
+        pairs = pairs[torch.argsort(key)]
+    return pairs, count
+
+
+def all_aabbs_overlap(aabbs1, aabbs2):
+    """Brute-force overlap of two box lists (reference: aabb_tree.py:465-500).
+
+    Returns ``(unique indices 1, unique indices 2, pairs)``; pairs are in the
+    reference's row-major order, as an int array of shape (k, 2).
+    """
+    pairs, _ = brute_force_pairs(aabbs1, aabbs2)
+    pairs = pairs.cpu().numpy().astype(np.int64)
+    return np.unique(pairs[:, 0]), np.unique(pairs[:, 1]), pairs
+
+
+def aabb_overlap(aabb1, aabb2):
+    """Closed-interval overlap of two boxes (reference: aabb_tree.py:503-527)."""
+    _, _, pairs = all_aabbs_overlap(np.asarray(aabb1)[np.newaxis], np.asarray(aabb2)[np.newaxis])
+    return len(pairs) > 0
+
+
+class AabbTree:
+    """AABB tree with the reference's interface (aabb_tree.py:15-191)."""
+
+    def __init__(self):
+        self.root = INDEX_NONE
+        self.filled_len = 0
+        self.aabbs = np.empty((0, 3, 2))
+        self.external_data_list = []
+        self.insert_index_list = []
+        self.insert_index_max = 0
+        self._bvh = None
+
+    def __len__(self):
+        return len(self.aabbs)
+
+    def insert_aabbs(self, aabbs, external_data_list=None, pre_insertion_methode="none"):
+        """Insert boxes (reference: aabb_tree.py:31-101); the device tree is rebuilt lazily.
+
+        `pre_insertion_methode` only influenced the shape of the reference's
+        insertion tree and is accepted for compatibility.
+        """
+        aabbs = np.asarray(aabbs, dtype=np.float64).reshape(-1, 3, 2)
+        n = len(aabbs)
+        if n == 0:
+            return
+        assert external_data_list is None or len(external_data_list) == n
+        self.aabbs = np.concatenate((self.aabbs, aabbs), axis=0)
+        self.external_data_list += list(external_data_list) if external_data_list is not None \
+            else [None] * n
+        self.insert_index_list.extend(range(self.insert_index_max, self.insert_index_max + n))
+        self.insert_index_max += n
+        self.filled_len = len(self.aabbs)
+        self.root = 0
+        self._bvh = None
+
+    def insert_aabb(self, aabb, external_data=None):
+        """Insert a single box (reference: aabb_tree.py:103-115)."""
+        self.insert_aabbs([aabb], [external_data], pre_insertion_methode="none")
+
+    def _tree(self):
+        if self._bvh is None:
+            self._bvh = Lbvh(self.aabbs)
+        return self._bvh
+
+    def overlaps_aabb_tree(self, other):
+        """Overlaps with another tree (reference: aabb_tree.py:121-159).
+
+        Returns ``(is_overlapping, unique indices of self, unique indices of other,
+        pairs)`` with pairs as an int array (k, 2) of (index in self, index in other),
+        sorted by (other, self).
+        """
+        if len(self) == 0 or len(other) == 0:
+            empty = np.empty((0, 2), dtype=np.int64)
+            return False, np.array([]), np.array([]), empty
+        bvh = self._tree()
+        if other is self:
+            pairs, _ = bvh.overlap_self()
+        else:
+            pairs, _ = bvh.overlap(other.aabbs)
+        pairs = pairs.cpu().numpy().astype(np.int64)
+        pairs = pairs[np.lexsort((pairs[:, 0], pairs[:, 1]))]
+        return len(pairs) > 0, np.unique(pairs[:, 0]), np.unique(pairs[:, 1]), pairs
+
+    def overlaps_aabb(self, aabb):
+        """Leaves overlapping one box (reference: aabb_tree.py:161-181)."""
+        if len(self) == 0:
+            return False, np.array([])
+        pairs, _ = self._tree().overlap(np.asarray(aabb, dtype=np.float64).reshape(1, 3, 2))
+        overlaps = np.sort(pairs[:, 0].cpu().numpy().astype(np.int64))
+        return len(overlaps) > 0, overlaps
+
+    def get_root_aabb(self):
+        """AABB of the whole tree (reference: aabb_tree.py:183-191)."""
+        return self._tree().root_aabb().cpu().numpy()

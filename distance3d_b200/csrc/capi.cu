@@ -179,7 +179,10 @@ __global__ void k_debug_norm(const double *v, int64_t n, double *out, int mode) 
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
     double x = v[3 * t], y = v[3 * t + 1], z = v[3 * t + 2];
-    out[t] = mode == 0 ? norm_x87(x, y, z) : norm_x87_exact(x, y, z);
+    if (mode == 0) { out[t] = norm_x87(x, y, z); return; }
+    // exact emulation alone, seeded with a plain fp64 estimate
+    double g = sqrt(x * x + y * y + z * z);
+    out[t] = (g > 1e-140 && g < 1e140) ? norm_x87_exact(x, y, z, g, 0.0) : norm_x87(x, y, z);
 }
 
 }  // namespace

@@ -17,4 +17,4 @@ int d3d_sm_count();
                                  cudaGetErrorString(err__));                              \
     } while (0)
 
-static inline int64_t d3d_min64(int64_t a, int64_t b) { return a < b ? a : b; }
+static __host__ __device__ inline int64_t d3d_min64(int64_t a, int64_t b) { return a < b ? a : b; }

