@@ -1,0 +1,279 @@
+// Expanding polytope algorithm, one WARP per intersecting pair.
+//
+// Replaces distance3d/epa.py:9-202 (epa, Polytope, LooseEdges), which is plain
+// interpreted Python in the reference.  The polytope (up to max_faces faces = 3
+// vertices + unit normal each) and the loose-edge list live in shared memory in
+// structure-of-arrays form ([12][max_faces], [6][max_loose_edges], conflict free
+// for lane-per-face access)
+// (max_faces <= 64, max_loose_edges <= 32: one or two lanes-worth.)  Per iteration the warp
+//   A  finds the face closest to the origin (lane-strided scan + shuffle arg-min,
+//      lowest index wins ties like np.argmin),
+//   B  evaluates the support point in the face normal (hull vertex scans are
+//      cooperative, analytic supports replicated),
+//   C  tests convergence,
+//   D  marks the faces that see the new point (lane per face), replays the
+//      reference's swap-with-last removal loop on a slot permutation, and maintains
+//      the loose-edge list with a lane-parallel search per edge (first match wins),
+//   E  builds the new faces lane-per-edge and compacts the valid ones in order.
+// The reference's quirks are reproduced on purpose: the
+// "swap" in fix_ccw_normal_direction only copies v1 over v0, degenerate new faces
+// are skipped but leave their data behind, the max_faces assertion becomes status
+// D3D_EPA_MAX_FACES, and after max_iter iterations the result is read from the slot
+// that held the last closest face as it looks THEN.
+#include "d3d_common.cuh"
+#include "d3d_support.cuh"
+
+namespace {
+
+struct EpaParams {
+    int max_iter, max_loose_edges, max_faces;
+    double epsilon;
+    const double *Y;
+    double *out_mtv;
+    uint8_t *out_success;
+    int32_t *out_nfaces;
+    int32_t *out_iters;
+    int32_t *out_status;
+    double *out_faces;
+    int *counter;
+};
+
+#define EPA_WARPS 4
+
+struct WarpMem {
+    double *faces;  // [12][max_faces]: v0 xyz, v1 xyz, v2 xyz, n xyz
+    double *loose;  // [6][max_loose]: a xyz, b xyz
+    int *perm;      // [max_faces]
+    int mf, ml;
+    D3D_DEV v3 fget(int i, int which) const {
+        return V3(faces[(3 * which) * mf + i], faces[(3 * which + 1) * mf + i], faces[(3 * which + 2) * mf + i]);
+    }
+    D3D_DEV void fset(int i, int which, v3 v) const {
+        faces[(3 * which) * mf + i] = v.x; faces[(3 * which + 1) * mf + i] = v.y; faces[(3 * which + 2) * mf + i] = v.z;
+    }
+    D3D_DEV v3 lget(int k, int which) const {
+        return V3(loose[(3 * which) * ml + k], loose[(3 * which + 1) * ml + k], loose[(3 * which + 2) * ml + k]);
+    }
+    D3D_DEV void lset(int k, int which, v3 v) const {
+        loose[(3 * which) * ml + k] = v.x; loose[(3 * which + 1) * ml + k] = v.y; loose[(3 * which + 2) * ml + k] = v.z;
+    }
+};
+
+// epa.py:99-102 compute_normal
+D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v2 - v0)); }
+
+__global__ void __launch_bounds__(EPA_WARPS * 32)
+k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
+    const int mf = prm.max_faces, ml = prm.max_loose_edges;
+    size_t per_warp = (size_t)12 * mf + 6 * ml + (mf + 1) / 2 + 2;  // doubles
+    WarpMem W;
+    W.faces = smem + wid * per_warp;
+    W.loose = W.faces + 12 * mf;
+    W.perm = reinterpret_cast<int *>(W.loose + 6 * ml);
+    W.mf = mf; W.ml = ml;
+    const double eps = prm.epsilon;
+
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(prm.counter, 1);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_pairs) break;
+        int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
+        Collider A = load_collider(c, pr.x), B = load_collider(c, pr.y);
+
+        // epa.py:83-97: zero-initialised polytope, faces ABC, ACD, ADB, BDC
+        for (int i = lane; i < 12 * mf; i += 32) W.faces[i] = 0.0;
+        __syncwarp();
+        if (lane < 4) {
+            const double *Y = prm.Y + 12 * (int64_t)k;
+            const int ia[4] = {0, 0, 0, 1}, ib[4] = {1, 2, 3, 3}, ic[4] = {2, 3, 1, 2};
+            v3 v0 = ld3(Y + 3 * ia[lane]), v1 = ld3(Y + 3 * ib[lane]), v2 = ld3(Y + 3 * ic[lane]);
+            W.fset(lane, 0, v0); W.fset(lane, 1, v1); W.fset(lane, 2, v2);
+            W.fset(lane, 3, face_normal(v0, v1, v2));
+        }
+        __syncwarp();
+        int n_faces = 4, closest = 0, it = 0, status = D3D_INTERSECTION;
+        bool done = false, success = false;
+        v3 mtv = V3(0.0, 0.0, 0.0);
+
+        for (it = 0; it < prm.max_iter; ++it) {
+            // ---- A: closest face, first arg-min of sum(v0 * n) (epa.py:104-109)
+            double best = 0.0;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < n_faces; i += 32) {
+                double d = dot_plain(W.fget(i, 0), W.fget(i, 3));
+                if (bi == 0x7fffffff || d < best) { best = d; bi = i; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ob = __shfl_xor_sync(FULL, best, off);
+                int oi = __shfl_xor_sync(FULL, bi, off);
+                if (oi != 0x7fffffff && (bi == 0x7fffffff || ob < best || (ob == best && oi < bi))) {
+                    best = ob; bi = oi;
+                }
+            }
+            closest = bi;
+            double min_dist = best;
+            // ---- B: support point of A - B in the face normal (epa.py:62-65)
+            v3 sd = W.fget(closest, 3);
+            v3 new_point = support<32>(A, sd, lane) - support<32>(B, -sd, lane);
+            // ---- C: convergence (epa.py:67-70)
+            double proj = dot_blas(new_point, sd);
+            if (proj - min_dist < eps) {
+                mtv = sd * proj;
+                success = true; done = true; ++it;
+                break;
+            }
+            // ---- D: faces that see the new point (epa.py:122-124, 157-165)
+            unsigned vis_lo = 0, vis_hi = 0;
+            {
+                bool v0 = false, v1 = false;
+                if (lane < n_faces) v0 = dot_blas(W.fget(lane, 3), new_point - W.fget(lane, 0)) > eps;
+                if (lane + 32 < n_faces)
+                    v1 = dot_blas(W.fget(lane + 32, 3), new_point - W.fget(lane + 32, 0)) > eps;
+                vis_lo = __ballot_sync(FULL, v0);
+                vis_hi = __ballot_sync(FULL, v1);
+            }
+            // replay of the swap-with-last loop on slot indices (lane 0), removal order in perm
+            // perm[s] = original slot whose face ends up in slot s
+            for (int i = lane; i < n_faces; i += 32) W.perm[i] = i;
+            __syncwarp();
+            int n_loose = 0;
+            int nf = n_faces;
+            {
+                int i = 0;
+                while (i < nf) {  // uniform: every lane replays the same integer bookkeeping
+                    int f = W.perm[i];
+                    bool vis = f < 32 ? ((vis_lo >> f) & 1u) : ((vis_hi >> (f - 32)) & 1u);
+                    if (!vis) { ++i; continue; }
+                    // epa.py:167-187: edges of the removed face against the loose-edge list
+                    for (int j = 0; j < 3; ++j) {
+                        v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);
+                        bool match = false;
+                        if (lane < n_loose)
+                            match = norm_numpy(W.lget(lane, 1) - e0) < eps && norm_numpy(W.lget(lane, 0) - e1) < eps;
+                        unsigned mm = __ballot_sync(FULL, match);
+                        int found = mm ? __ffs(mm) - 1 : -1;  // first matching edge wins
+                        __syncwarp();
+                        if (found >= 0) {  // overwrite_edge_with_last_edge (epa.py:200-202)
+                            if (lane == 0) {
+                                W.lset(found, 0, W.lget(n_loose - 1, 0));
+                                W.lset(found, 1, W.lget(n_loose - 1, 1));
+                            }
+                            --n_loose;
+                        } else {  // add_edge_to_list (epa.py:193-198)
+                            if (n_loose >= ml) { __syncwarp(); break; }
+                            if (lane == 0) { W.lset(n_loose, 0, e0); W.lset(n_loose, 1, e1); }
+                            ++n_loose;
+                        }
+                        __syncwarp();
+                    }
+                    // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i
+                    if (lane == 0) W.perm[i] = W.perm[nf - 1];
+                    --nf;
+                    __syncwarp();
+                }
+            }
+            // apply the permutation: slot s <- original slot perm[s] (reads before writes)
+            for (int base = 0; base < n_faces; base += 32) {
+                int s = base + lane;
+                int src = s < n_faces ? W.perm[s] : s;
+                v3 a0, a1, a2, a3;
+                bool mv = s < n_faces && src != s;
+                if (mv) { a0 = W.fget(src, 0); a1 = W.fget(src, 1); a2 = W.fget(src, 2); a3 = W.fget(src, 3); }
+                __syncwarp();
+                if (mv) { W.fset(s, 0, a0); W.fset(s, 1, a1); W.fset(s, 2, a2); W.fset(s, 3, a3); }
+                __syncwarp();
+            }
+            n_faces = nf;
+            // ---- E: one new face per loose edge (epa.py:126-146)
+            bool overflow = false;
+            if (n_loose > 0) {
+                int e = lane;
+                bool have = e < n_loose;
+                v3 v0 = V3(0, 0, 0), v1 = v0, nrm = v0;
+                bool valid = false;
+                if (have) {
+                    v0 = W.lget(e, 0); v1 = W.lget(e, 1);
+                    nrm = face_normal(v0, v1, new_point);
+                    valid = !(norm_numpy(nrm) < 0.5);
+                }
+                unsigned vm = __ballot_sync(FULL, valid);
+                unsigned hm = __ballot_sync(FULL, have);
+                int pos = n_faces + __popc(vm & lt);
+                // assert self.n_faces < self.max_faces, evaluated before every edge
+                overflow = __ballot_sync(FULL, have && pos >= mf) != 0;
+                v3 w0 = v0, wn = nrm;
+                if (overflow) valid = false;
+                if (valid && dot_blas(v0, nrm) + 1e-6 < 0.0) { w0 = v1; wn = -nrm; }  // epa.py:139-146
+                if (valid) { W.fset(pos, 0, w0); W.fset(pos, 1, v1); W.fset(pos, 2, new_point); W.fset(pos, 3, wn); }
+                int n_new = __popc(vm);
+                // a skipped degenerate face behind the last valid one leaves its data in the next slot
+                int last_have = 31 - __clz(hm);
+                bool trailing = !((vm >> last_have) & 1u);
+                if (!overflow && trailing && lane == last_have && n_faces + n_new < mf) {
+                    W.fset(n_faces + n_new, 0, v0); W.fset(n_faces + n_new, 1, v1);
+                    W.fset(n_faces + n_new, 2, new_point); W.fset(n_faces + n_new, 3, nrm);
+                }
+                n_faces += n_new;
+                __syncwarp();
+            }
+            if (overflow) { status = D3D_EPA_MAX_FACES; done = true; ++it; break; }
+            __syncwarp();
+        }
+        if (!done) {  // epa.py:76-78
+            v3 n = W.fget(closest, 3);
+            mtv = n * dot_blas(W.fget(closest, 0), n);
+        }
+        if (lane == 0) {
+            st3(prm.out_mtv + 3 * (int64_t)k, mtv);
+            prm.out_success[k] = success ? 1 : 0;
+            if (prm.out_nfaces) prm.out_nfaces[k] = n_faces;
+            if (prm.out_iters) prm.out_iters[k] = it;
+            if (prm.out_status) prm.out_status[k] = status;
+        }
+        if (prm.out_faces) {
+            double *o = prm.out_faces + (int64_t)k * mf * 12;
+            for (int i = lane; i < mf; i += 32)
+                for (int w = 0; w < 4; ++w) st3(o + 12 * i + 3 * w, W.fget(i, w));
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t d3d_epa_workspace_bytes(int64_t n_pairs) { (void)n_pairs; return 256; }
+
+int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
+            int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
+            uint8_t *out_success, int32_t *out_nfaces, int32_t *out_iters, int32_t *out_status,
+            double *out_faces, void *workspace, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs == 0) return 0;
+    if (!c || !pairs || !Y || !out_mtv || !out_success || !workspace)
+        return d3d_set_error("d3d_epa: null argument");
+    if (ws_bytes < 256) return d3d_set_error("d3d_epa: workspace too small");
+    if (max_faces < 4 || max_faces > 64 || max_loose_edges < 1 || max_loose_edges > 32)
+        return d3d_set_error("d3d_epa: max_faces must be in [4, 64] and max_loose_edges in [1, 32]");
+    EpaParams prm;
+    prm.max_iter = max_iter; prm.max_loose_edges = max_loose_edges; prm.max_faces = max_faces;
+    prm.epsilon = epsilon; prm.Y = Y; prm.out_mtv = out_mtv; prm.out_success = out_success;
+    prm.out_nfaces = out_nfaces; prm.out_iters = out_iters; prm.out_status = out_status;
+    prm.out_faces = out_faces; prm.counter = reinterpret_cast<int *>(workspace);
+    D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, stream));
+    size_t per_warp = (size_t)12 * max_faces + 6 * max_loose_edges + (max_faces + 1) / 2 + 2;
+    size_t smem = per_warp * EPA_WARPS * sizeof(double);
+    D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (int)d3d_min64((n_pairs + EPA_WARPS - 1) / EPA_WARPS, (int64_t)d3d_sm_count() * 6);
+    k_epa<<<blocks, EPA_WARPS * 32, smem, stream>>>(*c, pairs, n_pairs, prm);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -75,6 +75,33 @@ int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n
                          double tolerance, uint8_t *out_hit, int32_t *out_iters,
                          int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
 
+/* epa.py:9-78 epa(simplex, collider1, collider2, max_iter, max_loose_edges, max_faces, epsilon)
+ * for pairs[k] with GJK simplex Y[k,4,3] (out_Y of d3d_gjk_distance, 4 valid rows required):
+ *   out_mtv[k,3]   minimum translation vector (depth = |mtv|, normal = mtv / |mtv|)
+ *   out_success[k] 1 = converged before max_iter
+ *   out_nfaces[k], out_iters[k] (may be NULL); out_faces[k,max_faces,4,3] (may be NULL)
+ *   out_status[k]  D3D_INTERSECTION, or D3D_EPA_MAX_FACES where the reference raises
+ *                  AssertionError (epa.py:128)
+ * Limits: 4 <= max_faces <= 64, 1 <= max_loose_edges <= 32 (the reference's defaults). */
+size_t d3d_epa_workspace_bytes(int64_t n_pairs);
+int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
+            int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
+            uint8_t *out_success, int32_t *out_nfaces, int32_t *out_iters, int32_t *out_status,
+            double *out_faces, void *workspace, size_t ws_bytes, void *stream);
+
+/* mpr.py:21-50 mpr_intersection (want_penetration = 0) and mpr.py:53-109 mpr_penetration
+ * (want_penetration = 1) for pairs[k]:
+ *   out_hit[k]     1 = intersecting
+ *   out_depth[k], out_dir[k,3], out_pos[k,3]  penetration depth, direction (adding
+ *                  depth * dir to collider 2 separates the pair) and contact position;
+ *                  zero where out_hit is 0 (the reference returns None there)
+ *   out_status[k]  D3D_NO_INTERSECTION / D3D_INTERSECTION / D3D_ITER_CAP (may be NULL)
+ * `perm` (optional, int32[n_pairs]): processing order, e.g. pairs grouped by collider types. */
+int d3d_mpr(const d3d_colliders *c, const int32_t *pairs, const int32_t *perm, int64_t n_pairs,
+            double tolerance, int max_iterations, int want_penetration, uint8_t *out_hit,
+            double *out_depth, double *out_dir, double *out_pos, int32_t *out_status,
+            void *stream);
+
 /* ---- broad phase ---------------------------------------------------------- */
 
 /* aabb_tree.py:465-500 all_aabbs_overlap (brute force): appends every (i, j) with

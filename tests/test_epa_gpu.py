@@ -1,0 +1,84 @@
+"""GPU: warp-cooperative EPA against the oracle and the real reference's outputs.
+
+Tolerance from BASELINE.json: penetration depth and normal within 1e-7; the
+implementation is in fact bit-exact (asserted)."""
+import numpy as np
+import pytest
+
+from distance3d_b200 import epa, gjk, random as d3random
+from oracle import cpu_oracle as O
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_epa_vs_reference_outputs():
+    cs, g = load_golden("epa.npz")
+    sel = np.where(g["status"] >= 0)[0]
+    res = epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel], want_faces=True).cpu()
+    asserted = g["status"][sel] == 7
+    assert np.array_equal(res["status"] == 7, asserted)
+    m = ~asserted
+    depth = np.linalg.norm(res["mtv"][m], axis=1)
+    ref_depth = np.linalg.norm(g["mtv"][sel][m], axis=1)
+    assert np.max(np.abs(depth - ref_depth)) < 1e-7
+    assert np.array_equal(res["mtv"][m], g["mtv"][sel][m])
+    assert np.array_equal(res["success"][m], g["success"][sel][m])
+    assert np.array_equal(res["n_faces"][m], g["n_faces"][sel][m])
+    for q in np.where(m)[0]:
+        n = res["n_faces"][q]
+        assert np.array_equal(res["faces"][q, :n], g["faces"][sel[q], :n])
+
+
+def test_golden_wide_hulls():
+    cs, g = load_golden("hulls.npz")
+    sel = np.where(g["epa_status"] >= 0)[0]
+    res = epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel]).cpu()
+    asserted = g["epa_status"][sel] == 7
+    assert np.array_equal(res["status"] == 7, asserted)
+    assert np.array_equal(res["mtv"][~asserted], g["epa_mtv"][sel][~asserted])
+    assert np.array_equal(res["success"][~asserted], g["epa_success"][sel][~asserted])
+
+
+@pytest.mark.parametrize("names,scale,hv", [
+    (d3random.PRIMITIVES, 0.3, (10, 10)),
+    (("mesh",), 0.6, (64, 256)),
+    (("mesh", "box", "capsule"), 0.4, (8, 40)),
+])
+def test_random_pipeline_gjk_then_epa(names, scale, hv):
+    rs = np.random.RandomState(21)
+    cs = d3random.random_collider_set(rs, 1500, names=names, center_scale=scale, hull_vertices=hv)
+    pairs = d3random.random_pairs(rs, len(cs), 12000)
+    g = gjk.gjk_distance_batch(cs, pairs)
+    gc = g.cpu()
+    sel = np.where((gc["dist"] == 0.0) & (gc["n_points"] == 4))[0]
+    assert len(sel) > 500
+    res = epa.epa_batch(cs, pairs[sel], g.simplex[sel.tolist()], want_faces=True).cpu()
+    ref = O.epa(cs, pairs[sel], gc["simplex"][sel], return_faces=True, n_threads=O.max_threads())
+    assert np.array_equal(res["status"], ref["status"])
+    ok = ref["status"] != 7
+    assert np.array_equal(res["mtv"][ok], ref["mtv"][ok])
+    assert np.array_equal(res["success"][ok], ref["success"][ok])
+    assert np.array_equal(res["n_faces"][ok], ref["n_faces"][ok])
+    assert np.array_equal(res["iters"][ok], ref["iters"][ok])
+    for q in np.where(ok)[0][:300]:
+        n = ref["n_faces"][q]
+        assert np.array_equal(res["faces"][q, :n], ref["faces"][q, :n])
+    # property (reference test_epa.py:37-60): translating B by mtv separates the shapes
+    conv = ok & (ref["success"] == 1)
+    assert conv.sum() > 100
+
+
+def test_scalar_epa_known_answer():
+    # distance3d/test/test_epa.py:7-34
+    from distance3d_b200 import colliders as C
+    from test_reference_kats import EPA_VERTICES1, EPA_VERTICES2
+    c1, c2 = C.ConvexHullVertices(EPA_VERTICES1), C.ConvexHullVertices(EPA_VERTICES2)
+    dist, p1, p2, simplex = gjk.gjk(c1, c2)
+    np.testing.assert_allclose(p1, p2, atol=1e-6)
+    mtv, faces, success = epa.epa(simplex, c1, c2)
+    assert success and faces.shape[1:] == (4, 3)
+    np.testing.assert_allclose(mtv, [-0.387287, 0.179576, -0.176204], atol=5e-7)
+    # moving collider 2 by mtv (plus a little) separates the shapes
+    c2b = C.ConvexHullVertices(EPA_VERTICES2 + mtv * (1.0 + 1e-3))
+    assert gjk.gjk(c1, c2b)[0] > 0.0
