@@ -123,17 +123,34 @@ class DeviceColliders:
 
     def __init__(self, cs, device):
         import torch
-        from . import _lib
-        self.device = device
-        self.n = len(cs)
         to = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
-        self.type = to(cs.type)
-        self.pose = to(cs.pose)
-        self.param = to(cs.param)
-        self.vert_off = to(cs.vert_off)
-        self.vert_len = to(cs.vert_len)
-        self.verts = to(cs.verts)
-        self.margin = None if cs.margin is None else to(cs.margin)
+        self._init(to(cs.type), to(cs.pose), to(cs.param), to(cs.vert_off), to(cs.vert_len),
+                   to(cs.verts), None if cs.margin is None else to(cs.margin))
+
+    @classmethod
+    def from_tensors(cls, type_, pose, param, vert_off=None, vert_len=None, verts=None, margin=None):
+        """Wrap device tensors that already live in HBM (no host round trip)."""
+        import torch
+        self = cls.__new__(cls)
+        n = type_.shape[0]
+        dev = type_.device
+        if vert_off is None:
+            vert_off = torch.zeros(n, dtype=torch.int32, device=dev)
+        if vert_len is None:
+            vert_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        if verts is None:
+            verts = torch.zeros((1, 3), dtype=torch.float64, device=dev)
+        self._init(type_.to(torch.int32).contiguous(), pose.reshape(n, 4, 4).contiguous(),
+                   param.reshape(n, 3).contiguous(), vert_off.contiguous(), vert_len.contiguous(),
+                   verts.reshape(-1, 3).contiguous(), margin)
+        return self
+
+    def _init(self, type_, pose, param, vert_off, vert_len, verts, margin):
+        from . import _lib
+        self.device = type_.device
+        self.n = int(type_.shape[0])
+        self.type, self.pose, self.param = type_, pose, param
+        self.vert_off, self.vert_len, self.verts, self.margin = vert_off, vert_len, verts, margin
         self.struct = CColliders()
         self.struct.n = self.n
         self.struct.type = self.type.data_ptr()

@@ -136,6 +136,33 @@ int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *str
 /* aabb_tree.py:183-191 AabbTree.get_root_aabb: out[3,2] */
 int d3d_bvh_root_aabb(const void *workspace, int64_t n, double *out, void *stream);
 
+/* ---- robot self-collision (BASELINE config 4) ------------------------------ */
+
+/* Batched forward kinematics; replaces the per-configuration pytransform3d calls
+ * UrdfTransformManager.set_joint + get_transform(frame, "origin") made by
+ * broad_phase.py:111,148.  The kinematic tree is flattened by
+ * distance3d_b200.urdf.UrdfTransformManager.compile_kinematics: for frame k the pose is
+ * prod_{s in [chain_off[k], chain_off[k+1])} chain_fixed[s] * joint(chain_joint[s], q)
+ * (revolute: Rodrigues rotation about joint_axis, value clipped to joint_limits).
+ * q[n_cfg, n_joints] -> out_pose[n_cfg, n_frames, 4, 4] (row-major). */
+int d3d_fk_urdf(int n_frames, int n_joints, const double *joint_axis, const double *joint_limits,
+                const int32_t *joint_type, const int32_t *chain_off, const double *chain_fixed,
+                const int32_t *chain_joint, const double *q, int64_t n_cfg, double *out_pose,
+                void *stream);
+
+/* self_collision.py:22-36: candidates of a collider = AABB overlaps minus white-list.  The
+ * non-white-listed (frame a, frame b) combinations are a fixed `pattern[n_pattern,2]`; for
+ * each of n_groups groups of group_size consecutive boxes the overlapping candidate pairs
+ * (global box indices) are appended to out_pairs[cap,2]; *out_count is exact. */
+int d3d_filter_pairs(const double *aabb, int64_t n_groups, int group_size, const int32_t *pattern,
+                     int n_pattern, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                     void *stream);
+
+/* self_collision.py:31-35: mask[pairs[t,0]] = mask[pairs[t,1]] = 1 for every t < min(*count, cap)
+ * with hit[t] != 0. */
+int d3d_scatter_hits(const int32_t *pairs, const uint8_t *hit, const unsigned long long *count,
+                     int64_t cap, uint8_t *mask, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

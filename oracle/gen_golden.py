@@ -159,6 +159,46 @@ def main():
     bpairs = np.array(bpairs, dtype=np.int32).reshape(-1, 2)
     np.savez_compressed(os.path.join(OUT, "aabb.npz"), aabb=A, tree_pairs=tpairs, brute_pairs=bpairs,
                         tree_nodes=tree.nodes, tree_root=tree.root, **set_arrays(cs4))
+    # ---- robot self-collision (config C4 shape): reference detect() over random joints
+    from pytransform3d.urdf import UrdfTransformManager
+    import distance3d.broad_phase
+    from distance3d import self_collision
+    urdf_path = os.path.join(refbridge.REPO, "tests", "data", "robot_arm.urdf")
+    tm = UrdfTransformManager()
+    with open(urdf_path) as f:
+        tm.load_urdf(f.read(), mesh_path=os.path.dirname(urdf_path))
+    bvh = distance3d.broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
+    bvh.fill_tree_with_colliders(tm, make_artists=False, fill_self_collision_whitelists=True)
+    rsq = np.random.RandomState(7)
+    q = rsq.uniform(-np.pi, np.pi, size=(150, 6))
+    q[0] = 0.0
+    q[1] = [0.0, 1.57, 1.57, 0.0, 1.93, 0.0]   # distance3d/test/test_self_collision.py:26-33 -> 0 contacts
+    q[2] = [0.0, 1.57, 1.57, 0.0, 2.05, 0.0]   # :35-42 -> 3 contacts
+    frames = list(bvh.colliders_.keys())
+    masks = np.zeros((len(q), len(frames)), dtype=np.uint8)
+    poses = np.zeros((len(q), len(frames), 4, 4))
+    for b in range(len(q)):
+        for j in range(6):
+            tm.set_joint("joint%d" % (j + 1), q[b, j])
+        bvh.update_collider_poses()
+        contacts = self_collision.detect(bvh)
+        masks[b] = [contacts[fr] for fr in frames]
+        poses[b] = [tm.get_transform(fr, "origin") for fr in frames]
+    assert masks[0].sum() == 0 and masks[1].sum() == 0 and masks[2].sum() == 3
+    np.savez_compressed(os.path.join(OUT, "self_collision.npz"), q=q, mask=masks, poses=poses,
+                        frames=np.array(frames))
+
+    # ---- MeshGraph (hill climbing with vertex caching in the reference) -----
+    rsm = np.random.RandomState(99)
+    meshes = refbridge.random_reference_colliders(rsm, 40, ["mesh"], hull_as_vertices=False,
+                                                  mesh=dict(n_vertices=30))
+    others = refbridge.random_reference_colliders(rsm, 40, ["sphere", "capsule", "box", "cylinder"])
+    cols5 = meshes + others
+    cs5 = refbridge.to_set(cols5)
+    pairs5 = np.stack([rsm.randint(0, 40, 300), rsm.randint(0, 80, 300)], axis=1).astype(np.int32)
+    g5 = run_gjk(cols5, pairs5)
+    np.savez_compressed(os.path.join(OUT, "meshgraph.npz"), pairs=pairs5, **set_arrays(cs5), **g5)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -148,3 +148,18 @@ def test_scalar_api_matches_reference_semantics():
     box = C.Box(np.eye(4), np.ones(3))
     np.testing.assert_allclose(box.aabb(), [[-0.5, 0.5]] * 3)
     np.testing.assert_allclose(box.support_function(np.array([1.0, 1.0, 1.0])), [0.5, 0.5, 0.5])
+
+
+def test_meshgraph_brute_force_support_vs_reference_hill_climbing():
+    """MeshGraph: the reference climbs the triangle graph from a cached vertex
+    (mesh.py:12-139); the GPU takes the arg-max over all vertices.  Same point except on
+    10*EPS plateaus, so results agree to the stated tolerance."""
+    cs, g = load_golden("meshgraph.npz")
+    res = gjk.gjk_distance_batch(cs, g["pairs"]).cpu()
+    ok = g["status"] <= 1
+    assert np.max(np.abs(res["dist"][ok] - g["dist"][ok])) < TOL
+    assert np.max(np.abs(res["closest_a"][ok] - g["a"][ok])) < 1e-7
+    hit, _, _ = gjk.gjk_intersection_batch(cs, g["pairs"])
+    near = g["dist"] < 1e-12
+    assert np.array_equal(hit.cpu().numpy()[ok & ~near], g["hit"][ok & ~near])
+    compare_distance(cs, g["pairs"], exact_types=EXACT)   # bit-exact against the oracle

@@ -1,0 +1,140 @@
+"""CPU: host-side logic (packing, URDF kinematics, white-lists, random generators) and
+the C ABI of the CUDA library (loads and exports every symbol of include/d3d_b200.h)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from distance3d_b200 import colliders as C, pack, random as d3random
+from distance3d_b200.urdf import UrdfTransformManager, TransformManager
+from distance3d_b200.urdf_utils import self_collision_whitelists, fast_transform_manager_initialization
+from util import GOLDEN
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(REPO, "tests", "data")
+
+
+def test_library_exports_every_declared_symbol():
+    so = os.path.join(REPO, "distance3d_b200", "libd3d_b200.so")
+    if not os.path.exists(so):
+        from distance3d_b200 import build
+        build.build()
+    lib = ctypes.CDLL(so)
+    header = open(os.path.join(REPO, "include", "d3d_b200.h")).read()
+    names = set(re.findall(r"\b(d3d_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+    assert lib.d3d_last_error_string is not None
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "distance3d_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "libd3d_oracle" not in text and "cpu_oracle" not in text, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from distance3d_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libd3d_b200.so")
+    with pytest.raises(_lib.D3DError):
+        _lib.lib()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from distance3d_b200 import gjk, _lib
+    with pytest.raises(_lib.D3DError):
+        gjk.gjk(C.Sphere(np.zeros(3), 1.0), C.Sphere(np.ones(3), 1.0))
+
+
+def test_pack_all_collider_types_and_margin():
+    T = np.eye(4)
+    cols = [C.Sphere(np.array([1.0, 2, 3]), 0.5), C.Capsule(T, 0.1, 0.2), C.Box(T, np.array([1.0, 2, 3])),
+            C.Ellipsoid(T, np.array([1.0, 2, 3])), C.Cylinder(T, 0.3, 0.4),
+            C.ConvexHullVertices(np.arange(12.0).reshape(4, 3)),
+            C.MeshGraph(T, np.arange(15.0).reshape(5, 3), np.array([[0, 1, 2]])),
+            C.Disk(np.zeros(3), 1.0, np.array([0.0, 0, 1])),
+            C.Ellipse(np.zeros(3), np.eye(3)[:2], np.array([1.0, 2])), C.Cone(T, 1.0, 2.0),
+            C.Margin(C.Sphere(np.zeros(3), 1.0), 0.25)]
+    cs = pack.pack_colliders(cols)
+    assert list(cs.type[:10]) == list(range(10)) and cs.type[10] == pack.SPHERE
+    assert cs.margin[10] == 0.25 and cs.margin[:10].sum() == 0
+    assert list(cs.vert_len) == [0, 0, 8, 0, 0, 4, 5, 0, 0, 0, 0]
+    assert cs.vert_off[5] == 8 and cs.vert_off[6] == 12 and cs.n_vertices == 17
+    np.testing.assert_array_equal(cs.pose[0, :3, 3], [1, 2, 3])
+    sub = cs.subset([5, 2])
+    assert list(sub.vert_len) == [4, 8] and sub.n_vertices == 12
+    np.testing.assert_array_equal(sub.verts[:4], np.arange(12.0).reshape(4, 3))
+    assert set(C.COLLIDERS) == {"sphere", "ellipsoid", "capsule", "disk", "ellipse", "cone",
+                                "cylinder", "box", "mesh"}
+
+
+def test_random_collider_set_shapes():
+    rs = np.random.RandomState(0)
+    cs = d3random.random_collider_set(rs, 5000, names=d3random.PRIMITIVES + ("mesh",),
+                                      hull_vertices=(6, 12))
+    assert len(cs) == 5000 and set(np.unique(cs.type)) == {0, 1, 2, 3, 4, 5}
+    R = cs.pose[:, :3, :3]
+    np.testing.assert_allclose(np.einsum("nij,nkj->nik", R, R), np.tile(np.eye(3), (5000, 1, 1)), atol=1e-12)
+    hull = cs.type == pack.HULL
+    assert cs.vert_len[hull].min() >= 6 and cs.vert_len[hull].max() <= 12
+    assert cs.vert_off[-1] + cs.vert_len[-1] == cs.n_vertices
+    pairs = d3random.random_pairs(rs, 5000, 1000)
+    assert np.all(pairs[:, 0] != pairs[:, 1])
+    for name, gen in d3random.RANDOM_GENERATORS.items():
+        args = gen(np.random.RandomState(1))
+        assert C.COLLIDERS[name](*args) is not None
+
+
+def load_robot_tm():
+    tm = UrdfTransformManager()
+    with open(os.path.join(DATA, "robot_arm.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=DATA)
+    return tm
+
+
+def test_urdf_kinematics_match_reference_poses():
+    g = np.load(os.path.join(GOLDEN, "self_collision.npz"))
+    tm = load_robot_tm()
+    tm.add_transform("robot_arm", "origin", np.eye(4))
+    frames = [str(f) for f in g["frames"]]
+    assert [o.frame for o in tm.collision_objects] == frames
+    kin = tm.compile_kinematics(frames, "origin")
+    assert kin["joint_names"] == ["joint%d" % i for i in range(1, 7)]
+    for b in (0, 2, 17):
+        for j in range(6):
+            tm.set_joint("joint%d" % (j + 1), g["q"][b, j])
+        for k, fr in enumerate(frames):
+            np.testing.assert_allclose(tm.get_transform(fr, "origin"), g["poses"][b, k], atol=1e-14)
+            # flattened chain reproduces the graph walk
+            T = np.eye(4)
+            for s in range(kin["chain_off"][k], kin["chain_off"][k + 1]):
+                T = T @ kin["chain_fixed"][s]
+                j = kin["chain_joint"][s]
+                if j >= 0:
+                    from distance3d_b200._transforms import matrix_from_axis_angle, transform_from
+                    T = T @ transform_from(matrix_from_axis_angle(kin["joint_axis"][j], g["q"][b, j]), np.zeros(3))
+            np.testing.assert_allclose(T, g["poses"][b, k], atol=1e-13)
+
+
+def test_self_collision_whitelists_match_survey():
+    tm = load_robot_tm()
+    wl = self_collision_whitelists(tm)
+    short = {k.split(":")[1]: sorted(f.split(":")[1] for f in v) for k, v in wl.items()}
+    assert short["link1/0"] == ["link1/0", "link2/0", "link2/1"]
+    assert short["link4/0"] == ["link3/0", "link4/0", "link5/0", "link5/1"]
+    assert short["link6/0"] == ["link5/0", "link5/1", "link6/0"]
+    tm2 = TransformManager()
+    fast_transform_manager_initialization(tm2, [1, 2, 3], "base")
+    fast_transform_manager_initialization(tm2, [4, 5], 1)
+    np.testing.assert_allclose(tm2.get_transform(5, "base"), np.eye(4))

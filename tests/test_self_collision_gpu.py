@@ -1,0 +1,104 @@
+"""GPU: URDF forward kinematics + batched self-collision (BASELINE config 4) and the
+scalar BoundingVolumeHierarchy / self_collision API, against the reference's pinned
+numbers and its own outputs on random joint configurations (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+
+from distance3d_b200 import broad_phase, colliders, self_collision
+from distance3d_b200.urdf import UrdfTransformManager, TransformManager
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def load_robot():
+    tm = UrdfTransformManager()
+    with open(os.path.join(DATA, "robot_arm.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=DATA)
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
+    bvh.fill_tree_with_colliders(tm, make_artists=False, fill_self_collision_whitelists=True)
+    return tm, bvh
+
+
+def test_bvh_reference_pins():
+    # distance3d/test/test_broad_phase.py:11-29
+    tm, bvh = load_robot()
+    assert len(bvh.get_artists()) == 0
+    assert len(bvh.get_collider_frames()) == 8 and len(bvh.get_colliders()) == 8
+    tm.set_joint("joint1", 3.1415926535)
+    bvh.update_collider_poses()
+    box = colliders.Box(np.eye(4), np.array([1, 1, 1], dtype=float))
+    assert len(bvh.aabb_overlapping_colliders(box)) == 5
+
+
+def test_self_collision_reference_pins():
+    # distance3d/test/test_self_collision.py:9-42
+    tm, bvh = load_robot()
+    assert np.count_nonzero(list(self_collision.detect(bvh).values())) == 0
+    assert not self_collision.detect_any(bvh)
+    for j, v in (("joint2", 1.57), ("joint3", 1.57), ("joint5", 1.93)):
+        tm.set_joint(j, v)
+    bvh.update_collider_poses()
+    assert np.count_nonzero(list(self_collision.detect(bvh).values())) == 0
+    tm.set_joint("joint5", 2.05)
+    bvh.update_collider_poses()
+    assert np.count_nonzero(list(self_collision.detect(bvh).values())) == 3
+    assert self_collision.detect_any(bvh)
+
+
+def test_batched_fk_and_contact_masks_vs_reference_outputs():
+    g = np.load(os.path.join(GOLDEN, "self_collision.npz"))
+    tm, bvh = load_robot()
+    model = self_collision.RobotModel(tm, bvh)
+    assert [str(f) for f in g["frames"]] == model.frames
+    assert len(model.pattern) == 17          # 28 - 11 white-listed pairs
+    poses = model.forward_kinematics(g["q"]).cpu().numpy()
+    assert np.max(np.abs(poses - g["poses"])) < 1e-12
+    mask, n_cand = model.detect_batch(g["q"])
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    assert mask[1].sum() == 0 and mask[2].sum() == 3
+    # chunked evaluation gives the same answer
+    mask2, _ = model.detect_batch(np.tile(g["q"], (3, 1)), chunk=64)
+    assert np.array_equal(mask2.cpu().numpy(), np.tile(g["mask"], (3, 1)))
+
+
+def test_bvh_from_colliders_translation_invariance():
+    # distance3d/test/test_broad_phase.py:32-101
+    from distance3d_b200 import random as d3random
+    from distance3d_b200._transforms import transform_from
+    tm = TransformManager()
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "origin")
+    rs = np.random.RandomState(232)
+    poses = {}
+    box2origin, size = d3random.rand_box(rs, center_scale=1.0)
+    bvh.add_collider("box", colliders.Box(box2origin, size)); poses["box"] = box2origin
+    center, radius = d3random.rand_sphere(rs, center_scale=1.0)
+    bvh.add_collider("sphere", colliders.Sphere(center, radius))
+    poses["sphere"] = transform_from(np.eye(3), center)
+    c2o, radius, height = d3random.rand_capsule(rs, center_scale=1.0)
+    bvh.add_collider("capsule", colliders.Capsule(c2o, radius, height)); poses["capsule"] = c2o
+    c2o, radius, length = d3random.rand_cylinder(rs, center_scale=1.0)
+    bvh.add_collider("cylinder", colliders.Cylinder(c2o, radius, length)); poses["cylinder"] = c2o
+    e2o, radii = d3random.rand_ellipsoid(rs, center_scale=1.0)
+    bvh.add_collider("ellipsoid", colliders.Ellipsoid(e2o, radii)); poses["ellipsoid"] = e2o
+    for frame, pose in poses.items():
+        tm.add_transform(frame, "origin", pose)
+
+    def overlaps():
+        return {f: sorted(bvh.aabb_overlapping_colliders(c, whitelist=(f,)).keys())
+                for f, c in bvh.colliders_.items()}
+
+    before = overlaps()
+    for frame, pose in poses.items():
+        moved = np.copy(pose)
+        moved[2, 3] -= 1.0
+        tm.add_transform(frame, "origin", moved)
+    bvh.update_collider_poses()
+    assert overlaps() == before
+    pairs = bvh.aabb_overlapping_with_other_bvh(bvh)
+    pairs1 = [((f, c), (f2, c2)) for (f, c), (f2, c2) in pairs if f != f2]
+    pairs2 = bvh.aabb_overlapping_with_self()
+    assert sorted((a[0], b[0]) for a, b in pairs1) == sorted((a[0], b[0]) for a, b in pairs2)
