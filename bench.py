@@ -42,6 +42,8 @@ def parse_args():
                     help="pairs timed on the host cores for cpu_baseline")
     ap.add_argument("--seed", type=int, default=84)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the broad-phase extra metrics")
+    ap.add_argument("--capsules", type=int, default=1000000, help="C2: capsules in the broad phase")
     return ap.parse_args()
 
 
@@ -125,6 +127,81 @@ def measure_fp64_peak(torch, _lib):
         flop = blocks * 256 * 8.0 * iters * 2.0
         best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+def make_capsules(n, center_scale=2.0, seed=32):
+    """BASELINE configs[1] (vis_capsules_benchmark.py:22-30 scaled up): n random capsules."""
+    from distance3d_b200 import random as d3random, pack
+    rs = np.random.RandomState(seed)
+    pose = d3random.random_transforms(rs, n)
+    pose[:, :3, 3] *= center_scale
+    param = np.zeros((n, 3))
+    param[:, 0] = (1.0 - rs.rand(n)) * 0.1
+    param[:, 1] = (1.0 - rs.rand(n)) * 0.5
+    z = np.zeros(n, dtype=np.int32)
+    return pack.ColliderSet(np.full(n, pack.CAPSULE, dtype=np.int32), pose, param, z, z, np.zeros((0, 3)))
+
+
+def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
+    """C2: AABBs of n capsules, LBVH build, all-overlap self query (dense and sparse sets)."""
+    from distance3d_b200 import aabb_tree
+    n = args.capsules
+    out = {"capsules": n}
+    for name, scale in (("dense", 2.0), ("constant_density", 2.0 * (n / 2000.0) ** (1.0 / 3.0))):
+        cs = make_capsules(n, scale)
+        dc = cs.device()
+        aabb = _lib.aabb_device(dc)
+        bvh = aabb_tree.Lbvh(aabb)
+        pairs, count = bvh.overlap_self(count_visits=True)
+        visits = bvh.visits()
+        buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=aabb.device)
+        del pairs
+        tb, tq = [], []
+        for it in range(steps + 2):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            bvh.rebuild()
+            e[1].record()
+            bvh.overlap_self(out=buf, capacity=buf.shape[0])
+            e[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tb.append(e[0].elapsed_time(e[1])); tq.append(e[1].elapsed_time(e[2]))
+        tb_ms, tq_ms = float(np.mean(tb)), float(np.mean(tq))
+        q_bytes = n * 48.0 + count * 8.0 + visits * 64.0
+        b_bytes = n * 176.0
+        out[name] = {
+            "center_scale": scale, "overlap_pairs": int(count), "node_visits": int(visits),
+            "build_ms": tb_ms, "query_ms": tq_ms,
+            "build_aabbs_per_s": n / (tb_ms * 1e-3), "overlap_pairs_per_s": count / (tq_ms * 1e-3),
+            "queries_per_s": n / (tq_ms * 1e-3),
+            "roofline_query": {"bound": "hbm", "achieved": q_bytes / (tq_ms * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s",
+                               "frac": q_bytes / (tq_ms * 1e-3) / 1e9 / hbm_peak,
+                               "bytes": "Q*48 + pairs*8 + node_visits*64 (SURVEY 8d)"},
+            "roofline_build": {"bound": "hbm", "achieved": b_bytes / (tb_ms * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s",
+                               "frac": b_bytes / (tb_ms * 1e-3) / 1e9 / hbm_peak,
+                               "bytes": "176 B per primitive (SURVEY 8d)"},
+        }
+        del buf, bvh
+        torch.cuda.empty_cache()
+        if cpu and name == "constant_density":
+            # reference algorithm (incremental tree + per-box stack query) on a bounded sample
+            from oracle import cpu_oracle
+            m = min(n, 50000)
+            A = cpu_oracle.aabb(make_capsules(m, 2.0 * (m / 2000.0) ** (1.0 / 3.0)))
+            t0 = time.perf_counter()
+            tree = cpu_oracle.Tree()
+            tree.insert_aabbs(A)
+            t1 = time.perf_counter()
+            ref_pairs = tree.query(A)
+            t2 = time.perf_counter()
+            out["cpu_baseline"] = {
+                "kind": "port", "cores": 1, "sample": "%d capsules at constant density" % m,
+                "build_aabbs_per_s": m / (t1 - t0), "queries_per_s": m / (t2 - t1),
+                "overlap_pairs_per_s": len(ref_pairs) / (t2 - t1)}
+    return out
 
 
 def cpu_baseline(cs, pairs, sample):
@@ -308,6 +385,11 @@ def main():
             "gpu_launches": 5 * args.steps,
             "clocks": clocks,
         }
+        if not args.no_extra:
+            del dc, out, pairs_d, host, host_out, host_pairs
+            torch.cuda.empty_cache()
+            line["broad_phase"] = bench_broad_phase(args, torch, _lib, hbm_peak,
+                                                    cpu=not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             cpu_value, threads, sample_n, ref = cpu_baseline(cs, pairs, args.cpu_sample)
             line["cpu_baseline"] = {

@@ -35,6 +35,7 @@ class Lbvh:
         nbytes = L.d3d_bvh_workspace_bytes(c_i64(self.n))
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._visits = torch.zeros(1, dtype=torch.int64, device=self.device)
         _lib._check(L.d3d_bvh_build(ptr(self.aabbs), c_i64(self.n), ptr(self.workspace),
                                     c_size(nbytes), _lib.stream_ptr()))
         self._order = None
@@ -55,7 +56,7 @@ class Lbvh:
                                                  _lib.stream_ptr()))
         return out
 
-    def overlap(self, query, capacity=None, order=None, out=None):
+    def overlap(self, query, capacity=None, order=None, out=None, count_visits=False):
         """All (tree index, query index) pairs with overlapping boxes.
 
         Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  When
@@ -74,16 +75,30 @@ class Lbvh:
                 out = torch.empty((capacity, 2), dtype=torch.int32, device=self.device)
             _lib._check(L.d3d_bvh_overlap(
                 ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq), ptr(out),
-                c_i64(out.shape[0]), ptr(self._count), _lib.stream_ptr()))
+                c_i64(out.shape[0]), ptr(self._count),
+                ptr(self._visits) if count_visits else None, _lib.stream_ptr()))
             count = int(self._count.item())
             if count <= out.shape[0]:
                 return out[:count], count
             capacity = count
             out = None
 
-    def overlap_self(self, capacity=None):
+    def overlap_self(self, capacity=None, out=None, count_visits=False):
         """Tree against its own leaves, queries walked in Morton order."""
-        return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order())
+        return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order(), out=out,
+                            count_visits=count_visits)
+
+    def visits(self):
+        """Node records fetched by the last overlap(count_visits=True) call."""
+        return int(self._visits.item())
+
+    def rebuild(self, aabbs=None):
+        """Rebuild the tree in place (same workspace) after the boxes changed."""
+        if aabbs is not None:
+            self.aabbs.copy_(aabbs.reshape(-1, 3, 2))
+        _lib._check(_lib.lib().d3d_bvh_build(ptr(self.aabbs), c_i64(self.n), ptr(self.workspace),
+                                             c_size(self.workspace.numel()), _lib.stream_ptr()))
+        self._order = None
 
 
 def brute_force_pairs(aabbs1, aabbs2, capacity=None):

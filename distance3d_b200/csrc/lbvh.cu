@@ -371,9 +371,10 @@ __device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, in
 __global__ void __launch_bounds__(128)
 k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
           const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
-          unsigned long long *count) {
+          unsigned long long *count, unsigned long long *visits) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_query || hdr->n <= 0) return;
+    unsigned n_visited = 0;
     int qi = order ? order[t] : (int)t;
     const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
     double2 qx = __ldg(qb), qy = __ldg(qb + 1), qz = __ldg(qb + 2);
@@ -386,6 +387,14 @@ k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double 
         bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
         if (ov && link.x < 0) append_pair(-link.x - 1, qi, out_pairs, cap, count);
         node = (ov && link.x >= 0) ? link.x : link.z;
+        ++n_visited;
+    }
+    if (visits) {  // measurement only: node records fetched (roofline traffic term)
+        unsigned total = n_visited;
+        unsigned m = __activemask();
+        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(m, total, off);
+        if (m == 0xffffffffu) { if ((threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)total); }
+        else atomicAdd(visits, (unsigned long long)n_visited);
     }
 }
 
@@ -472,15 +481,16 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
 
 int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
                     int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
-                    void *stream_) {
+                    unsigned long long *out_visits, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap: null argument");
     D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
     if (n_query == 0 || n == 0) return 0;
     if (!query) return d3d_set_error("d3d_bvh_overlap: null query");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
     k_overlap<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query,
-                                                                    out_pairs, cap, out_count);
+                                                                    out_pairs, cap, out_count, out_visits);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -125,10 +125,11 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
  * :121-159 overlaps_aabb_tree (:344-378 query_overlap_of_other_tree) when the query boxes are
  * the leaves of another tree: appends (tree object index, query index) for every overlapping
  * pair.  `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted
- * queries traverse coherently).  *out_count as for d3d_aabb_overlap_brute. */
+ * queries traverse coherently).  *out_count as for d3d_aabb_overlap_brute.  *out_visits
+ * (optional, may be NULL) receives the number of node records fetched (measurement). */
 int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
                     int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
-                    void *stream);
+                    unsigned long long *out_visits, void *stream);
 
 /* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
 int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);
