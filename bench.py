@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the broad-phase extra metrics")
     ap.add_argument("--capsules", type=int, default=1000000, help="C2: capsules in the broad phase")
+    ap.add_argument("--workload", default="gjk", choices=["gjk", "epa", "selfcollision", "pipeline"],
+                    help="gjk = headline (C1 + C2 extras); epa = C3; selfcollision = C4; pipeline = C5")
+    ap.add_argument("--items", type=int, default=0, help="size of the secondary workloads (0 = default)")
     return ap.parse_args()
 
 
@@ -204,6 +207,123 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
     return out
 
 
+def timed_steps(torch, dist, world, dev, fn, steps, warmup):
+    """max-over-ranks CUDA-event time per step of fn()."""
+    for _ in range(max(warmup, 3)):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def secondary_workload(args, torch, dist, rank, world, dev):
+    """C3 / C4 / C5 of BASELINE.json (own JSON line, same schema; not the headline)."""
+    from distance3d_b200 import _lib, gjk, epa, random as d3random, pipeline
+    rs = np.random.RandomState(args.seed + 1000 * rank)
+    line = {"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic"}
+    if args.workload == "epa":
+        # C3: intersecting convex hulls with 64-256 vertices, library of shapes, unique poses
+        n_pairs = args.items or 500000
+        cs = d3random.random_collider_set(rs, 2 * n_pairs, names=("mesh",), center_scale=0.7,
+                                          hull_vertices=(64, 256), hull_library=4096)
+        pairs = np.arange(2 * n_pairs, dtype=np.int32).reshape(n_pairs, 2)
+        dc = cs.device(dev)
+        g = gjk.gjk_distance_batch(dc, pairs)
+        sel = torch.nonzero((g.dist == 0.0) & (g.n_points == 4)).flatten()
+        pairs_d = torch.from_numpy(pairs).to(dev)[sel].contiguous()
+        Y = g.simplex[sel].contiguous()
+        n = int(sel.numel())
+        res = {}
+        ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=epa.epa_batch(dc, pairs_d, Y)),
+                         args.steps, args.warmup)
+        r = res["r"].cpu()
+        ms_gjk = timed_steps(torch, dist, world, dev, lambda: gjk.gjk_distance_batch(dc, pairs), 3, 1)
+        line.update({"metric": "epa_pairs_per_s", "value": world * n / (ms * 1e-3), "unit": "pairs/s",
+                     "ms_per_step": ms,
+                     "config": {"workload": "C3: EPA on intersecting convex hulls, 64-256 vertices, "
+                                            "4-point GJK simplex", "pairs_per_gpu": n,
+                                "hull_pairs_generated": n_pairs},
+                     "mean_epa_iterations": float(r["iters"].mean()),
+                     "max_faces_assert_rate": float((r["status"] == 7).mean()),
+                     "converged_rate": float(r["success"].mean()),
+                     "gjk_hull_pairs_per_s": world * n_pairs / (ms_gjk * 1e-3)})
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import cpu_oracle
+            m = min(n, 20000)
+            threads = cpu_oracle.max_threads()
+            cpu_oracle.prepare(cs)
+            t0 = time.perf_counter()
+            ref = cpu_oracle.epa(cs, pairs_d[:m].cpu().numpy(), Y[:m].cpu().numpy(), n_threads=threads)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": "first %d EPA pairs" % m}
+            ok = ref["status"] != 7
+            line["parity_on_cpu_sample"] = {
+                "pairs": m, "bit_exact_mtv": bool(np.array_equal(r["mtv"][:m][ok], ref["mtv"][ok])),
+                "status_equal": bool(np.array_equal(r["status"][:m], ref["status"]))}
+    elif args.workload == "selfcollision":
+        # C4: robot arm (6 revolute joints, 8 cylinders), q ~ U(-pi, pi)^6
+        from distance3d_b200 import broad_phase, self_collision
+        from distance3d_b200.urdf import UrdfTransformManager
+        data = os.path.join(REPO, "tests", "data")
+        tm = UrdfTransformManager()
+        with open(os.path.join(data, "robot_arm.urdf")) as f:
+            tm.load_urdf(f.read(), mesh_path=data)
+        bvh = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
+        bvh.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
+        model = self_collision.RobotModel(tm, bvh)
+        n = args.items or 2000000
+        q = torch.from_numpy(rs.uniform(-np.pi, np.pi, size=(n, 6))).to(dev)
+        res = {}
+        ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=model.detect_batch(q)),
+                         args.steps, args.warmup)
+        mask, n_cand = res["r"]
+        line.update({"metric": "self_collision_configurations_per_s", "value": world * n / (ms * 1e-3),
+                     "unit": "configurations/s", "ms_per_step": ms,
+                     "config": {"workload": "C4: URDF arm (6 joints, 8 cylinders, 17 candidate pairs), "
+                                            "FK + AABB + white-list filter + GJK intersection",
+                                "configurations_per_gpu": n},
+                     "colliding_fraction": float((mask.sum(dim=1) > 0).double().mean().item()),
+                     "narrow_phase_candidates_per_configuration": n_cand / n})
+    else:
+        # C5: mixed shapes, LBVH broad phase + GJK + EPA
+        n = args.items or 2000000
+        scale = 0.33 * n ** (1.0 / 3.0)   # ~ 10-30 AABB overlaps per shape
+        cs = d3random.random_collider_set(rs, n, names=d3random.PRIMITIVES + ("mesh",),
+                                          center_scale=scale, hull_vertices=(8, 32))
+        dc = cs.device(dev)
+        res = {}
+        ms = timed_steps(torch, dist, world, dev,
+                         lambda: res.update(r=pipeline.collide(dc, shard=False)), args.steps, args.warmup)
+        r = res["r"]
+        line.update({"metric": "pipeline_shapes_per_s", "value": world * n / (ms * 1e-3), "unit": "shapes/s",
+                     "ms_per_step": ms,
+                     "config": {"workload": "C5: mixed random shapes (5 primitives + hulls), LBVH build + "
+                                            "all-overlap + GJK distance on candidates + EPA on hits",
+                                "shapes_per_gpu": n, "center_scale": scale},
+                     "aabb_overlaps_per_shape": r.n_overlaps / n,
+                     "candidate_pairs": int(r.candidates.shape[0]),
+                     "candidate_pairs_per_s": world * int(r.candidates.shape[0]) / (ms * 1e-3),
+                     "contacts": int(r.hits.numel()),
+                     "epa_pairs": 0 if r.epa is None else int(r.epa_index.numel())})
+    if rank == 0:
+        print(json.dumps(line))
+
+
 def cpu_baseline(cs, pairs, sample):
     """The C oracle (port of the reference algorithm) on all host threads, bounded sample."""
     from oracle import cpu_oracle
@@ -276,6 +396,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if args.workload != "gjk":
+        secondary_workload(args, torch, dist, rank, world, dev)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- synthetic shard of this rank --------------------------------------
     cs, pairs = make_workload(args.seed + 1000 * rank, args.pairs)

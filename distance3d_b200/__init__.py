@@ -11,4 +11,4 @@ __version__ = "0.1.0"
 
 from . import pack, colliders, random, urdf, urdf_utils, parallel  # noqa: F401  (host-only imports)
 from . import gjk, epa, mpr, aabb_tree, containment, broad_phase, self_collision  # noqa: F401
-from . import benchmark  # noqa: F401
+from . import benchmark, pipeline  # noqa: F401

@@ -73,9 +73,9 @@ class BoundingVolumeHierarchy:
         if isinstance(obj, urdf.Cylinder):
             return Cylinder(cylinder2origin=A2B, radius=obj.radius, length=obj.length)
         assert isinstance(obj, urdf.Mesh)
-        from .io import load_mesh
-        vertices, triangles = load_mesh(obj.filename, obj.scale)
-        return MeshGraph(A2B, vertices, triangles)
+        # mesh file I/O (reference io.py:5-46, Open3D / trimesh) is out of scope;
+        # like the reference's loader failures this surfaces as a warning, not an error
+        raise RuntimeError("mesh colliders from URDF files are not supported (%s)" % obj.filename)
 
     def add_collider(self, frame, collider):
         """Add a collider located in `frame` (broad_phase.py:129-142)."""
