@@ -20,6 +20,8 @@
 // are skipped but leave their data behind, the max_faces assertion becomes status
 // D3D_EPA_MAX_FACES, and after max_iter iterations the result is read from the slot
 // that held the last closest face as it looks THEN.
+#include <math.h>
+
 #include "d3d_common.cuh"
 #include "d3d_support.cuh"
 
@@ -28,6 +30,8 @@ namespace {
 struct EpaParams {
     int max_iter, max_loose_edges, max_faces;
     double epsilon;
+    double eps_sq_thr;   // smallest t with sqrt(t) >= epsilon:  sqrt(s) < epsilon  <=>  s < t
+    double half_sq_thr;  // same for 0.5
     const double *Y;
     double *out_mtv;
     uint8_t *out_success;
@@ -62,7 +66,7 @@ struct WarpMem {
 // epa.py:99-102 compute_normal
 D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v2 - v0)); }
 
-__global__ void __launch_bounds__(EPA_WARPS * 32)
+__global__ void __launch_bounds__(EPA_WARPS * 32, 4)
 k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -153,8 +157,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     for (int j = 0; j < 3; ++j) {
                         v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);
                         bool match = false;
-                        if (lane < n_loose)
-                            match = norm_numpy(W.lget(lane, 1) - e0) < eps && norm_numpy(W.lget(lane, 0) - e1) < eps;
+                        if (lane < n_loose) {
+                            {  // np.linalg.norm(x) < eps without the square root (exactly equivalent)
+                                v3 d0 = W.lget(lane, 1) - e0, d1 = W.lget(lane, 0) - e1;
+                                match = dot_blas(d0, d0) < prm.eps_sq_thr && dot_blas(d1, d1) < prm.eps_sq_thr;
+                            }
+                        }
                         unsigned mm = __ballot_sync(FULL, match);
                         int found = mm ? __ffs(mm) - 1 : -1;  // first matching edge wins
                         __syncwarp();
@@ -199,7 +207,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 if (have) {
                     v0 = W.lget(e, 0); v1 = W.lget(e, 1);
                     nrm = face_normal(v0, v1, new_point);
-                    valid = !(norm_numpy(nrm) < 0.5);
+                    valid = !(dot_blas(nrm, nrm) < prm.half_sq_thr);
                 }
                 unsigned vm = __ballot_sync(FULL, valid);
                 unsigned hm = __ballot_sync(FULL, have);
@@ -244,6 +252,14 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
     }
 }
 
+// smallest double t with sqrt(t) >= x (sqrt is correctly rounded and monotone on host and device)
+double sqrt_threshold(double x) {
+    double t = x * x;
+    while (t > 0.0 && sqrt(nextafter(t, 0.0)) >= x) t = nextafter(t, 0.0);
+    while (sqrt(t) < x) t = nextafter(t, 1e308);
+    return t;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,7 +279,8 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
         return d3d_set_error("d3d_epa: max_faces must be in [4, 64] and max_loose_edges in [1, 32]");
     EpaParams prm;
     prm.max_iter = max_iter; prm.max_loose_edges = max_loose_edges; prm.max_faces = max_faces;
-    prm.epsilon = epsilon; prm.Y = Y; prm.out_mtv = out_mtv; prm.out_success = out_success;
+    prm.epsilon = epsilon; prm.eps_sq_thr = sqrt_threshold(epsilon); prm.half_sq_thr = sqrt_threshold(0.5);
+    prm.Y = Y; prm.out_mtv = out_mtv; prm.out_success = out_success;
     prm.out_nfaces = out_nfaces; prm.out_iters = out_iters; prm.out_status = out_status;
     prm.out_faces = out_faces; prm.counter = reinterpret_cast<int *>(workspace);
     D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, stream));

@@ -117,16 +117,29 @@ __global__ void k_bin_scatter(int64_t n, GjkWorkspace w) {
 //   [32,44)  Y  simplex points of A - B   (slot s, component c at 32 + 3 s + c)
 //   [44,56)  P  support points on A
 //   [56,68)  Q  support points on B
-#define GJK_FIELDS 68
+#define GJK_FIELDS 68       // warp kernel: everything in shared memory
+#ifndef GJK_PQ_LOCAL
+#define GJK_PQ_LOCAL 0
+#endif
+#define GJK_FIELDS_THREAD (GJK_PQ_LOCAL ? 44 : 68)
 #define GJK_OFF_B 16
 #define GJK_OFF_Y 32
 #define GJK_OFF_P 44
 #define GJK_OFF_Q 56
 
+// P and Q are touched once per iteration (store) and at the very end (closest points).
+// GJK_PQ_LOCAL = 1 keeps them in per-thread LOCAL memory to make room for a 4th resident
+// CTA per SM; measured on B200 this is slower (1.66e8 vs 1.80e8 pairs/s: the extra warps
+// add instruction-cache pressure, the kernel is fetch-latency bound), so the default
+// is shared memory and 3 CTAs per SM.
 template <int STRIDE>
 struct Simplex {
     double *base;
-    D3D_DEV double &at(int off, int s, int c) const { return base[(off + 3 * s + c) * STRIDE]; }
+    double *pq;  // 24 doubles: P then Q (stride 1)
+    D3D_DEV double &at(int off, int s, int c) const {
+        if (GJK_PQ_LOCAL && STRIDE != 1 && off >= GJK_OFF_P) return pq[(off - GJK_OFF_P) + 3 * s + c];
+        return base[(off + 3 * s + c) * STRIDE];
+    }
     D3D_DEV v3 get(int off, int s) const { return V3(at(off, s, 0), at(off, s, 1), at(off, s, 2)); }
     D3D_DEV void set(int off, int s, v3 v) const { at(off, s, 0) = v.x; at(off, s, 1) = v.y; at(off, s, 2) = v.z; }
 };
@@ -329,17 +342,20 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
 }
 
 #define GJK_THREADS 128
+#define GJK_BLOCKS_PER_SM (GJK_PQ_LOCAL ? 4 : 3)
 #define GJK_CHUNK 256
 #define GJK_REFILL_MIN 8  // refill when at least this many lanes of the warp are idle
 
 // One thread per pair, persistent, lanes refill from a warp-private chunk.
 template <int MODE>
-__global__ void __launch_bounds__(GJK_THREADS, 3)
+__global__ void __launch_bounds__(GJK_THREADS, GJK_BLOCKS_PER_SM)
 k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
     extern __shared__ double smem[];
     double *base = smem + threadIdx.x;
+    double pq_local[24];
     Simplex<GJK_THREADS> S;
     S.base = base;
+    S.pq = pq_local;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
     const int total = w.counters[2];
@@ -399,6 +415,7 @@ k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, G
     double *base = smem + (threadIdx.x >> 5) * GJK_FIELDS;
     Simplex<1> S;
     S.base = base;
+    S.pq = base + GJK_OFF_P;
     const int first = w.counters[2], total = w.counters[3];
     for (;;) {
         int idx = 0;
@@ -430,9 +447,9 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
-    size_t smem = sizeof(double) * GJK_FIELDS * GJK_THREADS;
+    size_t smem = sizeof(double) * GJK_FIELDS_THREAD * GJK_THREADS;
     D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * 3);
+    int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
     k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     int wblocks = (int)d3d_min64((n_pairs + 3) / 4, (int64_t)sms * 3);
     k_gjk_warp<MODE><<<wblocks, GJK_THREADS, 0, stream>>>(*c, pairs, w, prm);

@@ -47,7 +47,12 @@ def _p(a):
 
 
 def max_threads():
-    return int(lib().d3do_max_threads())
+    """Host threads available to this process (torchrun exports OMP_NUM_THREADS=1, so
+    the OpenMP default is not used: the thread count is passed explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def prepare(cs):
