@@ -155,17 +155,28 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
         dc = cs.device()
         aabb = _lib.aabb_device(dc)
         bvh = aabb_tree.Lbvh(aabb)
-        pairs, count = bvh.overlap_self(count_visits=True)
-        visits = bvh.visits()
+        modes = {}
+        for packet in (False, True):   # per-thread vs warp-packet traversal: keep the faster
+            tm = []
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pairs, count = bvh.overlap_self(count_visits=True, packet=packet)
+                e1.record()
+                torch.cuda.synchronize()
+                tm.append(e0.elapsed_time(e1))
+            modes[packet] = (min(tm), bvh.visits())
+            del pairs
+        packet = modes[True][0] < modes[False][0]
+        visits = modes[packet][1]
         buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=aabb.device)
-        del pairs
         tb, tq = [], []
         for it in range(steps + 2):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
             bvh.rebuild()
             e[1].record()
-            bvh.overlap_self(out=buf, capacity=buf.shape[0])
+            bvh.overlap_self(out=buf, packet=packet)
             e[2].record()
             torch.cuda.synchronize()
             if it >= 2:
@@ -175,6 +186,8 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
         b_bytes = n * 176.0
         out[name] = {
             "center_scale": scale, "overlap_pairs": int(count), "node_visits": int(visits),
+            "traversal": "warp packet" if packet else "per thread",
+            "query_ms_per_thread_mode": modes[False][0], "query_ms_packet_mode": modes[True][0],
             "build_ms": tb_ms, "query_ms": tq_ms,
             "build_aabbs_per_s": n / (tb_ms * 1e-3), "overlap_pairs_per_s": count / (tq_ms * 1e-3),
             "queries_per_s": n / (tq_ms * 1e-3),

@@ -40,7 +40,8 @@ def lib():
         L.d3d_last_error_string.restype = ctypes.c_char_p
         L.d3d_gjk_workspace_bytes.restype = c_size
         L.d3d_gjk_workspace_bytes.argtypes = [c_i64]
-        for name in ("d3d_epa_workspace_bytes", "d3d_bvh_workspace_bytes"):
+        for name in ("d3d_epa_workspace_bytes", "d3d_bvh_workspace_bytes",
+                     "d3d_bvh_query_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = c_size
                 getattr(L, name).argtypes = [c_i64]

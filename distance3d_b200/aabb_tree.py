@@ -36,6 +36,7 @@ class Lbvh:
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._visits = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._qws = None
         _lib._check(L.d3d_bvh_build(ptr(self.aabbs), c_i64(self.n), ptr(self.workspace),
                                     c_size(nbytes), _lib.stream_ptr()))
         self._order = None
@@ -56,37 +57,44 @@ class Lbvh:
                                                  _lib.stream_ptr()))
         return out
 
-    def overlap(self, query, capacity=None, order=None, out=None, count_visits=False):
+    def overlap(self, query, capacity=None, order=None, out=None, count_visits=False, packet=None):
         """All (tree index, query index) pairs with overlapping boxes.
 
-        Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  When
-        `capacity` is too small the query is re-run once with the exact size.
+        Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  Two passes on
+        the device: the exact count is known before the pair buffer is allocated (pass
+        `out` to re-use a buffer; it is replaced when too small).  `capacity` is accepted
+        for compatibility and ignored.  `packet`: warp-packet traversal (default: on when the
+        queries are spatially ordered, i.e. `order` is given).
         """
+        if packet is None:
+            packet = order is not None
         torch = _lib.torch_cuda()
         if not isinstance(query, torch.Tensor):
             query = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float64)).to(self.device)
         query = query.reshape(-1, 3, 2).contiguous()
         nq = int(query.shape[0])
-        if capacity is None:
-            capacity = max(1024, 16 * nq)
         L = _lib.lib()
-        while True:
-            if out is None or out.shape[0] < capacity:
-                out = torch.empty((capacity, 2), dtype=torch.int32, device=self.device)
-            _lib._check(L.d3d_bvh_overlap(
-                ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq), ptr(out),
-                c_i64(out.shape[0]), ptr(self._count),
-                ptr(self._visits) if count_visits else None, _lib.stream_ptr()))
-            count = int(self._count.item())
-            if count <= out.shape[0]:
-                return out[:count], count
-            capacity = count
-            out = None
+        qbytes = L.d3d_bvh_query_workspace_bytes(c_i64(nq))
+        if self._qws is None or self._qws.numel() < qbytes:
+            self._qws = torch.empty(qbytes, dtype=torch.uint8, device=self.device)
+        _lib._check(L.d3d_bvh_overlap_count(
+            ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
+            ctypes.c_int(1 if packet else 0), ptr(self._count),
+            ptr(self._visits) if count_visits else None, ptr(self._qws), c_size(self._qws.numel()),
+            _lib.stream_ptr()))
+        count = int(self._count.item())
+        if out is None or out.shape[0] < count:
+            out = torch.empty((max(count, 1), 2), dtype=torch.int32, device=self.device)
+        _lib._check(L.d3d_bvh_overlap_fill(
+            ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
+            ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._qws),
+            _lib.stream_ptr()))
+        return out[:count], count
 
-    def overlap_self(self, capacity=None, out=None, count_visits=False):
+    def overlap_self(self, capacity=None, out=None, count_visits=False, packet=None):
         """Tree against its own leaves, queries walked in Morton order."""
         return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order(), out=out,
-                            count_visits=count_visits)
+                            count_visits=count_visits, packet=packet)
 
     def visits(self):
         """Node records fetched by the last overlap(count_visits=True) call."""

@@ -17,9 +17,11 @@
 //                   search on the common prefix of the (unique) keys; also emits the
 //                   "rope" (next node in depth-first order when a subtree is skipped)
 //   k_refit         bottom-up AABB union, second arrival proceeds (atomic flags)
-//   k_overlap       stackless traversal: node = overlap ? first child : rope; hits are
-//                   appended with a warp-aggregated atomic (ballot + one atomic per
-//                   converged group), exact count even when the buffer overflows
+//   k_overlap<F>    stackless traversal: node = overlap ? first child : rope.  Two passes:
+//                   count hits per query, exclusive scan, then fill -- no atomics, exact
+//                   count before anything is written, deterministic order
+//   k_brute         brute force; its pairs are appended with a warp-aggregated atomic
+//                   (ballot + one atomic per converged group)
 //
 // Node record = 64 bytes (one 128-bit-load quartet): lo[3], hi[3], left, right,
 // rope, parent.  Internal node i in [0, n-1), leaf j (sorted position) at n-1+j;
@@ -115,12 +117,24 @@ __global__ void k_bounds_partial(const double *__restrict__ aabb, int64_t n, dou
     }
 }
 
-__global__ void k_bounds_final(const double *partials, int n_partials, BvhHeader *hdr, int64_t n) {
+__global__ void __launch_bounds__(256)
+k_bounds_final(const double *partials, int n_partials, BvhHeader *hdr, int64_t n) {
+    // 256 threads: component c = threadIdx.x % 6 of partial rows threadIdx.x / 6, +42, ...
+    __shared__ double sh[252];
+    int c = threadIdx.x % 6, r0 = threadIdx.x / 6;
+    if (threadIdx.x < 252) {
+        double v = c < 3 ? 1e300 : -1e300;
+        for (int b = r0; b < n_partials; b += 42) {
+            double x = partials[b * 6 + c];
+            v = c < 3 ? fmin(v, x) : fmax(v, x);
+        }
+        sh[threadIdx.x] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < 6) {
-        double v = partials[threadIdx.x];
-        for (int b = 1; b < n_partials; ++b)
-            v = threadIdx.x < 3 ? fmin(v, partials[b * 6 + threadIdx.x])
-                                : fmax(v, partials[b * 6 + threadIdx.x]);
+        double v = sh[threadIdx.x];
+        for (int r = 1; r < 42; ++r)
+            v = threadIdx.x < 3 ? fmin(v, sh[r * 6 + threadIdx.x]) : fmax(v, sh[r * 6 + threadIdx.x]);
         hdr->bounds[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) { hdr->n = n; hdr->root = 0; }
@@ -171,37 +185,36 @@ k_sort_hist(const unsigned long long *__restrict__ keys, int64_t n, int shift, u
     hist[threadIdx.x * blocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-// Exclusive scan of hist (256 * blocks entries) by one block of 1024 threads.
+// Exclusive scan of hist (256 * blocks entries) by one block of 1024 threads: every
+// thread owns a contiguous run (serial scan), the run totals are scanned across the block.
 __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *hist, int total) {
     __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+    int per = (total + 1023) / 1024;
+    int begin = threadIdx.x * per, end = min(begin + per, total);
+    unsigned sum = 0;
+    for (int i = begin; i < end; ++i) sum += hist[i];
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < total; base += 1024) {
-        int i = base + threadIdx.x;
-        unsigned v = i < total ? hist[i] : 0u;
-        unsigned x = v;
+    unsigned x = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned s = warp_sums[lane];
         for (int off = 1; off < 32; off <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, x, off);
-            if (lane >= off) x += y;
+            unsigned y = __shfl_up_sync(0xffffffffu, s, off);
+            if (lane >= off) s += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned s = warp_sums[lane];
-            for (int off = 1; off < 32; off <<= 1) {
-                unsigned y = __shfl_up_sync(0xffffffffu, s, off);
-                if (lane >= off) s += y;
-            }
-            warp_sums[lane] = s;
-        }
-        __syncthreads();
-        unsigned prefix = carry + (wid ? warp_sums[wid - 1] : 0u) + x - v;
-        if (i < total) hist[i] = prefix;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = prefix + v;
-        __syncthreads();
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    unsigned acc = (wid ? warp_sums[wid - 1] : 0u) + x - sum;
+    for (int i = begin; i < end; ++i) {
+        unsigned v = hist[i];
+        hist[i] = acc;
+        acc += v;
     }
 }
 
@@ -368,34 +381,199 @@ __device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, in
     if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(a, b);
 }
 
+// Traversal of one query box.  FILL = false: count the overlapping leaves;
+// FILL = true: write (object, query) pairs to out[offset ..).  Two passes instead of an
+// atomic append: the single-pass version spent 80 % of its time waiting for the
+// same-address atomic (profiles/r01_ncu_overlap_v1.txt); the two-pass form has no atomics,
+// an exact count before anything is written, and a deterministic output order
+// (queries in Morton order, leaves in depth-first order).
+template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
-          const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
-          unsigned long long *count, unsigned long long *visits) {
+          const int32_t *__restrict__ order, int64_t n_query, unsigned *__restrict__ counts,
+          const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
+          unsigned long long *visits) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_query || hdr->n <= 0) return;
-    unsigned n_visited = 0;
+    if (t >= n_query) return;
     int qi = order ? order[t] : (int)t;
     const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
     double2 qx = __ldg(qb), qy = __ldg(qb + 1), qz = __ldg(qb + 2);
-    int node = hdr->root;
+    int node = hdr->n > 0 ? hdr->root : -1;
+    unsigned n_hits = 0, n_visited = 0;
+    unsigned long long pos = FILL ? offsets[t] : 0ull;
     while (node >= 0) {
         const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
         double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);  // lo.x lo.y | lo.z hi.x | hi.y hi.z
         int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));   // left right rope parent
         // aabb_tree.py:520-527 (closed intervals)
         bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
-        if (ov && link.x < 0) append_pair(-link.x - 1, qi, out_pairs, cap, count);
+        if (ov && link.x < 0) {
+            if (FILL) {
+                if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-link.x - 1, qi);
+                ++pos;
+            } else {
+                ++n_hits;
+            }
+        }
         node = (ov && link.x >= 0) ? link.x : link.z;
         ++n_visited;
     }
-    if (visits) {  // measurement only: node records fetched (roofline traffic term)
+    if (!FILL) counts[t] = n_hits;
+    if (!FILL && visits) {  // measurement only: node records fetched (roofline traffic term)
         unsigned total = n_visited;
         unsigned m = __activemask();
-        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(m, total, off);
-        if (m == 0xffffffffu) { if ((threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)total); }
-        else atomicAdd(visits, (unsigned long long)n_visited);
+        if (m == 0xffffffffu) {
+            for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(m, total, off);
+            if ((threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)total);
+        } else {
+            atomicAdd(visits, (unsigned long long)n_visited);
+        }
     }
+}
+
+// Packet traversal: the 32 queries of a warp (neighbours in Morton order) walk the tree
+// TOGETHER.  The node is fetched once per warp (uniform address, one wavefront) and every
+// lane tests its own box; the warp descends when ANY lane overlaps.  The union of the
+// nodes seen by 32 coherent queries is a small multiple of what one query sees, so the
+// L2 traffic drops by an order of magnitude on dense scenes.  Same results as k_overlap.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
+                 const int32_t *__restrict__ order, int64_t n_query, unsigned *__restrict__ counts,
+                 const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
+                 unsigned long long *visits) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool valid = t < n_query;
+    int qi = valid ? (order ? order[t] : (int)t) : 0;
+    double2 qx = make_double2(1e308, -1e308), qy = qx, qz = qx;  // empty box: never overlaps
+    if (valid) {
+        const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
+        qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
+    }
+    int node = hdr->n > 0 ? hdr->root : -1;  // warp-uniform
+    unsigned n_hits = 0, n_visited = 0;
+    unsigned long long pos = (FILL && valid) ? offsets[t] : 0ull;
+    while (node >= 0) {
+        const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
+        double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
+        if (link.x < 0) {  // leaf (uniform branch)
+            if (ov) {
+                if (FILL) {
+                    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-link.x - 1, qi);
+                    ++pos;
+                } else {
+                    ++n_hits;
+                }
+            }
+            node = link.z;
+        } else {
+            node = __any_sync(0xffffffffu, ov) ? link.x : link.z;
+        }
+        ++n_visited;
+    }
+    if (!FILL && valid) counts[t] = n_hits;
+    if (!FILL && visits && (threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)n_visited);
+}
+
+// ---- exclusive scan counts[u32] -> offsets[u64] (three small kernels) ----------
+#define SCAN_TILE 4096  // 1024 threads x 4 items
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const unsigned *__restrict__ counts, int64_t n, unsigned long long *offsets,
+             unsigned long long *tile_sums) {
+    __shared__ unsigned long long warp_sums[32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    unsigned long long v[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = base + i < n ? counts[base + i] : 0u; sum += v[i]; }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long x = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = warp_sums[lane];
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, s, off);
+            if (lane >= off) s += y;
+        }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    unsigned long long excl = (wid ? warp_sums[wid - 1] : 0ull) + x - sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (base + i < n) offsets[base + i] = excl;
+        excl += v[i];
+    }
+    if (threadIdx.x == 1023) tile_sums[blockIdx.x] = excl;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_top(unsigned long long *tile_sums, int n_tiles, unsigned long long *total) {
+    // single block, serial over chunks of 1024 tiles
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned long long v = i < n_tiles ? tile_sums[i] : 0ull, x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long s = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        unsigned long long prefix = carry + (wid ? warp_sums[wid - 1] : 0ull) + x - v;
+        if (i < n_tiles) tile_sums[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_scan_add(unsigned long long *offsets, int64_t n, const unsigned long long *tile_sums) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) offsets[i] += tile_sums[i / SCAN_TILE];
+}
+
+struct QueryLayout {
+    unsigned *counts;
+    unsigned long long *offsets;
+    unsigned long long *tile_sums;
+    int n_tiles;
+};
+
+inline size_t query_ws_bytes(int64_t nq) {
+    size_t q = (size_t)(nq > 0 ? nq : 1);
+    return au(q * 4) + au(q * 8) + au(((q + SCAN_TILE - 1) / SCAN_TILE) * 8);
+}
+
+inline QueryLayout query_carve(void *ws, int64_t nq) {
+    size_t q = (size_t)(nq > 0 ? nq : 1);
+    QueryLayout L;
+    char *p = reinterpret_cast<char *>(ws);
+    L.counts = reinterpret_cast<unsigned *>(p); p += au(q * 4);
+    L.offsets = reinterpret_cast<unsigned long long *>(p); p += au(q * 8);
+    L.tile_sums = reinterpret_cast<unsigned long long *>(p);
+    L.n_tiles = (int)((q + SCAN_TILE - 1) / SCAN_TILE);
+    return L;
 }
 
 // aabb_tree.py:465-500 all_aabbs_overlap: every (i, j) with overlapping boxes
@@ -455,7 +633,7 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
     if (!aabb) return d3d_set_error("d3d_bvh_build: null aabb");
     int pb = (int)d3d_min64((n + 255) / 256, 1024);
     k_bounds_partial<<<pb, 256, 0, stream>>>(aabb, n, L.partials);
-    k_bounds_final<<<1, 32, 0, stream>>>(L.partials, pb, L.hdr, n);
+    k_bounds_final<<<1, 256, 0, stream>>>(L.partials, pb, L.hdr, n);
     unsigned nb = (unsigned)((n + 255) / 256);
     k_morton<<<nb, 256, 0, stream>>>(aabb, n, L.hdr, L.keys[0]);
     int cur = 0;
@@ -479,20 +657,63 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
     return 0;
 }
 
-int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
-                    int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
-                    unsigned long long *out_visits, void *stream_) {
+size_t d3d_bvh_query_workspace_bytes(int64_t n_query) { return query_ws_bytes(n_query); }
+
+/* pass 1: per-query hit counts + exclusive scan; *out_count = total number of pairs */
+int d3d_bvh_overlap_count(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                          int64_t n_query, int packet, unsigned long long *out_count,
+                          unsigned long long *out_visits, void *query_ws, size_t query_ws_size,
+                          void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap: null argument");
+    if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap_count: null argument");
     D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
     if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
     if (n_query == 0 || n == 0) return 0;
-    if (!query) return d3d_set_error("d3d_bvh_overlap: null query");
+    if (!query || !query_ws) return d3d_set_error("d3d_bvh_overlap_count: null query / workspace");
+    if (query_ws_size < query_ws_bytes(n_query)) return d3d_set_error("d3d_bvh_overlap_count: query workspace too small");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    k_overlap<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query,
-                                                                    out_pairs, cap, out_count, out_visits);
+    QueryLayout Q = query_carve(query_ws, n_query);
+    if (packet)
+        k_overlap_packet<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+            L.nodes, L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
+    else
+        k_overlap<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+            L.nodes, L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
+    k_scan_tiles<<<Q.n_tiles, 1024, 0, stream>>>(Q.counts, n_query, Q.offsets, Q.tile_sums);
+    k_scan_top<<<1, 1024, 0, stream>>>(Q.tile_sums, Q.n_tiles, out_count);
+    k_scan_add<<<(unsigned)((n_query + 255) / 256), 256, 0, stream>>>(Q.offsets, n_query, Q.tile_sums);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+/* pass 2: writes the pairs (positions >= cap are dropped); needs the query workspace of pass 1 */
+int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                         int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                         const void *query_ws, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_query == 0 || n == 0 || cap == 0) return 0;
+    if (!workspace || !query || !out_pairs || !query_ws) return d3d_set_error("d3d_bvh_overlap_fill: null argument");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    QueryLayout Q = query_carve(const_cast<void *>(query_ws), n_query);
+    if (packet)
+        k_overlap_packet<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+            L.nodes, L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
+    else
+        k_overlap<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+            L.nodes, L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                    int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                    unsigned long long *out_count, unsigned long long *out_visits, void *query_ws,
+                    size_t query_ws_size, void *stream_) {
+    int rc = d3d_bvh_overlap_count(workspace, n, query, order, n_query, packet, out_count, out_visits,
+                                   query_ws, query_ws_size, stream_);
+    if (rc) return rc;
+    return d3d_bvh_overlap_fill(workspace, n, query, order, n_query, packet, out_pairs, cap, query_ws,
+                                stream_);
 }
 
 /* sorted object order of the tree (Morton order): out[j] = object index of leaf j */

@@ -123,13 +123,29 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
 
 /* aabb_tree.py:161-181 AabbTree.overlaps_aabb (:381-403 query_overlap) for n_query boxes and
  * :121-159 overlaps_aabb_tree (:344-378 query_overlap_of_other_tree) when the query boxes are
- * the leaves of another tree: appends (tree object index, query index) for every overlapping
- * pair.  `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted
- * queries traverse coherently).  *out_count as for d3d_aabb_overlap_brute.  *out_visits
- * (optional, may be NULL) receives the number of node records fetched (measurement). */
+ * the leaves of another tree: every overlapping (tree object index, query index) pair.
+ *   d3d_bvh_overlap_count  pass 1: counts per query + exclusive scan into the query workspace;
+ *                          *out_count (device, 64-bit) = exact number of pairs
+ *   d3d_bvh_overlap_fill   pass 2: writes out_pairs[cap,2] (positions >= cap are dropped), pairs
+ *                          grouped by query in processing order, leaves in depth-first order
+ *   d3d_bvh_overlap        both passes
+ * `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted queries
+ * traverse coherently).  packet = 1: the 32 queries of a warp traverse together (node fetched
+ * once per warp; use with spatially sorted queries, best on dense scenes), packet = 0: one
+ * independent traversal per thread.  Identical results.  *out_visits (optional) = node
+ * records fetched (measurement). */
+size_t d3d_bvh_query_workspace_bytes(int64_t n_query);
+int d3d_bvh_overlap_count(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                          int64_t n_query, int packet, unsigned long long *out_count,
+                          unsigned long long *out_visits, void *query_ws, size_t query_ws_size,
+                          void *stream);
+int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                         int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                         const void *query_ws, void *stream);
 int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
-                    int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
-                    unsigned long long *out_visits, void *stream);
+                    int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                    unsigned long long *out_count, unsigned long long *out_visits, void *query_ws,
+                    size_t query_ws_size, void *stream);
 
 /* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
 int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);

@@ -52,6 +52,9 @@ def test_random_boxes_vs_oracle_tree(n, scale):
     bvh = aabb_tree.Lbvh(A)
     pairs, count = bvh.overlap_self()
     pairs = pairs.cpu().numpy()
+    # per-thread and warp-packet traversal produce the same list (same order, too)
+    pairs_t, count_t = bvh.overlap_self(packet=False)
+    assert count_t == count and np.array_equal(pairs_t.cpu().numpy(), pairs)
     ref_tree = O.Tree()
     ref_tree.insert_aabbs(A)
     ref = ref_tree.query(A)
