@@ -459,36 +459,40 @@ def main():
     hit_frac = float((res["dist"] == 0.0).mean())
 
     # ---- end to end through the public API with HOST buffers ---------------
-    host = {k: torch.from_numpy(getattr(cs, k)).pin_memory()
-            for k in ("type", "pose", "param", "vert_off", "vert_len", "verts")}
-    host_pairs = torch.from_numpy(pairs).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_pairs.numel() * 4
-    host_out = {k: torch.empty_like(getattr(out, k), device="cpu").pin_memory()
-                for k in ("dist", "closest_a", "closest_b", "status")}
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    # distance3d_b200.stream.GjkDistanceStream: per step the batch's collider arrays and pairs
+    # travel from pinned host memory to the device, d3d_prepare + d3d_gjk_distance run, and
+    # dist / closest points / status travel back; two slots keep PCIe and the SMs busy at once.
+    from distance3d_b200 import stream as d3stream
+    host = d3stream.pin_batch(cs, pairs)
+    pipe = d3stream.GjkDistanceStream(len(cs), n, cs.n_vertices, slots=2, device=dev)
+    e2e_steps = max(4, min(args.steps, 8))
 
-    def e2e_step():
-        for k, v in host.items():
-            getattr(dc, k).copy_(v.reshape(getattr(dc, k).shape), non_blocking=True)
-        pairs_d.copy_(host_pairs, non_blocking=True)
-        _lib.prepare(dc)
-        r = gjk.gjk_distance_batch(dc, pairs_d, out=out)
-        for k, v in host_out.items():
-            v.copy_(getattr(r, k), non_blocking=True)
+    def e2e_run(k_steps):
+        prev = None
+        last = None
+        for _ in range(k_steps):
+            ticket = pipe.submit(host)
+            if prev is not None:
+                last = pipe.result(prev)
+            prev = ticket
+        return pipe.result(prev)
 
-    e2e_steps = max(3, min(args.steps, 5))
-    e2e_step()
+    e2e_res = e2e_run(2)
     barrier()
+    cur = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
+    e0.record(cur)
+    e2e_res = e2e_run(e2e_steps)
+    pipe.drain_into(cur)
+    e1.record(cur)
     barrier()
     t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n / (float(t.item()) * 1e-3)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    e2e_ok = bool(np.array_equal(e2e_res["dist"].numpy(), res["dist"]))
+    del pipe
 
     if rank == 0:
         fp64_peak = measure_fp64_peak(torch, _lib)
@@ -520,12 +524,13 @@ def main():
                 "hbm_frac": per_gpu * BYTES_PER_PAIR / 1e9 / hbm_peak,
             },
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "api": "stream.GjkDistanceStream (2 slots)",
+                    "result_equals_device_run": e2e_ok},
             "gpu_launches": 5 * args.steps,
             "clocks": clocks,
         }
         if not args.no_extra:
-            del dc, out, pairs_d, host, host_out, host_pairs
+            del dc, out, pairs_d, host
             torch.cuda.empty_cache()
             line["broad_phase"] = bench_broad_phase(args, torch, _lib, hbm_peak,
                                                     cpu=not args.no_cpu_baseline)

@@ -163,3 +163,29 @@ def test_meshgraph_brute_force_support_vs_reference_hill_climbing():
     near = g["dist"] < 1e-12
     assert np.array_equal(hit.cpu().numpy()[ok & ~near], g["hit"][ok & ~near])
     compare_distance(cs, g["pairs"], exact_types=EXACT)   # bit-exact against the oracle
+
+
+def test_streamed_host_pipeline_equals_batch_call():
+    from distance3d_b200 import stream as d3stream
+    rs = np.random.RandomState(15)
+    pipe = d3stream.GjkDistanceStream(6000, 3000, 20000, slots=2)
+    with pytest.raises(ValueError):
+        d3stream.GjkDistanceStream(10, 10, 10).submit(d3stream.pin_batch(
+            d3random.random_collider_set(rs, 50), d3random.random_pairs(rs, 50, 5)))
+    batches = []
+    for b in range(5):
+        cs = d3random.random_collider_set(rs, 2000 + 500 * b, names=d3random.PRIMITIVES + ("mesh",))
+        pairs = d3random.random_pairs(rs, len(cs), 1000 + 300 * b)
+        batches.append((cs, pairs, d3stream.pin_batch(cs, pairs)))
+    tickets = []
+    results = []
+    for k, (cs, pairs, host) in enumerate(batches):
+        tickets.append(pipe.submit(host))
+        if k >= 1:
+            results.append({n: v.clone() for n, v in pipe.result(tickets[k - 1]).items()})
+    results.append({n: v.clone() for n, v in pipe.result(tickets[-1]).items()})
+    for (cs, pairs, _), got in zip(batches, results):
+        ref = O.gjk_distance(cs, pairs)
+        assert np.array_equal(got["dist"].numpy(), ref["dist"])
+        assert np.array_equal(got["closest_a"].numpy(), ref["a"])
+        assert np.array_equal(got["status"].numpy(), ref["status"])
