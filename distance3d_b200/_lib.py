@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libd3d_b200.so")
+# D3D_B200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("D3D_B200_LIB") or os.path.join(_HERE, "libd3d_b200.so")
 
 MAX_FLOAT = float(np.finfo(float).max)
 EPSILON = float(np.finfo(float).eps)

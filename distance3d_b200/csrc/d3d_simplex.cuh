@@ -12,7 +12,7 @@ D3D_DEV void bary_line(v3 a, v3 b, double &u, double &v) {
         if (dot_blas(a, a) < dot_blas(b, b)) { u = 1.0; v = 0.0; }
         else { u = 0.0; v = 1.0; }
     } else {
-        v = -dot_blas(a, ab) / denominator;
+        v = ddiv(-dot_blas(a, ab), denominator);
         u = 1.0 - v;
     }
 }
@@ -29,8 +29,8 @@ D3D_DEV void bary_plane(v3 a, v3 b, v3 c, double &u, double &v, double &w) {
             else { bary_line(a, c, u, w); v = 0.0; }
         } else {
             double a0 = dot_blas(a, v0), a1 = dot_blas(a, v1);
-            v = (d01 * a1 - d11 * a0) / denominator;
-            w = (d01 * a0 - d00 * a1) / denominator;
+            v = ddiv(d01 * a1 - d11 * a0, denominator);
+            w = ddiv(d01 * a0 - d00 * a1, denominator);
             u = 1.0 - v - w;
         }
     } else {
@@ -41,8 +41,8 @@ D3D_DEV void bary_plane(v3 a, v3 b, v3 c, double &u, double &v, double &w) {
             else { bary_line(b, c, v, w); u = 0.0; }
         } else {
             double c1 = dot_blas(c, v1), c2 = dot_blas(c, v2);
-            u = (d22 * c1 - d12 * c2) / denominator;
-            v = (d11 * c2 - d12 * c1) / denominator;
+            u = ddiv(d22 * c1 - d12 * c2, denominator);
+            v = ddiv(d11 * c2 - d12 * c1, denominator);
             w = 1.0 - u - v;
         }
     }
@@ -58,7 +58,7 @@ D3D_DEV void bary_tetra(v3 a, v3 b, v3 c, v3 d, double &u, double &v, double &w,
     double vb6 = -triple(a, vac, vad);
     double vc6 = -triple(a, vad, vab);
     double vd6 = -triple(a, vab, vac);
-    double v6 = 1.0 / triple(vab, vac, vad);
+    double v6 = ddiv(1.0, triple(vab, vac, vad));
     u = va6 * v6; v = vb6 * v6; w = vc6 * v6; x = vd6 * v6;
 }
 
@@ -134,7 +134,7 @@ D3D_DEV v3 closest_triangle(v3 a, v3 b, v3 c, int &set) {
         v3 dir = (region == 3) ? ab : ((region == 5) ? ac : bc);
         double num = (region == 3) ? d1 : ((region == 5) ? d2 : d4_d3);
         double den = (region == 3) ? (d1 - d3) : ((region == 5) ? (d2 - d6) : (d4_d3 + d5_d6));
-        double t = num / den;
+        double t = ddiv(num, den);
         return base + dir * t;
     }
     return (region == 1) ? a : ((region == 2) ? b : c);

@@ -187,21 +187,21 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     }
     case D3D_CAPSULE: {  // geometry.py:243-256
         v3 l = rot_t(c, d);
-        double s = sqrt(l.x * l.x + l.y * l.y + l.z * l.z);
+        double s = dsqrt(l.x * l.x + l.y * l.y + l.z * l.z);
         v3 v;
         if (s == 0.0) v = V3(c.p0(), 0.0, 0.0);
-        else v = l * (c.p0() / s);
+        else v = l * ddiv(c.p0(), s);
         if (l.z > 0.0) v.z += 0.5 * c.p1();
         else v.z -= 0.5 * c.p1();
         return xform(c, v);
     }
     case D3D_CYLINDER: {  // geometry.py:194-206
         v3 l = rot_t(c, d);
-        double s = sqrt(l.x * l.x + l.y * l.y);
+        double s = dsqrt(l.x * l.x + l.y * l.y);
         double z = (l.z < 0.0) ? -0.5 * c.p1() : 0.5 * c.p1();
         v3 v;
         if (s == 0.0) v = V3(c.p0(), 0.0, z);
-        else { double k = c.p0() / s; v = V3(l.x * k, l.y * k, z); }
+        else { double k = ddiv(c.p0(), s); v = V3(l.x * k, l.y * k, z); }
         return xform(c, v);
     }
     case D3D_ELLIPSOID: {  // geometry.py:282-284

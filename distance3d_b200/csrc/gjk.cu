@@ -341,10 +341,17 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
     if (prm.out_status) prm.out_status[k] = state;
 }
 
+#ifndef GJK_THREADS
 #define GJK_THREADS 128
+#endif
+#ifndef GJK_BLOCKS_PER_SM
 #define GJK_BLOCKS_PER_SM (GJK_PQ_LOCAL ? 4 : 3)
+#endif
 #define GJK_CHUNK 256
-#define GJK_REFILL_MIN 8  // refill when at least this many lanes of the warp are idle
+#ifndef GJK_REFILL_MIN
+#define GJK_REFILL_MIN 8
+#endif
+// refill when at least this many lanes of the warp are idle
 
 // One thread per pair, persistent, lanes refill from a warp-private chunk.
 template <int MODE>
