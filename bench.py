@@ -317,7 +317,7 @@ def secondary_workload(args, torch, dist, rank, world, dev):
         n = args.items or 2000000
         scale = 0.33 * n ** (1.0 / 3.0)   # ~ 10-30 AABB overlaps per shape
         cs = d3random.random_collider_set(rs, n, names=d3random.PRIMITIVES + ("mesh",),
-                                          center_scale=scale, hull_vertices=(8, 32))
+                                          center_scale=scale, hull_vertices=(10, 10))
         dc = cs.device(dev)
         res = {}
         ms = timed_steps(torch, dist, world, dev,
@@ -325,7 +325,7 @@ def secondary_workload(args, torch, dist, rank, world, dev):
         r = res["r"]
         line.update({"metric": "pipeline_shapes_per_s", "value": world * n / (ms * 1e-3), "unit": "shapes/s",
                      "ms_per_step": ms,
-                     "config": {"workload": "C5: mixed random shapes (5 primitives + hulls), LBVH build + "
+                     "config": {"workload": "C5: mixed random shapes (5 primitives + 10-vertex hulls), LBVH build + "
                                             "all-overlap + GJK distance on candidates + EPA on hits",
                                 "shapes_per_gpu": n, "center_scale": scale},
                      "aabb_overlaps_per_shape": r.n_overlaps / n,

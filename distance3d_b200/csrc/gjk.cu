@@ -15,11 +15,17 @@
 //   k_gjk<MODE,32> one WARP per pair for wide hulls: vertex max-dot by strided
 //                 scan + __shfl_xor reduction (lowest index wins ties), the
 //                 simplex solve is replicated on all lanes
+#include <stdlib.h>
+
 #include "d3d_common.cuh"
 #include "d3d_simplex.cuh"
 #include "d3d_support.cuh"
 
-#define D3D_THREAD_HULL_MAX 16
+// hulls / meshes with more vertices than this go to the warp-per-pair kernel (measured on
+// B200: thread-per-pair wins up to ~64 vertices, 103 vs 47 Mpairs/s at 17-32 vertices; the
+// warp kernel wins 3x at 64-256 vertices)
+// (runtime override for tuning: environment variable D3D_THREAD_HULL_MAX)
+#define D3D_THREAD_HULL_MAX_DEFAULT 64
 #define D3D_NBINS (D3D_NUM_TYPES * D3D_NUM_TYPES + 1)
 #define D3D_WIDE_BIN (D3D_NUM_TYPES * D3D_NUM_TYPES)
 
@@ -51,13 +57,13 @@ inline GjkWorkspace carve(void *ws, int64_t n) {
     return w;
 }
 
-__device__ __forceinline__ bool is_wide(const d3d_colliders &c, int i) {
+__device__ __forceinline__ bool is_wide(const d3d_colliders &c, int i, int hull_max) {
     int t = __ldg(c.type + i);
-    return (t == D3D_HULL || t == D3D_MESH) && __ldg(c.vert_len + i) > D3D_THREAD_HULL_MAX;
+    return (t == D3D_HULL || t == D3D_MESH) && __ldg(c.vert_len + i) > hull_max;
 }
 
 __global__ void k_pair_keys(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n,
-                            GjkWorkspace w) {
+                            GjkWorkspace w, int hull_max) {
     __shared__ int sh[D3D_NBINS];
     for (int i = threadIdx.x; i < D3D_NBINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -65,7 +71,7 @@ __global__ void k_pair_keys(d3d_colliders c, const int32_t *__restrict__ pairs, 
          k += (int64_t)gridDim.x * blockDim.x) {
         int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
         int key;
-        if (is_wide(c, pr.x) || is_wide(c, pr.y)) key = D3D_WIDE_BIN;
+        if (is_wide(c, pr.x, hull_max) || is_wide(c, pr.y, hull_max)) key = D3D_WIDE_BIN;
         else key = __ldg(c.type + pr.x) * D3D_NUM_TYPES + __ldg(c.type + pr.y);
         w.keys[k] = (uint8_t)key;
         atomicAdd(&sh[key], 1);
@@ -451,7 +457,12 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 4096, stream));
     int sms = d3d_sm_count();
     int bin_blocks = (int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8);
-    k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w);
+    static int hull_max = -1;
+    if (hull_max < 0) {
+        const char *e = getenv("D3D_THREAD_HULL_MAX");
+        hull_max = e ? atoi(e) : D3D_THREAD_HULL_MAX_DEFAULT;
+    }
+    k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
     size_t smem = sizeof(double) * GJK_FIELDS_THREAD * GJK_THREADS;

@@ -1,7 +1,7 @@
 import sys, time; sys.path.insert(0,"/root/repo")
 import numpy as np, torch
 from distance3d_b200 import gjk, random as R
-names=["sphere","ellipsoid","capsule","cylinder","box"]
+names=sys.argv[1].split(",") if len(sys.argv)>1 else ["sphere","ellipsoid","capsule","cylinder","box"]
 n=1<<20
 def run(cs,pairs,label):
     dc=cs.device(); pd=torch.from_numpy(pairs).cuda()
@@ -24,9 +24,10 @@ for a in names:
         import numpy as np
         type_=np.concatenate([csa.type,csb.type]); pose=np.concatenate([csa.pose,csb.pose]); param=np.concatenate([csa.param,csb.param])
         vl=np.concatenate([csa.vert_len,csb.vert_len]); vo=np.zeros(2*n,dtype=np.int64); vo[1:]=np.cumsum(vl[:-1])
-        cs=ColliderSet(type_,pose,param,vo,vl,np.zeros((int(vl.sum()),3)))
+        cs=ColliderSet(type_,pose,param,vo,vl,np.concatenate([csa.verts[:int(csa.vert_len.sum())] if csa.vert_len.sum() else np.zeros((0,3)), csb.verts[:int(csb.vert_len.sum())] if csb.vert_len.sum() else np.zeros((0,3))]))
         pairs=np.stack([np.arange(n),np.arange(n)+n],axis=1).astype(np.int32)
         run(cs,pairs,a+"-"+b)
 rs=np.random.RandomState(1)
 cs=R.random_collider_set(rs,2*n,names=R.PRIMITIVES); pairs=np.arange(2*n,dtype=np.int32).reshape(n,2)
 run(cs,pairs,"mix")
+cs=R.random_collider_set(rs,2*n,names=R.PRIMITIVES+("mesh",)); run(cs,pairs,"mix6 (10-vertex hulls)")
