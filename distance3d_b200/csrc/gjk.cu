@@ -207,11 +207,15 @@ D3D_DEV double max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
     return m;
 }
 
-// One iteration of _distance_loop (MODE 0, _gjk_jolt.py:224-288) or
-// _intersection_loop (MODE 1, _gjk_jolt.py:83-135).
+// ---------------------------------------------------------------------------
+// One GJK iteration = gjk_pre (supports, early exits, add the point) -> closest point of the
+// simplex to the origin -> gjk_post (bookkeeping of _distance_loop / _intersection_loop).
+
+// First half of _distance_loop (MODE 0, _gjk_jolt.py:228-242) / _intersection_loop (MODE 1,
+// :86-97).  Returns true when the simplex solve is needed.
 template <int MODE, int G, int STRIDE>
-D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
-    if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return; }
+D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
+    if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return false; }
     ++s.iters;
     v3 p = support_call<G, STRIDE>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
     v3 q = support_call<G, STRIDE>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
@@ -220,22 +224,23 @@ D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     if (MODE == 0) {
         if (dot < 0.0 && dot * dot > s.v_len_sq * prm.max_distance_squared) {
             s.state = D3D_CLIPPED;
-            return;
+            return false;
         }
     } else {
-        if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return; }
+        if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return false; }
     }
     S.set(GJK_OFF_Y, s.n_points, w);
     if (MODE == 0) { S.set(GJK_OFF_P, s.n_points, p); S.set(GJK_OFF_Q, s.n_points, q); }
     ++s.n_points;
+    return true;
+}
 
+// Second half (_gjk_jolt.py:244-288 / :100-135) given the solver's answer.
+template <int MODE, int STRIDE>
+D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, bool ok,
+                      v3 v_new, double v_len_sq_new, int simplex) {
     v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
        y3 = S.get(GJK_OFF_Y, 3);
-    v3 v_new;
-    double v_len_sq_new;
-    int simplex;
-    bool ok = closest_point_to_origin(y0, y1, y2, y3, s.n_points, s.prev_v_len_sq, v_new,
-                                      v_len_sq_new, simplex);
     if (ok) {
         s.sd = v_new;
         s.v_len_sq = v_len_sq_new;
@@ -293,6 +298,127 @@ D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
             }
         s.n_points = nn;
     }
+}
+
+// Whole iteration with the per-lane solver (warp-per-pair kernel: all lanes are in step).
+template <int MODE, int G, int STRIDE>
+D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
+    if (!gjk_pre<MODE, G, STRIDE>(s, S, prm, lane)) return;
+    v3 v_new;
+    double v_len_sq_new;
+    int simplex;
+    bool ok = closest_point_to_origin(S.get(GJK_OFF_Y, 0), S.get(GJK_OFF_Y, 1), S.get(GJK_OFF_Y, 2),
+                                      S.get(GJK_OFF_Y, 3), s.n_points, s.prev_v_len_sq, v_new,
+                                      v_len_sq_new, simplex);
+    gjk_post<MODE, STRIDE>(s, S, prm, ok, v_new, v_len_sq_new, simplex);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-collective simplex solve for the thread-per-pair kernel.
+//
+// A lane with a 3-point simplex has one candidate triangle, a lane with a tetrahedron
+// one to four (the faces the origin lies outside of), lanes with 1-2 points none; walking
+// them lane by lane leaves most of the warp idle (5.6 active threads per instruction in
+// closest_triangle, profiles/r01_ncu_k_gjk_thread_v3_outlined_div.txt).  Here the
+// (owner lane, face) work items of the whole warp are listed in shared memory and the warp
+// evaluates them 32 at a time: any lane can take any item because the simplex points of
+// every pair live in shared memory.  Owners then fold the results of their own items in
+// ascending face order with the reference's strict '<' rule, so the outcome is bit-identical
+// to closest_point_tetrahedron (_gjk_jolt.py:573-631).
+struct TriResult {
+    double qx, qy, qz, dist_sq;
+};
+struct WarpScratch {
+    TriResult *res;       // [32] results of the current round
+    int *set;             // [32] feature sets of the current round (already in tetra numbering)
+    unsigned char *desc;  // [128] item -> (owner lane << 2 | face)
+};
+#define GJK_SCRATCH_BYTES (32 * sizeof(TriResult) + 32 * sizeof(int) + 128)
+
+template <int STRIDE>
+D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, int n_points,
+                                          double prev_v_len_sq, const WarpScratch &W, int lane,
+                                          v3 &v_out, double &v_len_sq_out, int &set_out) {
+    const unsigned FULL = 0xffffffffu;
+    v3 v = V3(0.0, 0.0, 0.0);
+    int set = 1;
+    int faces = 0;  // candidate faces of this lane (bit f)
+    if (solve) {
+        if (n_points == 1) {
+            v = S.get(GJK_OFF_Y, 0);
+        } else if (n_points == 2) {
+            v = closest_line(S.get(GJK_OFF_Y, 0), S.get(GJK_OFF_Y, 1), set);
+        } else if (n_points == 3) {
+            faces = 1;
+        } else {
+            faces = origin_outside_planes(S.get(GJK_OFF_Y, 0), S.get(GJK_OFF_Y, 1), S.get(GJK_OFF_Y, 2),
+                                          S.get(GJK_OFF_Y, 3));
+            set = 0xf;  // inside all planes unless a face says otherwise
+        }
+    }
+    // exclusive scan of the face counts over the warp
+    int cnt = __popc(faces);
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int y = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += y;
+    }
+    int first = incl - cnt;
+    int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) {
+        // nothing to share: finish locally
+    } else {
+        int j = first;
+        for (int todo = faces; todo; todo &= todo - 1) W.desc[j++] = (unsigned char)((lane << 2) | (__ffs(todo) - 1));
+        __syncwarp();
+        double best_dist_sq = D3D_MAX_FLOAT;
+        for (int base = 0; base < total; base += 32) {
+            int item = base + lane;
+            if (item < total) {
+                int d = W.desc[item];
+                int o = d >> 2, f = d & 3;
+                Simplex<STRIDE> So;
+                So.base = S.base + (o - lane);
+                So.pq = nullptr;
+                // faces: abc, acd, adb, bdc (slot indices packed two bits each)
+                const int ia = (f == 3) ? 1 : 0;
+                const int ib = (f == 0) ? 1 : ((f == 1) ? 2 : 3);
+                const int ic = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2));
+                int sset;
+                v3 q = closest_triangle(So.get(GJK_OFF_Y, ia), So.get(GJK_OFF_Y, ib), So.get(GJK_OFF_Y, ic), sset);
+                int mapped;
+                if (f == 0) mapped = sset;
+                else if (f == 1) mapped = (sset & 1) + ((sset & 6) << 1);
+                else if (f == 2) mapped = (sset & 1) + ((sset & 2) << 2) + ((sset & 4) >> 1);
+                else mapped = ((sset & 1) << 1) + ((sset & 2) << 2) + (sset & 4);
+                TriResult r;
+                r.qx = q.x; r.qy = q.y; r.qz = q.z; r.dist_sq = dot_blas(q, q);
+                W.res[lane] = r;
+                W.set[lane] = mapped;
+            }
+            __syncwarp();
+            // owners fold their items of this round, ascending face order
+            int lo = max(first, base), hi = min(first + cnt, base + 32);
+            for (int it = lo; it < hi; ++it) {
+                TriResult r = W.res[it - base];
+                int f = W.desc[it] & 3;
+                if (f == 0 || r.dist_sq < best_dist_sq) {
+                    best_dist_sq = r.dist_sq;
+                    v = V3(r.qx, r.qy, r.qz);
+                    set = W.set[it - base];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (!solve) return false;
+    double v_len_sq = dot_blas(v, v);
+    if (v_len_sq < prev_v_len_sq) {
+        v_out = v; v_len_sq_out = v_len_sq; set_out = set;
+        return true;
+    }
+    return false;
 }
 
 // Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).
@@ -369,6 +495,14 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
     Simplex<GJK_THREADS> S;
     S.base = base;
     S.pq = pq_local;
+    WarpScratch W;
+    {
+        char *scratch = reinterpret_cast<char *>(smem + GJK_FIELDS_THREAD * GJK_THREADS) +
+                        (threadIdx.x >> 5) * GJK_SCRATCH_BYTES;
+        W.res = reinterpret_cast<TriResult *>(scratch);
+        W.set = reinterpret_cast<int *>(scratch + 32 * sizeof(TriResult));
+        W.desc = reinterpret_cast<unsigned char *>(scratch + 32 * sizeof(TriResult) + 32 * sizeof(int));
+    }
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
     const int total = w.counters[2];
@@ -411,10 +545,14 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
             run_mask = __ballot_sync(0xffffffffu, running);
             if (run_mask == 0) break;
         }
-        if (running) {
-            gjk_step<MODE, 1, GJK_THREADS>(s, S, prm, 0);
-            if (s.state != D3D_UNKNOWN) { running = false; finished = true; }
-        }
+        bool solve = running && gjk_pre<MODE, 1, GJK_THREADS>(s, S, prm, 0);
+        v3 v_new = V3(0.0, 0.0, 0.0);
+        double v_len_sq_new = 0.0;
+        int simplex = 0;
+        bool ok = closest_point_to_origin_warp<GJK_THREADS>(solve, S, s.n_points, s.prev_v_len_sq, W, lane,
+                                                            v_new, v_len_sq_new, simplex);
+        if (solve) gjk_post<MODE, GJK_THREADS>(s, S, prm, ok, v_new, v_len_sq_new, simplex);
+        if (running && s.state != D3D_UNKNOWN) { running = false; finished = true; }
     }
 }
 
@@ -465,7 +603,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
-    size_t smem = sizeof(double) * GJK_FIELDS_THREAD * GJK_THREADS;
+    size_t smem = sizeof(double) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
     D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
     k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
