@@ -458,6 +458,20 @@ def main():
     mean_iters = float(res["iters"].mean())
     hit_frac = float((res["dist"] == 0.0).mean())
 
+    # ---- opt-in fp32 arithmetic mode (extra, not the headline) ---------------
+    out32 = gjk.gjk_distance_batch(dc, pairs_d, dtype="f32")
+    ms32 = timed_steps(torch, dist, world, dev,
+                       lambda: gjk.gjk_distance_batch(dc, pairs_d, out=out32, dtype="f32"), 5, 3)
+    d32 = out32.dist.cpu().numpy()
+    v32 = (out32.status.cpu().numpy() <= 1) & (res["status"] <= 1)
+    err32 = np.abs(d32[v32] - res["dist"][v32])
+    fp32_mode = {"value": world * n / (ms32 * 1e-3), "unit": "pairs/s", "dtype": "f32",
+                 "mean_gjk_iterations": float(out32.iters.double().mean().item()),
+                 "abs_distance_error_vs_f64": {"p50": float(np.quantile(err32, 0.5)),
+                                               "p999": float(np.quantile(err32, 0.999)),
+                                               "max": float(err32.max())}}
+    del out32
+
     # ---- end to end through the public API with HOST buffers ---------------
     # distance3d_b200.stream.GjkDistanceStream: per step the batch's collider arrays and pairs
     # travel from pinned host memory to the device, d3d_prepare + d3d_gjk_distance run, and
@@ -527,6 +541,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "api": "stream.GjkDistanceStream (2 slots)",
                     "result_equals_device_run": e2e_ok},
             "gpu_launches": 5 * args.steps,
+            "fp32_mode": fp32_mode,
             "clocks": clocks,
         }
         if not args.no_extra:

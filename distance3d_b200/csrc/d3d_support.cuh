@@ -16,24 +16,24 @@ struct Collider {
     int type;
     int nv;
     const double *V;  // vertex range in the pool (box / hull: world frame, mesh: local)
-    double m_margin;
-    double m[15];     // r00 r01 r02 tx  r10 r11 r12 ty  r20 r21 r22 tz  p0 p1 p2
-    D3D_DEV double r00() const { return m[0]; }
-    D3D_DEV double r01() const { return m[1]; }
-    D3D_DEV double r02() const { return m[2]; }
-    D3D_DEV double tx() const { return m[3]; }
-    D3D_DEV double r10() const { return m[4]; }
-    D3D_DEV double r11() const { return m[5]; }
-    D3D_DEV double r12() const { return m[6]; }
-    D3D_DEV double ty() const { return m[7]; }
-    D3D_DEV double r20() const { return m[8]; }
-    D3D_DEV double r21() const { return m[9]; }
-    D3D_DEV double r22() const { return m[10]; }
-    D3D_DEV double tz() const { return m[11]; }
-    D3D_DEV double p0() const { return m[12]; }
-    D3D_DEV double p1() const { return m[13]; }
-    D3D_DEV double p2() const { return m[14]; }
-    D3D_DEV double margin() const { return m_margin; }
+    real m_margin;
+    real m[15];     // r00 r01 r02 tx  r10 r11 r12 ty  r20 r21 r22 tz  p0 p1 p2
+    D3D_DEV real r00() const { return m[0]; }
+    D3D_DEV real r01() const { return m[1]; }
+    D3D_DEV real r02() const { return m[2]; }
+    D3D_DEV real tx() const { return m[3]; }
+    D3D_DEV real r10() const { return m[4]; }
+    D3D_DEV real r11() const { return m[5]; }
+    D3D_DEV real r12() const { return m[6]; }
+    D3D_DEV real ty() const { return m[7]; }
+    D3D_DEV real r20() const { return m[8]; }
+    D3D_DEV real r21() const { return m[9]; }
+    D3D_DEV real r22() const { return m[10]; }
+    D3D_DEV real tz() const { return m[11]; }
+    D3D_DEV real p0() const { return m[12]; }
+    D3D_DEV real p1() const { return m[13]; }
+    D3D_DEV real p2() const { return m[14]; }
+    D3D_DEV real margin() const { return m_margin; }
 };
 
 // The same record staged in shared memory: field f of the owning thread lives at
@@ -45,24 +45,24 @@ struct ColliderSmem {
     int type;
     int nv;
     const double *V;
-    const double *base;
-    D3D_DEV double f(int i) const { return base[i * STRIDE]; }
-    D3D_DEV double r00() const { return f(0); }
-    D3D_DEV double r01() const { return f(1); }
-    D3D_DEV double r02() const { return f(2); }
-    D3D_DEV double tx() const { return f(3); }
-    D3D_DEV double r10() const { return f(4); }
-    D3D_DEV double r11() const { return f(5); }
-    D3D_DEV double r12() const { return f(6); }
-    D3D_DEV double ty() const { return f(7); }
-    D3D_DEV double r20() const { return f(8); }
-    D3D_DEV double r21() const { return f(9); }
-    D3D_DEV double r22() const { return f(10); }
-    D3D_DEV double tz() const { return f(11); }
-    D3D_DEV double p0() const { return f(12); }
-    D3D_DEV double p1() const { return f(13); }
-    D3D_DEV double p2() const { return f(14); }
-    D3D_DEV double margin() const { return f(15); }
+    const real *base;
+    D3D_DEV real f(int i) const { return base[i * STRIDE]; }
+    D3D_DEV real r00() const { return f(0); }
+    D3D_DEV real r01() const { return f(1); }
+    D3D_DEV real r02() const { return f(2); }
+    D3D_DEV real tx() const { return f(3); }
+    D3D_DEV real r10() const { return f(4); }
+    D3D_DEV real r11() const { return f(5); }
+    D3D_DEV real r12() const { return f(6); }
+    D3D_DEV real ty() const { return f(7); }
+    D3D_DEV real r20() const { return f(8); }
+    D3D_DEV real r21() const { return f(9); }
+    D3D_DEV real r22() const { return f(10); }
+    D3D_DEV real tz() const { return f(11); }
+    D3D_DEV real p0() const { return f(12); }
+    D3D_DEV real p1() const { return f(13); }
+    D3D_DEV real p2() const { return f(14); }
+    D3D_DEV real margin() const { return f(15); }
 };
 
 // 128-bit vectorised loads of the 4x4 pose (rows 0..2) and the parameters.
@@ -71,7 +71,7 @@ D3D_DEV Collider load_collider(const d3d_colliders &c, int64_t i) {
     o.type = __ldg(c.type + i);
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
-    o.m_margin = c.margin ? __ldg(c.margin + i) : 0.0;
+    o.m_margin = c.margin ? __ldg(c.margin + i) : R(0.0);
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -86,7 +86,7 @@ D3D_DEV Collider load_collider(const d3d_colliders &c, int64_t i) {
 
 // Stage collider i into the calling thread's shared-memory record.
 template <int STRIDE>
-D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, double *base) {
+D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, real *base) {
     ColliderSmem<STRIDE> o;
     o.type = __ldg(c.type + i);
     o.nv = __ldg(c.vert_len + i);
@@ -103,7 +103,7 @@ D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, d
     base[12 * STRIDE] = __ldg(p);
     base[13 * STRIDE] = __ldg(p + 1);
     base[14 * STRIDE] = __ldg(p + 2);
-    base[15 * STRIDE] = c.margin ? __ldg(c.margin + i) : 0.0;
+    base[15 * STRIDE] = c.margin ? __ldg(c.margin + i) : R(0.0);
     return o;
 }
 
@@ -123,8 +123,8 @@ D3D_DEV v3 xform(const C &c, v3 v) {
 // geometry.py:138-157: vertex i of a box, bit k of i selects +0.5 on axis (2-k)
 template <class C>
 D3D_DEV v3 box_vertex(const C &c, int i) {
-    v3 l = V3((i & 4) ? 0.5 * c.p0() : -0.5 * c.p0(), (i & 2) ? 0.5 * c.p1() : -0.5 * c.p1(),
-              (i & 1) ? 0.5 * c.p2() : -0.5 * c.p2());
+    v3 l = V3((i & 4) ? R(0.5) * c.p0() : -R(0.5) * c.p0(), (i & 2) ? R(0.5) * c.p1() : -R(0.5) * c.p1(),
+              (i & 1) ? R(0.5) * c.p2() : -R(0.5) * c.p2());
     return V3(c.tx() + dot_blas(l, V3(c.r00(), c.r01(), c.r02())), c.ty() + dot_blas(l, V3(c.r10(), c.r11(), c.r12())),
               c.tz() + dot_blas(l, V3(c.r20(), c.r21(), c.r22())));
 }
@@ -137,23 +137,23 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
     if (n == 1) return 0;
     if (G == 1) {
         int bi = 0;
-        double best = gemv_row(__ldg(V), __ldg(V + 1), __ldg(V + 2), d);
+        real best = gemv_row(__ldg(V), __ldg(V + 1), __ldg(V + 2), d);
         for (int i = 1; i < n; ++i) {
-            double val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
+            real val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
             if (val > best) { best = val; bi = i; }
         }
         return bi;
     }
-    double best = 0.0;
+    real best = R(0.0);
     int bi = 0x7fffffff;
     bool have = false;
     for (int i = lane; i < n; i += G) {
-        double val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
+        real val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
         if (!have || val > best) { best = val; bi = i; have = true; }
     }
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, best, off, G);
+        real ov = __shfl_xor_sync(0xffffffffu, best, off, G);
         int oi = __shfl_xor_sync(0xffffffffu, bi, off, G);
         bool ohave = __shfl_xor_sync(0xffffffffu, (int)have, off, G);
         if (ohave && (!have || ov > best || (ov == best && oi < bi))) {
@@ -166,12 +166,12 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
 // utils.py:78-122
 D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
     if (fabs(n.x) >= fabs(n.y)) {
-        double len = sqrt(n.x * n.x + n.z * n.z);
-        x = V3(-n.z / len, 0.0, n.x / len);
+        real len = sqrt(n.x * n.x + n.z * n.z);
+        x = V3(-n.z / len, R(0.0), n.x / len);
         y = V3(n.y * x.z, n.z * x.x - n.x * x.z, -n.y * x.x);
     } else {
-        double len = sqrt(n.y * n.y + n.z * n.z);
-        x = V3(0.0, n.z / len, -n.y / len);
+        real len = sqrt(n.y * n.y + n.z * n.z);
+        x = V3(R(0.0), n.z / len, -n.y / len);
         y = V3(n.y * x.z - n.z * x.y, -n.x * x.z, n.x * x.y);
     }
 }
@@ -180,28 +180,28 @@ template <int G, class C>
 D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     switch (c.type) {
     case D3D_SPHERE: {  // geometry.py:341-346
-        double s = norm3(d);
+        real s = norm3(d);
         v3 ctr = V3(c.tx(), c.ty(), c.tz());
-        if (s == 0.0) return ctr + V3(0.0, 0.0, c.p0());
+        if (s == R(0.0)) return ctr + V3(R(0.0), R(0.0), c.p0());
         return ctr + (d / s) * c.p0();
     }
     case D3D_CAPSULE: {  // geometry.py:243-256
         v3 l = rot_t(c, d);
-        double s = dsqrt(l.x * l.x + l.y * l.y + l.z * l.z);
+        real s = dsqrt(l.x * l.x + l.y * l.y + l.z * l.z);
         v3 v;
-        if (s == 0.0) v = V3(c.p0(), 0.0, 0.0);
+        if (s == R(0.0)) v = V3(c.p0(), R(0.0), R(0.0));
         else v = l * ddiv(c.p0(), s);
-        if (l.z > 0.0) v.z += 0.5 * c.p1();
-        else v.z -= 0.5 * c.p1();
+        if (l.z > R(0.0)) v.z += R(0.5) * c.p1();
+        else v.z -= R(0.5) * c.p1();
         return xform(c, v);
     }
     case D3D_CYLINDER: {  // geometry.py:194-206
         v3 l = rot_t(c, d);
-        double s = dsqrt(l.x * l.x + l.y * l.y);
-        double z = (l.z < 0.0) ? -0.5 * c.p1() : 0.5 * c.p1();
+        real s = dsqrt(l.x * l.x + l.y * l.y);
+        real z = (l.z < R(0.0)) ? -R(0.5) * c.p1() : R(0.5) * c.p1();
         v3 v;
-        if (s == 0.0) v = V3(c.p0(), 0.0, z);
-        else { double k = ddiv(c.p0(), s); v = V3(l.x * k, l.y * k, z); }
+        if (s == R(0.0)) v = V3(c.p0(), R(0.0), z);
+        else { real k = ddiv(c.p0(), s); v = V3(l.x * k, l.y * k, z); }
         return xform(c, v);
     }
     case D3D_ELLIPSOID: {  // geometry.py:282-284
@@ -212,11 +212,11 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     case D3D_BOX: {  // colliders.py:132 over the 8 vertices of geometry.py:157
         if (G == 1) {
             v3 bestv = box_vertex(c, 0);
-            double best = gemv_row(bestv.x, bestv.y, bestv.z, d);
+            real best = gemv_row(bestv.x, bestv.y, bestv.z, d);
 #pragma unroll 1
             for (int i = 1; i < 8; ++i) {
                 v3 v = box_vertex(c, i);
-                double val = gemv_row(v.x, v.y, v.z, d);
+                real val = gemv_row(v.x, v.y, v.z, d);
                 if (val > best) { best = val; bestv = v; }
             }
             return bestv;
@@ -234,40 +234,40 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         v3 n = V3(c.r02(), c.r12(), c.r22());
         v3 x, y;
         plane_basis(n, x, y);
-        v3 pt = V3(dot_blas(x, d), dot_blas(y, d), 0.0);
-        double nrm = norm3(pt);
-        if (nrm == 0.0) return ctr;
+        v3 pt = V3(dot_blas(x, d), dot_blas(y, d), R(0.0));
+        real nrm = norm3(pt);
+        if (nrm == R(0.0)) return ctr;
         pt = pt * (c.p0() / nrm);
         return V3(ctr.x + gemv_row(x.x, y.x, n.x, pt), ctr.y + gemv_row(x.y, y.y, n.y, pt),
                   ctr.z + gemv_row(x.z, y.z, n.z, pt));
     }
     case D3D_ELLIPSE: {  // geometry.py:412-414
         v3 a0 = V3(c.r00(), c.r10(), c.r20()), a1 = V3(c.r01(), c.r11(), c.r21());
-        double l0 = gemv_row(a0.x, a0.y, a0.z, d), l1 = gemv_row(a1.x, a1.y, a1.z, d);
-        double w0 = c.p0() * l0, w1 = c.p1() * l1;
-        double nrm = norm_dd(w0, w1, 0.0);
-        if (nrm != 0.0) { w0 = w0 / nrm; w1 = w1 / nrm; }
+        real l0 = gemv_row(a0.x, a0.y, a0.z, d), l1 = gemv_row(a1.x, a1.y, a1.z, d);
+        real w0 = c.p0() * l0, w1 = c.p1() * l1;
+        real nrm = norm_dd(w0, w1, R(0.0));
+        if (nrm != R(0.0)) { w0 = w0 / nrm; w1 = w1 / nrm; }
         w0 *= c.p0(); w1 *= c.p1();
         return V3(c.tx() + fma(w1, a1.x, w0 * a0.x), c.ty() + fma(w1, a1.y, w0 * a0.y),
                   c.tz() + fma(w1, a1.z, w0 * a0.z));
     }
     case D3D_CONE: {  // geometry.py:443-454
         v3 l = rot_t(c, d);
-        v3 dp = V3(l.x, l.y, 0.0);
-        double nrm = norm3(dp);
-        if (nrm == 0.0) dp = V3(0.0, 0.0, 0.0);
+        v3 dp = V3(l.x, l.y, R(0.0));
+        real nrm = norm3(dp);
+        if (nrm == R(0.0)) dp = V3(R(0.0), R(0.0), R(0.0));
         else dp = dp * (c.p0() / nrm);
-        v3 pt = (dot_blas(l, dp) >= l.z * c.p1()) ? dp : V3(0.0, 0.0, c.p1());
+        v3 pt = (dot_blas(l, dp) >= l.z * c.p1()) ? dp : V3(R(0.0), R(0.0), c.p1());
         return xform(c, pt);
     }
     }
-    return V3(0.0, 0.0, 0.0);
+    return V3(R(0.0), R(0.0), R(0.0));
 }
 
 template <int G, class C>
 D3D_DEV v3 support(const C &c, v3 d, int lane) {
     v3 s = support_unmargined<G>(c, d, lane);
-    if (c.margin() != 0.0) s = s + normalized(d) * c.margin();  // colliders.py:629-631
+    if (c.margin() != R(0.0)) s = s + normalized(d) * c.margin();  // colliders.py:629-631
     return s;
 }
 
@@ -276,12 +276,12 @@ template <class C>
 D3D_DEV v3 center_of(const C &c) {
     v3 t = V3(c.tx(), c.ty(), c.tz());
     if (c.type == D3D_HULL || c.type == D3D_MESH) {
-        v3 s = V3(0.0, 0.0, 0.0);
+        v3 s = V3(R(0.0), R(0.0), R(0.0));
         for (int k = 0; k < c.nv; ++k) s = s + ld3(c.V + 3 * k);
-        s = s / (double)c.nv;
+        s = s / (real)c.nv;
         return c.type == D3D_HULL ? s : xform(c, s);
     }
     if (c.type == D3D_CONE)
-        return V3(t.x + 0.5 * c.p1() * c.r02(), t.y + 0.5 * c.p1() * c.r12(), t.z + 0.5 * c.p1() * c.r22());
+        return V3(t.x + R(0.5) * c.p1() * c.r02(), t.y + R(0.5) * c.p1() * c.r12(), t.z + R(0.5) * c.p1() * c.r22());
     return t;
 }

@@ -140,9 +140,9 @@ __global__ void k_bin_scatter(int64_t n, GjkWorkspace w) {
 // is shared memory and 3 CTAs per SM.
 template <int STRIDE>
 struct Simplex {
-    double *base;
-    double *pq;  // 24 doubles: P then Q (stride 1)
-    D3D_DEV double &at(int off, int s, int c) const {
+    real *base;
+    real *pq;  // 24 doubles: P then Q (stride 1)
+    D3D_DEV real &at(int off, int s, int c) const {
         if (GJK_PQ_LOCAL && STRIDE != 1 && off >= GJK_OFF_P) return pq[(off - GJK_OFF_P) + 3 * s + c];
         return base[(off + 3 * s + c) * STRIDE];
     }
@@ -151,9 +151,9 @@ struct Simplex {
 };
 
 struct GjkParams {
-    double tolerance_sq;
-    double max_distance_squared;
-    double sanity_check;
+    real tolerance_sq;
+    real max_distance_squared;
+    real sanity_check;
     double *out_dist;
     double *out_a;
     double *out_b;
@@ -168,18 +168,18 @@ template <int STRIDE>
 struct PairState {
     ColliderSmem<STRIDE> A, B;
     v3 sd;
-    double v_len_sq, prev_v_len_sq;
+    real v_len_sq, prev_v_len_sq;
     int n_points, iters, k, state;
 };
 
 template <int STRIDE>
 D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32_t *pairs, int k,
-                       double *base) {
+                       real *base) {
     int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
     s.A = stage_collider<STRIDE>(c, pr.x, base);
     s.B = stage_collider<STRIDE>(c, pr.y, base + GJK_OFF_B * STRIDE);
-    s.sd = V3(1.0, 0.0, 0.0);
-    s.v_len_sq = 1.0;  // np.dot(sd, sd), _gjk_jolt.py:197
+    s.sd = V3(R(1.0), R(0.0), R(0.0));
+    s.v_len_sq = R(1.0);  // np.dot(sd, sd), _gjk_jolt.py:197
     s.prev_v_len_sq = D3D_MAX_FLOAT;
     s.n_points = 0;
     s.iters = 0;
@@ -191,16 +191,16 @@ D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32
 // go through it (two calls), and because pairs are processed in (typeA, typeB) order
 // the switch is warp-uniform almost always.
 template <int G, int STRIDE>
-static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const double *base,
-                                               double dx, double dy, double dz, int lane) {
+static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const real *base,
+                                               real dx, real dy, real dz, int lane) {
     ColliderSmem<STRIDE> c;
     c.type = type; c.nv = nv; c.V = V; c.base = base;
     return support<G>(c, V3(dx, dy, dz), lane);
 }
 
 // max(|Y_i|^2) over the slots selected by mask (_gjk_jolt.py:634-640)
-D3D_DEV double max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
-    double m = (mask & 1) ? dot_blas(y0, y0) : -1.0;
+D3D_DEV real max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
+    real m = (mask & 1) ? dot_blas(y0, y0) : -R(1.0);
     if (mask & 2) m = fmax(m, dot_blas(y1, y1));
     if (mask & 4) m = fmax(m, dot_blas(y2, y2));
     if (mask & 8) m = fmax(m, dot_blas(y3, y3));
@@ -220,9 +220,9 @@ D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkPa
     v3 p = support_call<G, STRIDE>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
     v3 q = support_call<G, STRIDE>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
     v3 w = p - q;
-    double dot = dot_blas(s.sd, w);
+    real dot = dot_blas(s.sd, w);
     if (MODE == 0) {
-        if (dot < 0.0 && dot * dot > s.v_len_sq * prm.max_distance_squared) {
+        if (dot < R(0.0) && dot * dot > s.v_len_sq * prm.max_distance_squared) {
             s.state = D3D_CLIPPED;
             return false;
         }
@@ -238,7 +238,7 @@ D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkPa
 // Second half (_gjk_jolt.py:244-288 / :100-135) given the solver's answer.
 template <int MODE, int STRIDE>
 D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, bool ok,
-                      v3 v_new, double v_len_sq_new, int simplex) {
+                      v3 v_new, real v_len_sq_new, int simplex) {
     v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
        y3 = S.get(GJK_OFF_Y, 3);
     if (ok) {
@@ -250,7 +250,7 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
         simplex = (1 << s.n_points) - 1;
     }
     if (simplex == 0xf) {
-        if (MODE == 0) s.v_len_sq = 0.0;
+        if (MODE == 0) s.v_len_sq = R(0.0);
         s.state = D3D_INTERSECTION;
         return;
     }
@@ -274,14 +274,14 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
                 ++nn;
             }
         s.n_points = nn;
-        if (s.v_len_sq <= prm.tolerance_sq) { s.v_len_sq = 0.0; s.state = D3D_INTERSECTION; return; }
+        if (s.v_len_sq <= prm.tolerance_sq) { s.v_len_sq = R(0.0); s.state = D3D_INTERSECTION; return; }
         if (s.v_len_sq <= D3D_EPS * max_y_len_sq(y0, y1, y2, y3, simplex)) {
-            s.v_len_sq = 0.0;
+            s.v_len_sq = R(0.0);
             s.state = D3D_INTERSECTION;
             return;
         }
     }
-    s.sd = s.sd * -1.0;
+    s.sd = s.sd * -R(1.0);
     if (!(s.prev_v_len_sq >= s.v_len_sq)) { s.state = D3D_MONOTONICITY; return; }
     if (s.prev_v_len_sq - s.v_len_sq <= D3D_EPS * s.prev_v_len_sq) {
         s.state = D3D_NO_INTERSECTION;
@@ -305,7 +305,7 @@ template <int MODE, int G, int STRIDE>
 D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (!gjk_pre<MODE, G, STRIDE>(s, S, prm, lane)) return;
     v3 v_new;
-    double v_len_sq_new;
+    real v_len_sq_new;
     int simplex;
     bool ok = closest_point_to_origin(S.get(GJK_OFF_Y, 0), S.get(GJK_OFF_Y, 1), S.get(GJK_OFF_Y, 2),
                                       S.get(GJK_OFF_Y, 3), s.n_points, s.prev_v_len_sq, v_new,
@@ -326,7 +326,7 @@ D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
 // ascending face order with the reference's strict '<' rule, so the outcome is bit-identical
 // to closest_point_tetrahedron (_gjk_jolt.py:573-631).
 struct TriResult {
-    double qx, qy, qz, dist_sq;
+    real qx, qy, qz, dist_sq;
 };
 struct WarpScratch {
     TriResult *res;       // [32] results of the current round
@@ -337,10 +337,10 @@ struct WarpScratch {
 
 template <int STRIDE>
 D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, int n_points,
-                                          double prev_v_len_sq, const WarpScratch &W, int lane,
-                                          v3 &v_out, double &v_len_sq_out, int &set_out) {
+                                          real prev_v_len_sq, const WarpScratch &W, int lane,
+                                          v3 &v_out, real &v_len_sq_out, int &set_out) {
     const unsigned FULL = 0xffffffffu;
-    v3 v = V3(0.0, 0.0, 0.0);
+    v3 v = V3(R(0.0), R(0.0), R(0.0));
     int set = 1;
     int faces = 0;  // candidate faces of this lane (bit f)
     if (solve) {
@@ -372,7 +372,7 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
         int j = first;
         for (int todo = faces; todo; todo &= todo - 1) W.desc[j++] = (unsigned char)((lane << 2) | (__ffs(todo) - 1));
         __syncwarp();
-        double best_dist_sq = D3D_MAX_FLOAT;
+        real best_dist_sq = D3D_MAX_FLOAT;
         for (int base = 0; base < total; base += 32) {
             int item = base + lane;
             if (item < total) {
@@ -413,7 +413,7 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
         }
     }
     if (!solve) return false;
-    double v_len_sq = dot_blas(v, v);
+    real v_len_sq = dot_blas(v, v);
     if (v_len_sq < prev_v_len_sq) {
         v_out = v; v_len_sq_out = v_len_sq; set_out = set;
         return true;
@@ -435,12 +435,12 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
         }
         return;
     }
-    v3 a = V3(0.0, 0.0, 0.0), b = a;
-    double dist = D3D_MAX_FLOAT;
+    v3 a = V3(R(0.0), R(0.0), R(0.0)), b = a;
+    real dist = D3D_MAX_FLOAT;
     if (state == D3D_NO_INTERSECTION || state == D3D_INTERSECTION) {
         int n = s.n_points;
         // barycentric weights of the closest point (zero weight for unused slots)
-        double u = 1.0, v = 0.0, w = 0.0, x = 0.0;
+        real u = R(1.0), v = R(0.0), w = R(0.0), x = R(0.0);
         v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
            y3 = S.get(GJK_OFF_Y, 3);
         if (n == 2) bary_line(y0, y1, u, v);
@@ -455,10 +455,10 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
         }
         if (n >= 3) { a = a + S.get(GJK_OFF_P, 2) * w; b = b + S.get(GJK_OFF_Q, 2) * w; }
         if (n >= 4) { a = a + S.get(GJK_OFF_P, 3) * x; b = b + S.get(GJK_OFF_Q, 3) * x; }
-        double check_value = fabs(dot_blas(s.sd, s.sd) - s.v_len_sq);
+        real check_value = fabs(dot_blas(s.sd, s.sd) - s.v_len_sq);
         if (!(check_value < prm.sanity_check)) state = D3D_SANITY_FAILED;
         dist = sqrt(s.v_len_sq);
-        if (dist < D3D_EPS) { a = (a + b) * 0.5; b = a; }
+        if (dist < D3D_EPS) { a = (a + b) * R(0.5); b = a; }
     }
     if (!writer) return;
     prm.out_dist[k] = dist;
@@ -477,7 +477,11 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
 #define GJK_THREADS 128
 #endif
 #ifndef GJK_BLOCKS_PER_SM
+#ifdef D3D_F32
+#define GJK_BLOCKS_PER_SM 5  // fp32 state is half the size: 40 KB per CTA
+#else
 #define GJK_BLOCKS_PER_SM (GJK_PQ_LOCAL ? 4 : 3)
+#endif
 #endif
 #define GJK_CHUNK 256
 #ifndef GJK_REFILL_MIN
@@ -489,9 +493,9 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
 template <int MODE>
 __global__ void __launch_bounds__(GJK_THREADS, GJK_BLOCKS_PER_SM)
 k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
-    extern __shared__ double smem[];
-    double *base = smem + threadIdx.x;
-    double pq_local[24];
+    extern __shared__ real smem[];
+    real *base = smem + threadIdx.x;
+    real pq_local[24];
     Simplex<GJK_THREADS> S;
     S.base = base;
     S.pq = pq_local;
@@ -546,8 +550,8 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
             if (run_mask == 0) break;
         }
         bool solve = running && gjk_pre<MODE, 1, GJK_THREADS>(s, S, prm, 0);
-        v3 v_new = V3(0.0, 0.0, 0.0);
-        double v_len_sq_new = 0.0;
+        v3 v_new = V3(R(0.0), R(0.0), R(0.0));
+        real v_len_sq_new = R(0.0);
         int simplex = 0;
         bool ok = closest_point_to_origin_warp<GJK_THREADS>(solve, S, s.n_points, s.prev_v_len_sq, W, lane,
                                                             v_new, v_len_sq_new, simplex);
@@ -561,9 +565,9 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
 template <int MODE>
 __global__ void __launch_bounds__(GJK_THREADS, 4)
 k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
-    __shared__ double smem[(GJK_THREADS / 32) * GJK_FIELDS];
+    __shared__ real smem[(GJK_THREADS / 32) * GJK_FIELDS];
     const int lane = threadIdx.x & 31;
-    double *base = smem + (threadIdx.x >> 5) * GJK_FIELDS;
+    real *base = smem + (threadIdx.x >> 5) * GJK_FIELDS;
     Simplex<1> S;
     S.base = base;
     S.pq = base + GJK_OFF_P;
@@ -603,7 +607,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
-    size_t smem = sizeof(double) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
+    size_t smem = sizeof(real) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
     D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
     k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
@@ -615,11 +619,20 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
 
 }  // namespace
 
+// The fp32 instantiation of this file (gjk_f32.cu: -DD3D_F32) exports *_f32 entry points.
+#ifdef D3D_F32
+#define D3D_GJK_SYM(name) name##_f32
+#else
+#define D3D_GJK_SYM(name) name
+#endif
+
 extern "C" {
 
+#ifndef D3D_F32
 size_t d3d_gjk_workspace_bytes(int64_t n_pairs) { return gjk_ws_bytes(n_pairs); }
+#endif
 
-int d3d_gjk_distance(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+int D3D_GJK_SYM(d3d_gjk_distance)(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
                      double tolerance, double max_distance_squared, double sanity_check,
                      double *out_dist, double *out_a, double *out_b, double *out_Y,
                      int32_t *out_npoints, int32_t *out_iters, int32_t *out_status,
@@ -636,7 +649,7 @@ int d3d_gjk_distance(const d3d_colliders *c, const int32_t *pairs, int64_t n_pai
     return launch_gjk<0>(c, pairs, n_pairs, prm, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
-int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+int D3D_GJK_SYM(d3d_gjk_intersection)(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
                          double tolerance, uint8_t *out_hit, int32_t *out_iters,
                          int32_t *out_status, void *workspace, size_t ws_bytes, void *stream) {
     if (n_pairs == 0) return 0;

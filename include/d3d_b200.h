@@ -75,6 +75,22 @@ int d3d_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t n
                          double tolerance, uint8_t *out_hit, int32_t *out_iters,
                          int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
 
+/* Opt-in fp32 arithmetic (BASELINE north_star): same arguments and buffer types (fp64 in HBM)
+ * as d3d_gjk_distance / d3d_gjk_intersection, all arithmetic in single precision.  Not
+ * bit-compatible with the reference; tolerance against the fp64 path (unit-scale shapes,
+ * tests/test_gjk_gpu.py): 99.9 % of the distances within 1e-4, every result an upper bound at
+ * most 0.2 off (rare early termination on polytope-vs-curved pairs, as in Jolt's own
+ * single-precision GJK whose degeneracy thresholds this mode uses), intersection flags equal
+ * where the fp64 distance exceeds 1e-3. */
+int d3d_gjk_distance_f32(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                         double tolerance, double max_distance_squared, double sanity_check,
+                         double *out_dist, double *out_a, double *out_b, double *out_Y,
+                         int32_t *out_npoints, int32_t *out_iters, int32_t *out_status,
+                         void *workspace, size_t ws_bytes, void *stream);
+int d3d_gjk_intersection_f32(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,
+                             double tolerance, uint8_t *out_hit, int32_t *out_iters,
+                             int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
+
 /* epa.py:9-78 epa(simplex, collider1, collider2, max_iter, max_loose_edges, max_faces, epsilon)
  * for pairs[k] with GJK simplex Y[k,4,3] (out_Y of d3d_gjk_distance, 4 valid rows required):
  *   out_mtv[k,3]   minimum translation vector (depth = |mtv|, normal = mtv / |mtv|)

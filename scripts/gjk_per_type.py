@@ -1,15 +1,16 @@
-import sys, time; sys.path.insert(0,"/root/repo")
+import sys, time, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from distance3d_b200 import gjk, random as R
 names=sys.argv[1].split(",") if len(sys.argv)>1 else ["sphere","ellipsoid","capsule","cylinder","box"]
 n=1<<20
+DTYPE=os.environ.get("D3D_DTYPE","f64")
 def run(cs,pairs,label):
     dc=cs.device(); pd=torch.from_numpy(pairs).cuda()
-    out=gjk.gjk_distance_batch(dc,pd)
-    for _ in range(2): gjk.gjk_distance_batch(dc,pd,out=out)
+    out=gjk.gjk_distance_batch(dc,pd,dtype=DTYPE)
+    for _ in range(2): gjk.gjk_distance_batch(dc,pd,out=out,dtype=DTYPE)
     torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5): gjk.gjk_distance_batch(dc,pd,out=out)
+    for _ in range(5): gjk.gjk_distance_batch(dc,pd,out=out,dtype=DTYPE)
     e1.record(); torch.cuda.synchronize()
     ms=e0.elapsed_time(e1)/5
     it=out.iters.double().mean().item()

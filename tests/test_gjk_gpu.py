@@ -189,3 +189,29 @@ def test_streamed_host_pipeline_equals_batch_call():
         assert np.array_equal(got["dist"].numpy(), ref["dist"])
         assert np.array_equal(got["closest_a"].numpy(), ref["a"])
         assert np.array_equal(got["status"].numpy(), ref["status"])
+
+
+def test_fp32_mode_stated_tolerance():
+    """Opt-in fp32 arithmetic: tolerance against the fp64 oracle as stated in include/d3d_b200.h:
+    99.9 % of the distances within 1e-4 (unit-scale shapes), every valid result is an upper bound
+    that is at most 0.2 off (rare early termination on hull-vs-curved pairs, as in Jolt's own
+    single-precision GJK), intersection flags equal where the fp64 distance exceeds 1e-3."""
+    rs = np.random.RandomState(16)
+    cs = d3random.random_collider_set(rs, 4000, names=d3random.PRIMITIVES + ("mesh",))
+    pairs = d3random.random_pairs(rs, len(cs), 60000)
+    res = gjk.gjk_distance_batch(cs, pairs, dtype="f32").cpu()
+    ref = O.gjk_distance(cs, pairs, n_threads=O.max_threads())
+    ok = (ref["status"] <= 1) & (res["status"] <= 1)
+    assert ok.mean() > 0.999
+    err = np.abs(res["dist"][ok] - ref["dist"][ok])
+    print("fp32 distance error: max %.3e p99.9 %.3e mean %.3e" % (err.max(), np.quantile(err, 0.999), err.mean()))
+    assert np.quantile(err, 0.999) < 1e-4
+    assert err.max() < 0.2
+    assert np.mean(res["dist"][ok] - ref["dist"][ok] > -1e-3) == 1.0   # upper bound (up to contact flips)
+    hit, _, _ = gjk.gjk_intersection_batch(cs, pairs, dtype="f32")
+    ref_hit = O.gjk_intersection(cs, pairs, n_threads=O.max_threads())["hit"]
+    hit = hit.cpu().numpy()
+    far = ref["dist"] > 1e-3
+    assert np.array_equal(hit[far], ref_hit[far])
+    deep = ref["dist"] == 0.0
+    assert (hit[deep] == ref_hit[deep]).mean() > 0.995   # grazing contacts may flip
