@@ -271,6 +271,15 @@ D3D_DEV v3 support(const C &c, v3 d, int lane) {
     return s;
 }
 
+// Out-of-line instance of the ten-way support switch for kernels that keep their collider
+// records in registers / local memory (EPA, MPR): one copy of the code instead of one per call
+// site (the MPR kernel shrank from 209 KB to a fraction of that; these kernels are
+// instruction-fetch bound).
+template <int G>
+static __device__ __noinline__ v3 support_ni(const Collider &c, real dx, real dy, real dz, int lane) {
+    return support<G>(c, V3(dx, dy, dz), lane);
+}
+
 // colliders.py center(); hull / mesh means are sequential column sums (np.mean axis 0)
 template <class C>
 D3D_DEV v3 center_of(const C &c) {

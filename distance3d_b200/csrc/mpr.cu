@@ -31,8 +31,8 @@ struct MprParams {
 
 // minkowski.py:23-55
 D3D_DEV void mink_support(const Collider &A, const Collider &B, v3 d, v3 &v, v3 &v1, v3 &v2) {
-    v1 = support<1>(A, d, 0);
-    v2 = support<1>(B, -d, 0);
+    v1 = support_ni<1>(A, d.x, d.y, d.z, 0);
+    v2 = support_ni<1>(B, -d.x, -d.y, -d.z, 0);
     v = v1 - v2;
 }
 
