@@ -4,8 +4,8 @@
 #pragma once
 #include "d3d_math.cuh"
 
-// _gjk_jolt.py:291-312
-D3D_DEV void bary_line(v3 a, v3 b, real &u, real &v) {
+// _gjk_jolt.py:291-312 (out of line: nine call sites)
+static __device__ __noinline__ void bary_line(v3 a, v3 b, real &u, real &v) {
     v3 ab = b - a;
     real denominator = dot_blas(ab, ab);
     if (denominator < D3D_EPS_SQR) {

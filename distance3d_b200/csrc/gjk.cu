@@ -264,6 +264,7 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     if (MODE == 0) {
         // update_simplex_ypq (_gjk_jolt.py:654-664)
         int nn = 0;
+#pragma unroll 1
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
                 if (nn != i) {
@@ -291,6 +292,7 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     if (MODE == 1) {
         // update_simplex_y (_gjk_jolt.py:643-651)
         int nn = 0;
+#pragma unroll 1
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
                 if (nn != i) S.set(GJK_OFF_Y, nn, S.get(GJK_OFF_Y, i));
@@ -465,6 +467,7 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
     if (prm.out_a) st3(prm.out_a + 3 * k, a);
     if (prm.out_b) st3(prm.out_b + 3 * k, b);
     if (prm.out_Y) {
+#pragma unroll 1
         for (int i = 0; i < 4; ++i)
             st3(prm.out_Y + 12 * k + 3 * i, i < s.n_points ? S.get(GJK_OFF_Y, i) : V3(0.0, 0.0, 0.0));
     }
