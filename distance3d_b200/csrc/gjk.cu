@@ -229,8 +229,10 @@ D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkPa
     } else {
         if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return false; }
     }
+    if (STRIDE == 1) __syncwarp();
     S.set(GJK_OFF_Y, s.n_points, w);
     if (MODE == 0) { S.set(GJK_OFF_P, s.n_points, p); S.set(GJK_OFF_Q, s.n_points, q); }
+    if (STRIDE == 1) __syncwarp();
     ++s.n_points;
     return true;
 }
@@ -263,14 +265,18 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     }
     if (MODE == 0) {
         // update_simplex_ypq (_gjk_jolt.py:654-664)
+        if (STRIDE == 1) __syncwarp();
         int nn = 0;
 #pragma unroll 1
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
                 if (nn != i) {
-                    S.set(GJK_OFF_Y, nn, S.get(GJK_OFF_Y, i));
-                    S.set(GJK_OFF_P, nn, S.get(GJK_OFF_P, i));
-                    S.set(GJK_OFF_Q, nn, S.get(GJK_OFF_Q, i));
+                    v3 ty = S.get(GJK_OFF_Y, i), tp = S.get(GJK_OFF_P, i), tq = S.get(GJK_OFF_Q, i);
+                    if (STRIDE == 1) __syncwarp();  // warp kernel: the record is shared by 32 lanes
+                    S.set(GJK_OFF_Y, nn, ty);
+                    S.set(GJK_OFF_P, nn, tp);
+                    S.set(GJK_OFF_Q, nn, tq);
+                    if (STRIDE == 1) __syncwarp();
                 }
                 ++nn;
             }
@@ -291,11 +297,17 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     s.prev_v_len_sq = s.v_len_sq;
     if (MODE == 1) {
         // update_simplex_y (_gjk_jolt.py:643-651)
+        if (STRIDE == 1) __syncwarp();
         int nn = 0;
 #pragma unroll 1
         for (int i = 0; i < s.n_points; ++i)
             if (simplex & (1 << i)) {
-                if (nn != i) S.set(GJK_OFF_Y, nn, S.get(GJK_OFF_Y, i));
+                if (nn != i) {
+                    v3 ty = S.get(GJK_OFF_Y, i);
+                    if (STRIDE == 1) __syncwarp();
+                    S.set(GJK_OFF_Y, nn, ty);
+                    if (STRIDE == 1) __syncwarp();
+                }
                 ++nn;
             }
         s.n_points = nn;
