@@ -72,7 +72,8 @@ class Lbvh:
         if not isinstance(query, torch.Tensor):
             query = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float64)).to(self.device)
         query = query.reshape(-1, 3, 2).contiguous()
-        nq = int(query.shape[0])
+        # with `order` only the listed query boxes are processed (e.g. one rank's shard)
+        nq = int(order.shape[0]) if order is not None else int(query.shape[0])
         L = _lib.lib()
         qbytes = L.d3d_bvh_query_workspace_bytes(c_i64(nq))
         if self._qws is None or self._qws.numel() < qbytes:

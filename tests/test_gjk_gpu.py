@@ -215,3 +215,49 @@ def test_fp32_mode_stated_tolerance():
     assert np.array_equal(hit[far], ref_hit[far])
     deep = ref["dist"] == 0.0
     assert (hit[deep] == ref_hit[deep]).mean() > 0.995   # grazing contacts may flip
+
+
+def test_scalar_support_and_geometry_api_vs_reference_outputs():
+    """geometry.support_function_*, containment.*_aabb, minkowski.support_function on single
+    colliders reproduce the real reference's outputs stored in tests/golden/support.npz."""
+    from distance3d_b200 import colliders as C, geometry, containment, minkowski, mesh
+    cs, g = load_golden("support.npz")
+    seen = set()
+    for i in range(len(cs)):
+        t = int(cs.type[i])
+        if t in seen or (cs.margin is not None and cs.margin[i] != 0.0):
+            continue
+        seen.add(t)
+        T, p, d = cs.pose[i], cs.param[i], g["dirs"][i, 0]
+        if t == P.SPHERE:
+            got = geometry.support_function_sphere(d, T[:3, 3], p[0])
+            lo, hi = containment.sphere_aabb(T[:3, 3], p[0])
+        elif t == P.CAPSULE:
+            got = geometry.support_function_capsule(d, T, p[0], p[1])
+            lo, hi = containment.capsule_aabb(T, p[0], p[1])
+        elif t == P.CYLINDER:
+            got = geometry.support_function_cylinder(d, T, p[0], p[1])
+            lo, hi = containment.cylinder_aabb(T, p[0], p[1])
+        elif t == P.ELLIPSOID:
+            got = geometry.support_function_ellipsoid(d, T, p)
+            lo, hi = containment.ellipsoid_aabb(T, p)
+        elif t == P.CONE:
+            got = geometry.support_function_cone(d, T, p[0], p[1])
+            lo, hi = containment.cone_aabb(T, p[0], p[1])
+        elif t == P.BOX:
+            got = C.Box(T, p).support_function(d)
+            lo, hi = containment.box_aabb(T, p)
+            np.testing.assert_array_equal(geometry.convert_box_to_vertices(T, p).min(axis=0), lo)
+        else:
+            continue
+        np.testing.assert_array_equal(got, g["support"][i, 0])
+        np.testing.assert_array_equal(np.stack((lo, hi), axis=1), g["aabb"][i])
+    assert len(seen) >= 6
+    s1, s2 = C.Sphere(np.zeros(3), 1.0), C.Sphere(np.array([3.0, 0, 0]), 0.5)
+    v, v1, v2 = minkowski.support_function(s1, s2, np.array([1.0, 0.0, 0.0]))
+    np.testing.assert_allclose(v1, [1, 0, 0]); np.testing.assert_allclose(v2, [2.5, 0, 0])
+    np.testing.assert_allclose(v, [-1.5, 0, 0])
+    verts = np.random.RandomState(0).randn(30, 3)
+    tri = mesh.make_convex_mesh(verts)
+    idx, pt = mesh.MeshSupportFunction(np.eye(4), verts, tri)(np.array([0.0, 0.0, 1.0]))
+    assert idx == int(np.argmax(verts[:, 2])) and np.allclose(pt, verts[idx])
