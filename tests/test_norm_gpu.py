@@ -19,7 +19,14 @@ def _vectors():
     unit /= np.linalg.norm(unit, axis=1)[:, None]  # results close to 1.0 (a power of two)
     two_d = rs.randn(100000, 3)
     two_d[:, 2] = 0.0
-    return np.concatenate([v, special, unit, two_d])
+    # components of very different magnitude (exactness hazards of the double-double replay)
+    skew = rs.randn(100000, 3) * 10.0 ** rs.uniform(-12, 2, size=(100000, 3))
+    # products that land exactly on / next to powers of two and 64-bit ties
+    pow2 = np.zeros((4096, 3))
+    pow2[:, 0] = 2.0 ** rs.randint(-30, 30, size=4096)
+    pow2[:, 1] = pow2[:, 0] * 2.0 ** -rs.randint(0, 40, size=4096) * rs.choice([0.0, 1.0, 3.0], size=4096)
+    ints = rs.randint(1, 2 ** 20, size=(100000, 3)).astype(float)   # exact integer squares
+    return np.concatenate([v, special, unit, two_d, skew, pow2, ints])
 
 
 def test_production_norm_is_bit_exact():
