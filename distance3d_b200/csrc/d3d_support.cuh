@@ -151,7 +151,7 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
         real val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
         if (!have || val > best) { best = val; bi = i; have = true; }
     }
-#pragma unroll
+#pragma unroll 1
     for (int off = G / 2; off > 0; off >>= 1) {
         real ov = __shfl_xor_sync(0xffffffffu, best, off, G);
         int oi = __shfl_xor_sync(0xffffffffu, bi, off, G);

@@ -94,6 +94,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         Collider A = load_collider(c, pr.x), B = load_collider(c, pr.y);
 
         // epa.py:83-97: zero-initialised polytope, faces ABC, ACD, ADB, BDC
+#pragma unroll 1
         for (int i = lane; i < 12 * mf; i += 32) W.faces[i] = 0.0;
         __syncwarp();
         if (lane < 4) {
@@ -112,11 +113,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             // ---- A: closest face, first arg-min of sum(v0 * n) (epa.py:104-109)
             double best = 0.0;
             int bi = 0x7fffffff;
+#pragma unroll 1
             for (int i = lane; i < n_faces; i += 32) {
                 double d = dot_plain(W.fget(i, 0), W.fget(i, 3));
                 if (bi == 0x7fffffff || d < best) { best = d; bi = i; }
             }
-#pragma unroll
+#pragma unroll 1
             for (int off = 16; off > 0; off >>= 1) {
                 double ob = __shfl_xor_sync(FULL, best, off);
                 int oi = __shfl_xor_sync(FULL, bi, off);
@@ -148,6 +150,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             }
             // replay of the swap-with-last loop on slot indices (lane 0), removal order in perm
             // perm[s] = original slot whose face ends up in slot s
+#pragma unroll 1
             for (int i = lane; i < n_faces; i += 32) W.perm[i] = i;
             __syncwarp();
             int n_loose = 0;
@@ -159,6 +162,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     bool vis = f < 32 ? ((vis_lo >> f) & 1u) : ((vis_hi >> (f - 32)) & 1u);
                     if (!vis) { ++i; continue; }
                     // epa.py:167-187: edges of the removed face against the loose-edge list
+#pragma unroll 1
                     for (int j = 0; j < 3; ++j) {
                         v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);
                         bool match = false;
@@ -191,6 +195,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 }
             }
             // apply the permutation: slot s <- original slot perm[s] (reads before writes)
+#pragma unroll 1
             for (int base = 0; base < n_faces; base += 32) {
                 int s = base + lane;
                 int src = s < n_faces ? W.perm[s] : s;
@@ -250,7 +255,9 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         }
         if (prm.out_faces) {
             double *o = prm.out_faces + (int64_t)k * mf * 12;
+#pragma unroll 1
             for (int i = lane; i < mf; i += 32)
+#pragma unroll 1
                 for (int w = 0; w < 4; ++w) st3(o + 12 * i + 3 * w, W.fget(i, w));
         }
         __syncwarp();
