@@ -313,6 +313,20 @@ def secondary_workload(args, torch, dist, rank, world, dev):
                                 "configurations_per_gpu": n},
                      "colliding_fraction": float((mask.sum(dim=1) > 0).double().mean().item()),
                      "narrow_phase_candidates_per_configuration": n_cand / n})
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import cpu_oracle
+            m = min(n, 200000)
+            threads = cpu_oracle.max_threads()
+            kin = tm.compile_kinematics(model.frames, "origin")
+            qs = q[:m].cpu().numpy()
+            t0 = time.perf_counter()
+            ref_mask, _ = cpu_oracle.self_collision_masks(model.template, kin, model.pattern, qs, threads)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": m / dt, "unit": "configurations/s", "cores": threads,
+                                    "kind": "port", "sample": "first %d configurations" % m}
+            line["parity_on_cpu_sample"] = {
+                "configurations": m,
+                "mask_agreement": float((mask[:m].cpu().numpy() == ref_mask).mean())}
     else:
         # C5: mixed shapes, LBVH broad phase + GJK + EPA
         n = args.items or 2000000
@@ -334,6 +348,31 @@ def secondary_workload(args, torch, dist, rank, world, dev):
                      "candidate_pairs_per_s": world * int(r.candidates.shape[0]) / (ms * 1e-3),
                      "contacts": int(r.hits.numel()),
                      "epa_pairs": 0 if r.epa is None else int(r.epa_index.numel())})
+        if rank == 0 and not args.no_cpu_baseline:
+            # reference algorithms on a bounded sample: incremental tree + stack queries, GJK, EPA
+            from oracle import cpu_oracle
+            m = min(n, 50000)
+            threads = cpu_oracle.max_threads()
+            sub = d3random.random_collider_set(np.random.RandomState(args.seed), m,
+                                               names=d3random.PRIMITIVES + ("mesh",),
+                                               center_scale=0.33 * m ** (1.0 / 3.0), hull_vertices=(10, 10))
+            t0 = time.perf_counter()
+            A = cpu_oracle.aabb(sub)
+            tree = cpu_oracle.Tree()
+            tree.insert_aabbs(A)
+            pr = tree.query(A)
+            cand = pr[pr[:, 0] < pr[:, 1]]
+            g = cpu_oracle.gjk_distance(sub, cand, n_threads=threads)
+            sel = (g["dist"] == 0.0) & (g["n_points"] == 4)
+            cpu_oracle.epa(sub, cand[sel], g["Y"][sel], n_threads=threads)
+            dt = time.perf_counter() - t0
+            gpu = pipeline.collide(sub, shard=False)
+            line["cpu_baseline"] = {"value": m / dt, "unit": "shapes/s", "cores": threads, "kind": "port",
+                                    "sample": "%d shapes at the same density (tree build / query single-threaded, "
+                                              "GJK / EPA on all threads)" % m}
+            line["parity_on_cpu_sample"] = {
+                "shapes": m, "candidates_equal": bool(len(cand) == gpu.candidates.shape[0]),
+                "contacts_equal": bool(int((g["dist"] == 0.0).sum()) == gpu.hits.numel())}
     if rank == 0:
         print(json.dumps(line))
 

@@ -222,3 +222,40 @@ def norm(v):
     out = np.zeros(len(v))
     lib().d3do_norm(_p(v), c_i64(len(v)), _p(out))
     return out
+
+
+def fk(kin, q, n_threads=1):
+    """Poses [B,K,4,4] of a flattened URDF chain (`UrdfTransformManager.compile_kinematics`)."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    n_joints = len(kin["joint_names"])
+    n_frames = len(kin["chain_off"]) - 1
+    q = q.reshape(-1, n_joints)
+    out = np.zeros((len(q), n_frames, 4, 4))
+    arrs = {k: np.ascontiguousarray(kin[k]) for k in ("joint_axis", "joint_limits", "joint_type",
+                                                      "chain_off", "chain_fixed", "chain_joint")}
+    lib().d3do_fk(c_int(n_frames), c_int(n_joints), _p(arrs["joint_axis"]), _p(arrs["joint_limits"]),
+                  _p(arrs["joint_type"]), _p(arrs["chain_off"]), _p(arrs["chain_fixed"]),
+                  _p(arrs["chain_joint"]), _p(q), c_i64(len(q)), _p(out), c_int(n_threads))
+    return out
+
+
+def self_collision_masks(template, kin, pattern, q, n_threads=1):
+    """Reference semantics of self_collision.detect (self_collision.py:5-36) for many joint
+    configurations: FK, AABBs, white-list filtered candidates, gjk_intersection.
+    `template`: ColliderSet of the K colliders (shape parameters), `pattern` int32[C,2]."""
+    from distance3d_b200.pack import ColliderSet
+    poses = fk(kin, q, n_threads)
+    B, K = poses.shape[:2]
+    z = np.zeros(B * K, dtype=np.int32)
+    cs = ColliderSet(np.tile(template.type, B), poses.reshape(-1, 4, 4), np.tile(template.param, (B, 1)),
+                     z, z, np.zeros((0, 3)))
+    boxes = aabb(cs).reshape(B, K, 3, 2)
+    a, b = boxes[:, pattern[:, 0]], boxes[:, pattern[:, 1]]
+    ov = np.all((a[..., 0] <= b[..., 1]) & (a[..., 1] >= b[..., 0]), axis=-1)   # [B, C]
+    bi, ci = np.nonzero(ov)
+    pairs = np.stack((bi * K + pattern[ci, 0], bi * K + pattern[ci, 1]), axis=1).astype(np.int32)
+    hit = gjk_intersection(cs, pairs, n_threads=n_threads)["hit"].astype(bool)
+    mask = np.zeros(B * K, dtype=np.uint8)
+    mask[pairs[hit, 0]] = 1
+    mask[pairs[hit, 1]] = 1
+    return mask.reshape(B, K), len(pairs)

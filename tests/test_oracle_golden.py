@@ -104,3 +104,29 @@ def test_broad_phase_tree_and_brute_force_identical_lists():
     # tree result == brute force as a set
     brute = O.all_aabbs_overlap(A, A)
     assert set(map(tuple, brute)) == set(map(tuple, g["tree_pairs"]))
+
+
+def test_self_collision_masks_equal_reference_detect():
+    """FK + AABB + white-list + gjk_intersection of the oracle reproduce the reference's
+    self_collision.detect over 150 joint configurations (tests/golden/self_collision.npz)."""
+    import os
+    from distance3d_b200 import colliders as C, pack
+    from distance3d_b200.urdf import UrdfTransformManager
+    from distance3d_b200.urdf_utils import self_collision_whitelists
+    from distance3d_b200.self_collision import _candidate_pattern
+    from util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "self_collision.npz"))
+    data = os.path.join(os.path.dirname(GOLDEN), "data")
+    tm = UrdfTransformManager()
+    with open(os.path.join(data, "robot_arm.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=data)
+    tm.add_transform("robot_arm", "origin", np.eye(4))
+    frames = [str(f) for f in g["frames"]]
+    template = pack.pack_colliders([C.Cylinder(np.eye(4), o.radius, o.length) for o in tm.collision_objects])
+    pattern = _candidate_pattern(frames, self_collision_whitelists(tm))
+    kin = tm.compile_kinematics(frames, "origin")
+    poses = O.fk(kin, g["q"])
+    assert np.max(np.abs(poses - g["poses"])) < 1e-14
+    masks, n_cand = O.self_collision_masks(template, kin, pattern, g["q"])
+    np.testing.assert_array_equal(masks, g["mask"])
+    assert n_cand > 100
