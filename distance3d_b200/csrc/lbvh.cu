@@ -53,6 +53,7 @@ struct BvhLayout {
     double *partials;             // [1024][6]
     unsigned long long *keys[2];  // [n] each
     unsigned *hist;               // [256][sort_blocks]
+    unsigned *digit_totals;       // [256]
     int *flags;                   // [n-1]
     int *range_last;              // [2n-1] last sorted leaf covered by each node
     BvhNode *nodes;               // [2n-1]
@@ -64,7 +65,7 @@ inline size_t au(size_t x) { return (x + 255) / 256 * 256; }
 inline size_t bvh_ws_bytes(int64_t n) {
     size_t nn = (size_t)(n > 0 ? n : 1);
     size_t sort_blocks = (nn + SORT_TILE - 1) / SORT_TILE;
-    return 256 + au(1024 * 6 * 8) + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nn * 4) +
+    return 256 + au(1024 * 6 * 8) + 1024 + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nn * 4) +
            au(2 * nn * 4) + au(2 * nn * sizeof(BvhNode));
 }
 
@@ -74,6 +75,7 @@ inline BvhLayout bvh_carve(void *ws, int64_t n) {
     char *p = reinterpret_cast<char *>(ws);
     L.hdr = reinterpret_cast<BvhHeader *>(p); p += 256;
     L.partials = reinterpret_cast<double *>(p); p += au(1024 * 6 * 8);
+    L.digit_totals = reinterpret_cast<unsigned *>(p); p += 1024;
     L.keys[0] = reinterpret_cast<unsigned long long *>(p); p += au(nn * 8);
     L.keys[1] = reinterpret_cast<unsigned long long *>(p); p += au(nn * 8);
     L.sort_blocks = (int)((nn + SORT_TILE - 1) / SORT_TILE);
@@ -185,37 +187,26 @@ k_sort_hist(const unsigned long long *__restrict__ keys, int64_t n, int shift, u
     hist[threadIdx.x * blocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-// Exclusive scan of hist (256 * blocks entries) by one block of 1024 threads: every
-// thread owns a contiguous run (serial scan), the run totals are scanned across the block.
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned *hist, int total) {
-    __shared__ unsigned warp_sums[32];
-    int per = (total + 1023) / 1024;
-    int begin = threadIdx.x * per, end = min(begin + per, total);
-    unsigned sum = 0;
-    for (int i = begin; i < end; ++i) sum += hist[i];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned x = sum;
-    for (int off = 1; off < 32; off <<= 1) {
-        unsigned y = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += y;
-    }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned s = warp_sums[lane];
+// Scan of the digit-major histogram hist[d * blocks + b] in two levels: one WARP per digit
+// turns its row into an exclusive prefix over the blocks and records the digit total; the
+// scatter kernel adds the exclusive prefix over the 256 digit totals (a block-local scan).
+__global__ void __launch_bounds__(256) k_sort_scan(unsigned *hist, int blocks, unsigned *digit_totals) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= 256) return;
+    unsigned *row = hist + (size_t)warp * blocks;
+    unsigned carry = 0;
+    for (int base = 0; base < blocks; base += 32) {
+        int i = base + lane;
+        unsigned v = i < blocks ? row[i] : 0u, x = v;
+#pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, s, off);
-            if (lane >= off) s += y;
+            unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
         }
-        warp_sums[lane] = s;
+        if (i < blocks) row[i] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    __syncthreads();
-    unsigned acc = (wid ? warp_sums[wid - 1] : 0u) + x - sum;
-    for (int i = begin; i < end; ++i) {
-        unsigned v = hist[i];
-        hist[i] = acc;
-        acc += v;
-    }
+    if (lane == 0) digit_totals[warp] = carry;
 }
 
 // Stable scatter.  Warp w of the block owns the contiguous slice
@@ -223,12 +214,29 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned *hist, int total) {
 // digits inside one step are ranked with __match_any_sync.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-               int64_t n, int shift, const unsigned *__restrict__ hist, int blocks) {
+               int64_t n, int shift, const unsigned *__restrict__ hist, int blocks,
+               const unsigned *__restrict__ digit_totals) {
     constexpr int WARPS = SORT_THREADS / 32;
     constexpr int PER_WARP = SORT_TILE / WARPS;
     constexpr int STEPS = PER_WARP / 32;
     __shared__ unsigned counts[WARPS][256];
+    __shared__ unsigned digit_base[256];
+    __shared__ unsigned warp_tot[WARPS];
     for (int i = threadIdx.x; i < WARPS * 256; i += SORT_THREADS) (&counts[0][0])[i] = 0;
+    {   // exclusive scan of the 256 digit totals (thread d owns digit d)
+        unsigned v = digit_totals[threadIdx.x], x = v;
+        int ln = threadIdx.x & 31, wd = threadIdx.x >> 5;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+            if (ln >= off) x += y;
+        }
+        if (ln == 31) warp_tot[wd] = x;
+        __syncthreads();
+        unsigned before = 0;
+        for (int w2 = 0; w2 < wd; ++w2) before += warp_tot[w2];
+        digit_base[threadIdx.x] = before + x - v;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1;
@@ -258,7 +266,7 @@ k_sort_scatter(const unsigned long long *__restrict__ in, unsigned long long *__
     // exclusive prefix over the warps of this block, per digit, plus the global offset
     {
         unsigned d = threadIdx.x;
-        unsigned acc = hist[d * blocks + blockIdx.x];
+        unsigned acc = digit_base[d] + hist[d * blocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
             unsigned c = counts[w][d];
@@ -353,17 +361,23 @@ __global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhN
 __global__ void k_refit(int n, BvhNode *nodes, int *flags) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    int cur = nodes[n - 1 + j].parent;
+    int node = n - 1 + j;
+    double lo[3], hi[3];  // box of the subtree this thread has finished (kept in registers)
+    for (int k = 0; k < 3; ++k) { lo[k] = nodes[node].lo[k]; hi[k] = nodes[node].hi[k]; }
+    int cur = nodes[node].parent;
     while (cur >= 0) {
+        __threadfence();                              // my subtree's box is visible ...
+        if (atomicAdd(&flags[cur], 1) == 0) return;   // ... before I announce it; first arrival stops
         __threadfence();
-        if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: sibling not ready
-        __threadfence();
-        volatile BvhNode *l = nodes + nodes[cur].left;
-        volatile BvhNode *r = nodes + nodes[cur].right;
+        int l = nodes[cur].left, r = nodes[cur].right;
+        const volatile BvhNode *sib = nodes + (l == node ? r : l);
         for (int k = 0; k < 3; ++k) {
-            nodes[cur].lo[k] = fmin(l->lo[k], r->lo[k]);
-            nodes[cur].hi[k] = fmax(l->hi[k], r->hi[k]);
+            lo[k] = fmin(lo[k], sib->lo[k]);
+            hi[k] = fmax(hi[k], sib->hi[k]);
+            nodes[cur].lo[k] = lo[k];
+            nodes[cur].hi[k] = hi[k];
         }
+        node = cur;
         cur = nodes[cur].parent;
     }
 }
@@ -639,9 +653,9 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
     int cur = 0;
     for (int shift = 32; shift < 64; shift += 8) {
         k_sort_hist<<<L.sort_blocks, SORT_THREADS, 0, stream>>>(L.keys[cur], n, shift, L.hist, L.sort_blocks);
-        k_sort_scan<<<1, 1024, 0, stream>>>(L.hist, 256 * L.sort_blocks);
+        k_sort_scan<<<32, 256, 0, stream>>>(L.hist, L.sort_blocks, L.digit_totals);
         k_sort_scatter<<<L.sort_blocks, SORT_THREADS, 0, stream>>>(L.keys[cur], L.keys[cur ^ 1], n, shift,
-                                                                  L.hist, L.sort_blocks);
+                                                                  L.hist, L.sort_blocks, L.digit_totals);
         cur ^= 1;
     }
     // 4 passes: sorted keys are back in keys[0]
