@@ -177,7 +177,7 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
             e[0].record()
             bvh.rebuild()
             e[1].record()
-            bvh.overlap_self(out=buf, packet=packet)
+            bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=packet)  # no host sync
             e[2].record()
             torch.cuda.synchronize()
             if it >= 2:

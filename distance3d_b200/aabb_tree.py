@@ -92,6 +92,26 @@ class Lbvh:
             _lib.stream_ptr()))
         return out[:count], count
 
+    def overlap_async(self, query, out, order=None, packet=None):
+        """Count + fill into a caller-provided buffer without synchronising the host.
+
+        Returns ``(out, count)`` where `count` is a device int64 tensor with the exact number of
+        pairs (entries beyond ``out.shape[0]`` are dropped; check `count` when in doubt)."""
+        torch = _lib.torch_cuda()
+        query = query.reshape(-1, 3, 2)
+        nq = int(order.shape[0]) if order is not None else int(query.shape[0])
+        if packet is None:
+            packet = order is not None
+        L = _lib.lib()
+        qbytes = L.d3d_bvh_query_workspace_bytes(c_i64(nq))
+        if self._qws is None or self._qws.numel() < qbytes:
+            self._qws = torch.empty(qbytes, dtype=torch.uint8, device=self.device)
+        _lib._check(L.d3d_bvh_overlap(
+            ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
+            ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._count), None,
+            ptr(self._qws), c_size(self._qws.numel()), _lib.stream_ptr()))
+        return out, self._count
+
     def overlap_self(self, capacity=None, out=None, count_visits=False, packet=None):
         """Tree against its own leaves, queries walked in Morton order."""
         return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order(), out=out,
