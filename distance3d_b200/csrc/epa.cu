@@ -148,8 +148,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 vis_lo = __ballot_sync(FULL, v0);
                 vis_hi = __ballot_sync(FULL, v1);
             }
-            // replay of the swap-with-last loop on slot indices (lane 0), removal order in perm
-            // perm[s] = original slot whose face ends up in slot s
+            // replay of the reference's swap-with-last loop on slot indices:
+            // perm[s] = original slot of the face that ends up in slot s
 #pragma unroll 1
             for (int i = lane; i < n_faces; i += 32) W.perm[i] = i;
             __syncwarp();
@@ -167,10 +167,9 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                         v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);
                         bool match = false;
                         if (lane < n_loose) {
-                            {  // np.linalg.norm(x) < eps without the square root (exactly equivalent)
-                                v3 d0 = W.lget(lane, 1) - e0, d1 = W.lget(lane, 0) - e1;
-                                match = dot_blas(d0, d0) < prm.eps_sq_thr && dot_blas(d1, d1) < prm.eps_sq_thr;
-                            }
+                            // np.linalg.norm(x) < eps without the square root (exactly equivalent)
+                            v3 d0 = W.lget(lane, 1) - e0, d1 = W.lget(lane, 0) - e1;
+                            match = dot_blas(d0, d0) < prm.eps_sq_thr && dot_blas(d1, d1) < prm.eps_sq_thr;
                         }
                         unsigned mm = __ballot_sync(FULL, match);
                         int found = mm ? __ffs(mm) - 1 : -1;  // first matching edge wins
