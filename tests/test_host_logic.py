@@ -138,3 +138,38 @@ def test_self_collision_whitelists_match_survey():
     fast_transform_manager_initialization(tm2, [1, 2, 3], "base")
     fast_transform_manager_initialization(tm2, [4, 5], 1)
     np.testing.assert_allclose(tm2.get_transform(5, "base"), np.eye(4))
+
+
+def test_c_abi_argument_checks_without_a_gpu():
+    """Misuse is reported through return codes + d3d_last_error_string before any CUDA call."""
+    so = os.path.join(REPO, "distance3d_b200", "libd3d_b200.so")
+    lib = ctypes.CDLL(so)
+    lib.d3d_last_error_string.restype = ctypes.c_char_p
+    lib.d3d_gjk_workspace_bytes.restype = ctypes.c_size_t
+    lib.d3d_bvh_workspace_bytes.restype = ctypes.c_size_t
+    lib.d3d_bvh_query_workspace_bytes.restype = ctypes.c_size_t
+    i64, dbl, vp = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+    # workspace sizes grow with the problem and never return 0
+    assert 0 < lib.d3d_gjk_workspace_bytes(i64(0)) < lib.d3d_gjk_workspace_bytes(i64(1 << 20))
+    assert 0 < lib.d3d_bvh_workspace_bytes(i64(1)) < lib.d3d_bvh_workspace_bytes(i64(1 << 20))
+    assert lib.d3d_bvh_query_workspace_bytes(i64(1 << 20)) >= (1 << 20) * 12
+    # empty batches are a no-op
+    assert lib.d3d_gjk_distance(None, None, i64(0), dbl(1e-10), dbl(1e5), dbl(1e-8), None, None, None,
+                                None, None, None, None, None, ctypes.c_size_t(0), None) == 0
+    assert lib.d3d_epa(None, None, i64(0), None, 64, 32, 64, dbl(1e-8), None, None, None, None, None,
+                       None, None, ctypes.c_size_t(0), None) == 0
+    # null arguments / bad limits
+    assert lib.d3d_gjk_distance(None, None, i64(5), dbl(1e-10), dbl(1e5), dbl(1e-8), None, None, None,
+                                None, None, None, None, None, ctypes.c_size_t(0), None) == -1
+    assert b"null argument" in lib.d3d_last_error_string()
+    cs = pack.pack_colliders([C.Sphere(np.zeros(3), 1.0)]).host_struct()
+    dummy = (ctypes.c_double * 64)()
+    pairs = (ctypes.c_int32 * 2)(0, 0)
+    rc = lib.d3d_epa(ctypes.byref(cs), pairs, i64(1), dummy, 64, 32, 65, dbl(1e-8), dummy,
+                     ctypes.cast(dummy, vp), None, None, None, None, ctypes.cast(dummy, vp),
+                     ctypes.c_size_t(512), None)
+    assert rc == -1 and b"max_faces" in lib.d3d_last_error_string()
+    assert lib.d3d_bvh_build(None, i64(-1), ctypes.cast(dummy, vp), ctypes.c_size_t(512), None) == -1
+    assert b"out of range" in lib.d3d_last_error_string()
+    assert lib.d3d_bvh_build(dummy, i64(1000), ctypes.cast(dummy, vp), ctypes.c_size_t(512), None) == -1
+    assert b"workspace too small" in lib.d3d_last_error_string()
