@@ -176,16 +176,24 @@ D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
     }
 }
 
-template <int G, class C>
+// TM = bit mask of the type tags this instance can meet: cases outside it are compiled out.
+// The GJK thread kernel has an instance for batches of analytic primitives only
+// (D3D_PRIMITIVE_MASK): the kernel is instruction-fetch bound and unused cases cost run time
+// (scripts/sweep_masks.sh: +6 % on the C1 mix, +13 % for a sphere-only instance).
+#define D3D_ALL_TYPES_MASK 0x3ff
+#define D3D_PRIMITIVE_MASK 0x1f  // sphere, capsule, box, ellipsoid, cylinder
+#define D3D_HAS(t) ((TM >> (t)) & 1)
+
+template <int G, int TM = D3D_ALL_TYPES_MASK, class C>
 D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     switch (c.type) {
-    case D3D_SPHERE: {  // geometry.py:341-346
+    case D3D_SPHERE: if (D3D_HAS(D3D_SPHERE)) {  // geometry.py:341-346
         real s = norm3(d);
         v3 ctr = V3(c.tx(), c.ty(), c.tz());
         if (s == R(0.0)) return ctr + V3(R(0.0), R(0.0), c.p0());
         return ctr + (d / s) * c.p0();
     }
-    case D3D_CAPSULE: {  // geometry.py:243-256
+    case D3D_CAPSULE: if (D3D_HAS(D3D_CAPSULE)) {  // geometry.py:243-256
         v3 l = rot_t(c, d);
         real s = dsqrt(l.x * l.x + l.y * l.y + l.z * l.z);
         v3 v;
@@ -195,7 +203,7 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         else v.z -= R(0.5) * c.p1();
         return xform(c, v);
     }
-    case D3D_CYLINDER: {  // geometry.py:194-206
+    case D3D_CYLINDER: if (D3D_HAS(D3D_CYLINDER)) {  // geometry.py:194-206
         v3 l = rot_t(c, d);
         real s = dsqrt(l.x * l.x + l.y * l.y);
         real z = (l.z < R(0.0)) ? -R(0.5) * c.p1() : R(0.5) * c.p1();
@@ -204,12 +212,12 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         else { real k = ddiv(c.p0(), s); v = V3(l.x * k, l.y * k, z); }
         return xform(c, v);
     }
-    case D3D_ELLIPSOID: {  // geometry.py:282-284
+    case D3D_ELLIPSOID: if (D3D_HAS(D3D_ELLIPSOID)) {  // geometry.py:282-284
         v3 r = V3(c.p0(), c.p1(), c.p2());
         v3 l = rot_t(c, d);
         return xform(c, vmul(normalized(vmul(l, r)), r));
     }
-    case D3D_BOX: {  // colliders.py:132 over the 8 vertices of geometry.py:157
+    case D3D_BOX: if (D3D_HAS(D3D_BOX)) {  // colliders.py:132 over the 8 vertices of geometry.py:157
         if (G == 1) {
             v3 bestv = box_vertex(c, 0);
             real best = gemv_row(bestv.x, bestv.y, bestv.z, d);
@@ -224,12 +232,12 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         return ld3(c.V + 3 * argmax_dot<G>(c.V, 8, d, lane));
     }
     case D3D_HULL:  // colliders.py:131-132
-        return ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, d, lane));
-    case D3D_MESH: {  // mesh.py:182-189 (arg-max form)
+        if (D3D_HAS(D3D_HULL)) return ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, d, lane));
+    case D3D_MESH: if (D3D_HAS(D3D_MESH)) {  // mesh.py:182-189 (arg-max form)
         v3 l = rot_t(c, d);
         return xform(c, ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, l, lane)));
     }
-    case D3D_DISK: {  // geometry.py:375-383
+    case D3D_DISK: if (D3D_HAS(D3D_DISK)) {  // geometry.py:375-383
         v3 ctr = V3(c.tx(), c.ty(), c.tz());
         v3 n = V3(c.r02(), c.r12(), c.r22());
         v3 x, y;
@@ -241,7 +249,7 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         return V3(ctr.x + gemv_row(x.x, y.x, n.x, pt), ctr.y + gemv_row(x.y, y.y, n.y, pt),
                   ctr.z + gemv_row(x.z, y.z, n.z, pt));
     }
-    case D3D_ELLIPSE: {  // geometry.py:412-414
+    case D3D_ELLIPSE: if (D3D_HAS(D3D_ELLIPSE)) {  // geometry.py:412-414
         v3 a0 = V3(c.r00(), c.r10(), c.r20()), a1 = V3(c.r01(), c.r11(), c.r21());
         real l0 = gemv_row(a0.x, a0.y, a0.z, d), l1 = gemv_row(a1.x, a1.y, a1.z, d);
         real w0 = c.p0() * l0, w1 = c.p1() * l1;
@@ -251,7 +259,7 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         return V3(c.tx() + fma(w1, a1.x, w0 * a0.x), c.ty() + fma(w1, a1.y, w0 * a0.y),
                   c.tz() + fma(w1, a1.z, w0 * a0.z));
     }
-    case D3D_CONE: {  // geometry.py:443-454
+    case D3D_CONE: if (D3D_HAS(D3D_CONE)) {  // geometry.py:443-454
         v3 l = rot_t(c, d);
         v3 dp = V3(l.x, l.y, R(0.0));
         real nrm = norm3(dp);
@@ -264,9 +272,9 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     return V3(R(0.0), R(0.0), R(0.0));
 }
 
-template <int G, class C>
+template <int G, int TM = D3D_ALL_TYPES_MASK, class C>
 D3D_DEV v3 support(const C &c, v3 d, int lane) {
-    v3 s = support_unmargined<G>(c, d, lane);
+    v3 s = support_unmargined<G, TM>(c, d, lane);
     if (c.margin() != R(0.0)) s = s + normalized(d) * c.margin();  // colliders.py:629-631
     return s;
 }

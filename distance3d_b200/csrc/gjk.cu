@@ -32,8 +32,10 @@
 namespace {
 
 struct GjkWorkspace {
-    int *counters;  // [0] next sorted index (thread kernel), [1] next (warp kernel),
-                    // [2] #pairs handled by the thread kernel, [3] total
+    int *counters;  // sorted order = [primitive-only bins | other thread bins | wide bin]
+                    // [0] next index, primitive instance of the thread kernel
+                    // [1] next index, warp kernel      [5] next index, generic thread kernel
+                    // [4] end of the primitive range   [2] end of the thread ranges   [3] total
     int *hist;      // [128]
     int *cursor;    // [128]
     uint8_t *keys;  // [P]
@@ -81,17 +83,38 @@ __global__ void k_pair_keys(d3d_colliders c, const int32_t *__restrict__ pairs, 
         if (sh[i]) atomicAdd(&w.hist[i], sh[i]);
 }
 
-__global__ void k_bin_scan(GjkWorkspace w, int64_t n) {
+__global__ void k_bin_scan(GjkWorkspace w, int64_t n, int split_min) {
+    __shared__ int hist[D3D_NBINS];
+    for (int i = threadIdx.x; i < D3D_NBINS; i += blockDim.x) hist[i] = w.hist[i];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < D3D_NBINS; ++i) {
-            int h = w.hist[i];
-            w.cursor[i] = acc;
-            if (i == D3D_WIDE_BIN) w.counters[2] = acc;
-            acc += h;
+        // Split the thread-kernel bins into [two analytic primitives | the rest] when the
+        // rest is empty or both parts are large; for small mixed batches the second launch
+        // tail costs more than the primitive instance saves (1 Mi pairs with 30 % hulls:
+        // 1.73e8 split vs 1.90e8 unsplit) and everything goes to the generic instance.
+        int n_prim = 0, n_rest = 0;
+        for (int i = 0; i < D3D_WIDE_BIN; ++i) {
+            bool prim = ((D3D_PRIMITIVE_MASK >> (i / D3D_NUM_TYPES)) & 1) &&
+                        ((D3D_PRIMITIVE_MASK >> (i % D3D_NUM_TYPES)) & 1);
+            if (prim) n_prim += hist[i]; else n_rest += hist[i];
         }
+        const bool split = n_prim > 0 && (n_rest == 0 || (n_prim >= split_min && n_rest >= split_min));
+        int acc = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = 0; i < D3D_WIDE_BIN; ++i) {
+                bool prim = split && ((D3D_PRIMITIVE_MASK >> (i / D3D_NUM_TYPES)) & 1) &&
+                            ((D3D_PRIMITIVE_MASK >> (i % D3D_NUM_TYPES)) & 1);
+                if (prim != (pass == 0)) continue;
+                w.cursor[i] = acc;
+                acc += hist[i];
+            }
+            w.counters[pass == 0 ? 4 : 2] = acc;
+        }
+        w.cursor[D3D_WIDE_BIN] = acc;
+        acc += hist[D3D_WIDE_BIN];
         w.counters[0] = 0;
         w.counters[1] = 0;
+        w.counters[5] = 0;
         w.counters[3] = acc;
     }
 }
@@ -190,12 +213,12 @@ D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32
 // One shared copy of the ten-way support switch per kernel: both colliders of a pair
 // go through it (two calls), and because pairs are processed in (typeA, typeB) order
 // the switch is warp-uniform almost always.
-template <int G, int STRIDE>
+template <int G, int STRIDE, int TM>
 static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const real *base,
                                                real dx, real dy, real dz, int lane) {
     ColliderSmem<STRIDE> c;
     c.type = type; c.nv = nv; c.V = V; c.base = base;
-    return support<G>(c, V3(dx, dy, dz), lane);
+    return support<G, TM>(c, V3(dx, dy, dz), lane);
 }
 
 // max(|Y_i|^2) over the slots selected by mask (_gjk_jolt.py:634-640)
@@ -213,12 +236,12 @@ D3D_DEV real max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
 
 // First half of _distance_loop (MODE 0, _gjk_jolt.py:228-242) / _intersection_loop (MODE 1,
 // :86-97).  Returns true when the simplex solve is needed.
-template <int MODE, int G, int STRIDE>
+template <int MODE, int G, int STRIDE, int TM>
 D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return false; }
     ++s.iters;
-    v3 p = support_call<G, STRIDE>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
-    v3 q = support_call<G, STRIDE>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
+    v3 p = support_call<G, STRIDE, TM>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
+    v3 q = support_call<G, STRIDE, TM>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
     v3 w = p - q;
     real dot = dot_blas(s.sd, w);
     if (MODE == 0) {
@@ -317,7 +340,7 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
 // Whole iteration with the per-lane solver (warp-per-pair kernel: all lanes are in step).
 template <int MODE, int G, int STRIDE>
 D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
-    if (!gjk_pre<MODE, G, STRIDE>(s, S, prm, lane)) return;
+    if (!gjk_pre<MODE, G, STRIDE, D3D_ALL_TYPES_MASK>(s, S, prm, lane)) return;
     v3 v_new;
     real v_len_sq_new;
     int simplex;
@@ -504,8 +527,14 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
 #endif
 // refill when at least this many lanes of the warp are idle
 
-// One thread per pair, persistent, lanes refill from a warp-private chunk.
-template <int MODE>
+// One thread per pair, persistent, lanes refill from a warp-private chunk.  Two instances per
+// mode: TM = D3D_PRIMITIVE_MASK walks the sorted range of primitive-only bins with a support
+// switch compiled for those five types (the kernel is instruction-fetch bound: +5 % on the C1
+// mix), TM = D3D_ALL_TYPES_MASK the remaining thread bins.  They are separate launches: one
+// kernel that runs both loops back to back measured 10 % SLOWER than the generic kernel alone
+// (2.40e8 vs 2.53e8 vs 2.66e8 pairs/s for the split), the larger kernel image costs more
+// than the saved launch tail.
+template <int MODE, int TM>
 __global__ void __launch_bounds__(GJK_THREADS, GJK_BLOCKS_PER_SM)
 k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
     extern __shared__ real smem[];
@@ -524,7 +553,10 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
     }
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
-    const int total = w.counters[2];
+    const bool prim = (TM == D3D_PRIMITIVE_MASK);
+    const int first = prim ? 0 : w.counters[4];
+    const int total = prim ? w.counters[4] : w.counters[2];
+    int *next = &w.counters[prim ? 0 : 5];
     int chunk_begin = 0, chunk_end = 0;
     bool exhausted = false;
     PairState<GJK_THREADS> s;
@@ -545,8 +577,8 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
                 while (handed < want && !exhausted) {
                     if (chunk_begin == chunk_end) {
                         int start = 0;
-                        if (lane == 0) start = atomicAdd(&w.counters[0], GJK_CHUNK);
-                        start = __shfl_sync(0xffffffffu, start, 0);
+                        if (lane == 0) start = atomicAdd(next, GJK_CHUNK);
+                        start = __shfl_sync(0xffffffffu, start, 0) + first;
                         if (start >= total) { exhausted = true; break; }
                         chunk_begin = start;
                         chunk_end = min(start + GJK_CHUNK, total);
@@ -564,7 +596,7 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
             run_mask = __ballot_sync(0xffffffffu, running);
             if (run_mask == 0) break;
         }
-        bool solve = running && gjk_pre<MODE, 1, GJK_THREADS>(s, S, prm, 0);
+        bool solve = running && gjk_pre<MODE, 1, GJK_THREADS, TM>(s, S, prm, 0);
         v3 v_new = V3(R(0.0), R(0.0), R(0.0));
         real v_len_sq_new = R(0.0);
         int simplex = 0;
@@ -620,12 +652,19 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
         hull_max = e ? atoi(e) : D3D_THREAD_HULL_MAX_DEFAULT;
     }
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
-    k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs);
+    k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs, sms * GJK_BLOCKS_PER_SM * GJK_THREADS * 8);
     k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
     size_t smem = sizeof(real) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
-    D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;  // per MODE instance of this function
+    if (!attr_set) {
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_PRIMITIVE_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_ALL_TYPES_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
-    k_gjk_thread<MODE><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    // ranges are read on the device; an instance whose range is empty exits at once
+    k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    k_gjk_thread<MODE, D3D_ALL_TYPES_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     int wblocks = (int)d3d_min64((n_pairs + 3) / 4, (int64_t)sms * 3);
     k_gjk_warp<MODE><<<wblocks, GJK_THREADS, 0, stream>>>(*c, pairs, w, prm);
     D3D_CUDA_CHECK(cudaGetLastError());

@@ -28,6 +28,7 @@ for a in names:
         cs=ColliderSet(type_,pose,param,vo,vl,np.concatenate([csa.verts[:int(csa.vert_len.sum())] if csa.vert_len.sum() else np.zeros((0,3)), csb.verts[:int(csb.vert_len.sum())] if csb.vert_len.sum() else np.zeros((0,3))]))
         pairs=np.stack([np.arange(n),np.arange(n)+n],axis=1).astype(np.int32)
         run(cs,pairs,a+"-"+b)
+if os.environ.get("D3D_SKIP_MIX"): sys.exit(0)
 rs=np.random.RandomState(1)
 cs=R.random_collider_set(rs,2*n,names=R.PRIMITIVES); pairs=np.arange(2*n,dtype=np.int32).reshape(n,2)
 run(cs,pairs,"mix")
