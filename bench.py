@@ -573,7 +573,7 @@ def main():
                 # full capture of a 1 Mi-pair launch (profiles/r01_ncu_k_gjk_thread_final.txt:
                 # 751.2 MB + 273.1 MB), scaled to this launch; algorithmic bytes are 496 B per pair
                 "traffic": n * NCU_DRAM_BYTES_PER_PAIR, "traffic_unit": "bytes per launch",
-                "kernel": "k_gjk_thread<0>",
+                "kernel": "k_gjk_thread<0, primitive instance>",
                 "note": "algorithmic flop = pairs x mean_iters x 350 (SURVEY 8d); peak = FP64 FMA "
                         "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_achieved_gbs": per_gpu * BYTES_PER_PAIR / 1e9,
@@ -584,7 +584,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "api": "stream.GjkDistanceStream (2 slots)",
                     "result_equals_device_run": e2e_ok},
-            "gpu_launches": 5 * args.steps,
+            # k_pair_keys, k_bin_scan, k_bin_scatter, k_gjk_thread x2 (primitive / generic instance),
+            # k_gjk_finish, k_gjk_warp
+            "gpu_launches": 7 * args.steps,
             "fp32_mode": fp32_mode,
             "clocks": clocks,
         }

@@ -39,8 +39,9 @@ def lib():
                 % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
         L.d3d_last_error_string.restype = ctypes.c_char_p
-        L.d3d_gjk_workspace_bytes.restype = c_size
-        L.d3d_gjk_workspace_bytes.argtypes = [c_i64]
+        for name in ("d3d_gjk_workspace_bytes", "d3d_gjk_intersection_workspace_bytes"):
+            getattr(L, name).restype = c_size
+            getattr(L, name).argtypes = [c_i64]
         for name in ("d3d_epa_workspace_bytes", "d3d_bvh_workspace_bytes",
                      "d3d_bvh_query_workspace_bytes"):
             if hasattr(L, name):

@@ -182,6 +182,7 @@ D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
 // (scripts/sweep_masks.sh: +6 % on the C1 mix, +13 % for a sphere-only instance).
 #define D3D_ALL_TYPES_MASK 0x3ff
 #define D3D_PRIMITIVE_MASK 0x1f  // sphere, capsule, box, ellipsoid, cylinder
+#define D3D_VERTEX_MASK 0x64     // box, hull, mesh: arg-max over a vertex list
 #define D3D_HAS(t) ((TM >> (t)) & 1)
 
 template <int G, int TM = D3D_ALL_TYPES_MASK, class C>
@@ -283,9 +284,9 @@ D3D_DEV v3 support(const C &c, v3 d, int lane) {
 // records in registers / local memory (EPA, MPR): one copy of the code instead of one per call
 // site (the MPR kernel shrank from 209 KB to a fraction of that; these kernels are
 // instruction-fetch bound).
-template <int G>
+template <int G, int TM = D3D_ALL_TYPES_MASK>
 static __device__ __noinline__ v3 support_ni(const Collider &c, real dx, real dy, real dz, int lane) {
-    return support<G>(c, V3(dx, dy, dz), lane);
+    return support<G, TM>(c, V3(dx, dy, dz), lane);
 }
 
 // colliders.py center(); hull / mesh means are sequential column sums (np.mean axis 0)

@@ -40,12 +40,19 @@ struct GjkWorkspace {
     int *cursor;    // [128]
     uint8_t *keys;  // [P]
     int *perm;      // [P]
+    int64_t n_pairs;
+    real *fin;      // [P][GJK_FIN_FIELDS] final state of the thread-kernel pairs (distance mode)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline size_t gjk_ws_bytes(int64_t n) {
-    return 4096 + align_up((size_t)n, 256) + align_up((size_t)n * 4, 256);
+// Distance mode: the thread kernel parks the final simplex of every pair in the workspace
+// (41 values per pair) and k_gjk_finish turns it into closest
+// points afterwards; see k_gjk_finish for why.
+#define GJK_FIN_FIELDS 41
+inline size_t gjk_ws_bytes(int64_t n, bool distance) {
+    return 4096 + align_up((size_t)n, 256) + align_up((size_t)n * 4, 256) +
+           (distance ? (size_t)n * GJK_FIN_FIELDS * sizeof(double) : 0);
 }
 
 inline GjkWorkspace carve(void *ws, int64_t n) {
@@ -56,6 +63,8 @@ inline GjkWorkspace carve(void *ws, int64_t n) {
     w.cursor = reinterpret_cast<int *>(p + 2048);
     w.keys = reinterpret_cast<uint8_t *>(p + 4096);
     w.perm = reinterpret_cast<int *>(p + 4096 + align_up((size_t)n, 256));
+    w.n_pairs = n;
+    w.fin = reinterpret_cast<real *>(p + 4096 + align_up((size_t)n, 256) + align_up((size_t)n * 4, 256));
     return w;
 }
 
@@ -119,21 +128,34 @@ __global__ void k_bin_scan(GjkWorkspace w, int64_t n, int split_min) {
     }
 }
 
-__global__ void k_bin_scatter(int64_t n, GjkWorkspace w) {
-    for (int64_t k0 = blockIdx.x * (int64_t)blockDim.x; k0 < n; k0 += (int64_t)gridDim.x * blockDim.x) {
-        int64_t k = k0 + threadIdx.x;
-        bool valid = k < n;
-        int key = valid ? w.keys[k] : -1;
-        unsigned active = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            unsigned peers = __match_any_sync(active, key);
-            int leader = __ffs(peers) - 1;
-            int lane = threadIdx.x & 31;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&w.cursor[key], __popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            w.perm[base + __popc(peers & ((1u << lane) - 1))] = (int)k;
+// Counting-sort scatter.  A block ranks a tile of keys in a shared-memory histogram and
+// reserves one range per (tile, bin) with a single global atomic: the batch has a few dozen
+// distinct keys, so per-warp reservations serialise on the same few addresses (4 Mi pairs:
+// 0.49 ms with one atomic per warp and key, profiles/r01_launches_final.csv).
+#define BIN_TILE_ITEMS 8
+__global__ void __launch_bounds__(256) k_bin_scatter(int64_t n, GjkWorkspace w) {
+    __shared__ int hist[D3D_NBINS];
+    const int64_t tile = 256 * BIN_TILE_ITEMS;
+    for (int64_t t0 = blockIdx.x * tile; t0 < n; t0 += (int64_t)gridDim.x * tile) {
+        for (int i = threadIdx.x; i < D3D_NBINS; i += 256) hist[i] = 0;
+        __syncthreads();
+        int key[BIN_TILE_ITEMS], rank[BIN_TILE_ITEMS];
+#pragma unroll
+        for (int j = 0; j < BIN_TILE_ITEMS; ++j) {
+            int64_t k = t0 + j * 256 + threadIdx.x;
+            key[j] = k < n ? w.keys[k] : -1;
+            if (key[j] >= 0) rank[j] = atomicAdd(&hist[key[j]], 1);
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D3D_NBINS; i += 256) {
+            int h = hist[i];
+            hist[i] = h ? atomicAdd(&w.cursor[i], h) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BIN_TILE_ITEMS; ++j)
+            if (key[j] >= 0) w.perm[hist[key[j]] + rank[j]] = (int)(t0 + j * 256 + threadIdx.x);
+        __syncthreads();
     }
 }
 
@@ -458,10 +480,10 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
     return false;
 }
 
-// Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).
-template <int MODE, int STRIDE>
-D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm,
-                        bool writer) {
+// Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).  PS: PairState or
+// FinState, SX: Simplex or SimplexFin.
+template <int MODE, class PS, class SX>
+D3D_DEV void gjk_finish(const PS &s, const SX &S, const GjkParams &prm, bool writer) {
     int64_t k = s.k;
     int state = s.state;
     if (MODE == 1) {
@@ -527,6 +549,78 @@ D3D_DEV void gjk_finish(const PairState<STRIDE> &s, const Simplex<STRIDE> &S, co
 #endif
 // refill when at least this many lanes of the warp are idle
 
+// ---------------------------------------------------------------------------
+// Deferred finish (thread kernel, distance mode).  gjk_finish is ~480 instructions, run by
+// the few lanes of a warp that have just finished a pair; inside the persistent kernel it
+// is 28 % of the loop's instruction footprint, and the kernel is instruction-fetch bound
+// (B200, 1 Mi mixed pairs: 2.17e8 pairs/s with the finish inline, 2.53e8 with the finish
+// stubbed out).  So the kernel only parks the final state and k_gjk_finish, one convergent
+// thread per pair, produces the outputs.
+struct FinState {
+    v3 sd;
+    real v_len_sq;
+    int n_points, iters, k, state;
+};
+struct SimplexFin {  // Y, P, Q of one parked pair (record of GJK_FIN_FIELDS values)
+    const real *base;
+    D3D_DEV v3 get(int off, int s) const {
+        const real *p = base + (off - GJK_OFF_Y + 3 * s);
+        return V3(p[0], p[1], p[2]);
+    }
+};
+#ifdef D3D_F32
+D3D_DEV real fin_pack(int v) { return __int_as_float(v); }
+D3D_DEV int fin_unpack(real v) { return __float_as_int(v); }
+#else
+D3D_DEV real fin_pack(int v) { return __longlong_as_double((long long)v); }
+D3D_DEV int fin_unpack(real v) { return (int)__double_as_longlong(v); }
+#endif
+
+template <int MODE>
+D3D_DEV void gjk_finish_or_park(const PairState<GJK_THREADS> &s, const Simplex<GJK_THREADS> &S,
+                                const GjkParams &prm, const GjkWorkspace &w) {
+    if (MODE == 1) {
+        gjk_finish<1>(s, S, prm, true);
+        return;
+    }
+    // one contiguous record per pair, indexed by the pair's number k: the stores of a lane
+    // fill whole sectors and k_gjk_finish reads and writes in pair order
+    real *o = w.fin + (int64_t)s.k * GJK_FIN_FIELDS;
+#pragma unroll 1
+    for (int i = 0; i < s.n_points; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            o[3 * i + j] = S.at(GJK_OFF_Y, i, j);
+            o[12 + 3 * i + j] = S.at(GJK_OFF_P, i, j);
+            o[24 + 3 * i + j] = S.at(GJK_OFF_Q, i, j);
+        }
+    }
+    o[36] = s.sd.x;
+    o[37] = s.sd.y;
+    o[38] = s.sd.z;
+    o[39] = s.v_len_sq;
+    o[40] = fin_pack(s.n_points | (s.state << 4) | (s.iters << 8));
+}
+
+// Pairs of the warp kernel (wide hulls) are finished by that kernel: their key is the wide bin.
+__global__ void __launch_bounds__(256) k_gjk_finish(GjkWorkspace w, GjkParams prm) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < w.n_pairs;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        if (w.keys[k] == D3D_WIDE_BIN) continue;
+        SimplexFin S;
+        S.base = w.fin + k * GJK_FIN_FIELDS;
+        FinState s;
+        s.sd = V3(S.base[36], S.base[37], S.base[38]);
+        s.v_len_sq = S.base[39];
+        int packed = fin_unpack(S.base[40]);
+        s.n_points = packed & 15;
+        s.state = (packed >> 4) & 15;
+        s.iters = packed >> 8;
+        s.k = (int)k;
+        gjk_finish<0>(s, S, prm, true);
+    }
+}
+
 // One thread per pair, persistent, lanes refill from a warp-private chunk.  Two instances per
 // mode: TM = D3D_PRIMITIVE_MASK walks the sorted range of primitive-only bins with a support
 // switch compiled for those five types (the kernel is instruction-fetch bound: +5 % on the C1
@@ -568,7 +662,7 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
         unsigned run_mask = __ballot_sync(0xffffffffu, running);
         int idle = 32 - __popc(run_mask);
         if (idle >= GJK_REFILL_MIN || run_mask == 0) {
-            if (finished) { gjk_finish<MODE, GJK_THREADS>(s, S, prm, true); finished = false; }
+            if (finished) { gjk_finish_or_park<MODE>(s, S, prm, w); finished = false; }
             if (!exhausted) {
                 unsigned need = ~run_mask;
                 int rank = __popc(need & lt_mask);
@@ -631,7 +725,7 @@ k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, G
             gjk_step<MODE, 32, 1>(s, S, prm, lane);
             __syncwarp();
         }
-        gjk_finish<MODE, 1>(s, S, prm, lane == 0);
+        gjk_finish<MODE>(s, S, prm, lane == 0);
         __syncwarp();
     }
 }
@@ -641,7 +735,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
                void *workspace, size_t ws_bytes, cudaStream_t stream) {
     if (n_pairs == 0) return 0;
     if (n_pairs > 0x7fffffff) return d3d_set_error("d3d_gjk: more than 2^31-1 pairs in one call");
-    if (ws_bytes < gjk_ws_bytes(n_pairs)) return d3d_set_error("d3d_gjk: workspace too small");
+    if (ws_bytes < gjk_ws_bytes(n_pairs, MODE == 0)) return d3d_set_error("d3d_gjk: workspace too small");
     GjkWorkspace w = carve(workspace, n_pairs);
     D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 4096, stream));
     int sms = d3d_sm_count();
@@ -653,7 +747,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     }
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs, sms * GJK_BLOCKS_PER_SM * GJK_THREADS * 8);
-    k_bin_scatter<<<bin_blocks, 256, 0, stream>>>(n_pairs, w);
+    k_bin_scatter<<<(int)d3d_min64((n_pairs + 256 * BIN_TILE_ITEMS - 1) / (256 * BIN_TILE_ITEMS), (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, w);
     size_t smem = sizeof(real) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
     static bool attr_set = false;  // per MODE instance of this function
     if (!attr_set) {
@@ -665,6 +759,8 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     // ranges are read on the device; an instance whose range is empty exits at once
     k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     k_gjk_thread<MODE, D3D_ALL_TYPES_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    if (MODE == 0)
+        k_gjk_finish<<<(int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8), 256, 0, stream>>>(w, prm);
     int wblocks = (int)d3d_min64((n_pairs + 3) / 4, (int64_t)sms * 3);
     k_gjk_warp<MODE><<<wblocks, GJK_THREADS, 0, stream>>>(*c, pairs, w, prm);
     D3D_CUDA_CHECK(cudaGetLastError());
@@ -683,7 +779,8 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
 extern "C" {
 
 #ifndef D3D_F32
-size_t d3d_gjk_workspace_bytes(int64_t n_pairs) { return gjk_ws_bytes(n_pairs); }
+size_t d3d_gjk_workspace_bytes(int64_t n_pairs) { return gjk_ws_bytes(n_pairs, true); }
+size_t d3d_gjk_intersection_workspace_bytes(int64_t n_pairs) { return gjk_ws_bytes(n_pairs, false); }
 #endif
 
 int D3D_GJK_SYM(d3d_gjk_distance)(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs,

@@ -122,7 +122,7 @@ def gjk_intersection_batch(colliders, pairs, tolerance=1e-10, want_iters=False, 
     iters = torch.empty(n, dtype=torch.int32, device=dc.device) if want_iters else None
     status = torch.empty(n, dtype=torch.int32, device=dc.device)
     L = _lib.lib()
-    ws_bytes = L.d3d_gjk_workspace_bytes(c_i64(n))
+    ws_bytes = L.d3d_gjk_intersection_workspace_bytes(c_i64(n))
     ws = workspace(ws_bytes, dc.device)
     fn = L.d3d_gjk_intersection if dtype == "f64" else L.d3d_gjk_intersection_f32
     _lib._check(fn(

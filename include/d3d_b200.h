@@ -53,8 +53,11 @@ int d3d_center(const d3d_colliders *c, double *out, void *stream);
  * (containment.py:6-229): out[n,3,2] = [[xmin,xmax],[ymin,ymax],[zmin,zmax]]. */
 int d3d_aabb(const d3d_colliders *c, double *out, void *stream);
 
-/* Workspace size for d3d_gjk_distance / d3d_gjk_intersection over n_pairs pairs. */
+/* Workspace sizes over n_pairs pairs.  d3d_gjk_distance needs ~333 B per pair (the pair
+ * order by collider types plus the parked final simplex of every pair), d3d_gjk_intersection
+ * 5 B per pair.  The larger size is accepted by both calls. */
 size_t d3d_gjk_workspace_bytes(int64_t n_pairs);
+size_t d3d_gjk_intersection_workspace_bytes(int64_t n_pairs);
 
 /* gjk/_gjk_jolt.py:138-221 gjk_distance_jolt (= gjk.gjk, gjk/__init__.py:27) for
  * pairs[k] = (index of collider 1, index of collider 2):
