@@ -185,8 +185,18 @@ D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
 #define D3D_VERTEX_MASK 0x64     // box, hull, mesh: arg-max over a vertex list
 #define D3D_HAS(t) ((TM >> (t)) & 1)
 
+// Types whose support is evaluated in the collider frame share ONE copy of the world->local
+// rotation of d and of the local->world transform of the result (code size: the GJK kernels
+// are instruction-fetch bound).
+#define D3D_LOCAL_FRAME_MASK ((1 << D3D_CAPSULE) | (1 << D3D_CYLINDER) | (1 << D3D_ELLIPSOID) | \
+                              (1 << D3D_MESH) | (1 << D3D_CONE))
+
 template <int G, int TM = D3D_ALL_TYPES_MASK, class C>
 D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
+    const bool local_frame = (D3D_LOCAL_FRAME_MASK >> c.type) & 1;
+    v3 l = d;
+    if ((TM & D3D_LOCAL_FRAME_MASK) && local_frame) l = rot_t(c, d);
+    v3 v = V3(R(0.0), R(0.0), R(0.0));
     switch (c.type) {
     case D3D_SPHERE: if (D3D_HAS(D3D_SPHERE)) {  // geometry.py:341-346
         real s = norm3(d);
@@ -194,50 +204,49 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         if (s == R(0.0)) return ctr + V3(R(0.0), R(0.0), c.p0());
         return ctr + (d / s) * c.p0();
     }
+    break;
     case D3D_CAPSULE: if (D3D_HAS(D3D_CAPSULE)) {  // geometry.py:243-256
-        v3 l = rot_t(c, d);
         real s = dsqrt(l.x * l.x + l.y * l.y + l.z * l.z);
-        v3 v;
         if (s == R(0.0)) v = V3(c.p0(), R(0.0), R(0.0));
         else v = l * ddiv(c.p0(), s);
         if (l.z > R(0.0)) v.z += R(0.5) * c.p1();
         else v.z -= R(0.5) * c.p1();
-        return xform(c, v);
     }
+    break;
     case D3D_CYLINDER: if (D3D_HAS(D3D_CYLINDER)) {  // geometry.py:194-206
-        v3 l = rot_t(c, d);
         real s = dsqrt(l.x * l.x + l.y * l.y);
         real z = (l.z < R(0.0)) ? -R(0.5) * c.p1() : R(0.5) * c.p1();
-        v3 v;
         if (s == R(0.0)) v = V3(c.p0(), R(0.0), z);
         else { real k = ddiv(c.p0(), s); v = V3(l.x * k, l.y * k, z); }
-        return xform(c, v);
     }
+    break;
     case D3D_ELLIPSOID: if (D3D_HAS(D3D_ELLIPSOID)) {  // geometry.py:282-284
         v3 r = V3(c.p0(), c.p1(), c.p2());
-        v3 l = rot_t(c, d);
-        return xform(c, vmul(normalized(vmul(l, r)), r));
+        v = vmul(normalized(vmul(l, r)), r);
     }
+    break;
     case D3D_BOX: if (D3D_HAS(D3D_BOX)) {  // colliders.py:132 over the 8 vertices of geometry.py:157
         if (G == 1) {
             v3 bestv = box_vertex(c, 0);
             real best = gemv_row(bestv.x, bestv.y, bestv.z, d);
 #pragma unroll 1
             for (int i = 1; i < 8; ++i) {
-                v3 v = box_vertex(c, i);
-                real val = gemv_row(v.x, v.y, v.z, d);
-                if (val > best) { best = val; bestv = v; }
+                v3 bv = box_vertex(c, i);
+                real val = gemv_row(bv.x, bv.y, bv.z, d);
+                if (val > best) { best = val; bestv = bv; }
             }
             return bestv;
         }
         return ld3(c.V + 3 * argmax_dot<G>(c.V, 8, d, lane));
     }
+    break;
     case D3D_HULL:  // colliders.py:131-132
         if (D3D_HAS(D3D_HULL)) return ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, d, lane));
+        break;
     case D3D_MESH: if (D3D_HAS(D3D_MESH)) {  // mesh.py:182-189 (arg-max form)
-        v3 l = rot_t(c, d);
-        return xform(c, ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, l, lane)));
+        v = ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, l, lane));
     }
+    break;
     case D3D_DISK: if (D3D_HAS(D3D_DISK)) {  // geometry.py:375-383
         v3 ctr = V3(c.tx(), c.ty(), c.tz());
         v3 n = V3(c.r02(), c.r12(), c.r22());
@@ -250,6 +259,7 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         return V3(ctr.x + gemv_row(x.x, y.x, n.x, pt), ctr.y + gemv_row(x.y, y.y, n.y, pt),
                   ctr.z + gemv_row(x.z, y.z, n.z, pt));
     }
+    break;
     case D3D_ELLIPSE: if (D3D_HAS(D3D_ELLIPSE)) {  // geometry.py:412-414
         v3 a0 = V3(c.r00(), c.r10(), c.r20()), a1 = V3(c.r01(), c.r11(), c.r21());
         real l0 = gemv_row(a0.x, a0.y, a0.z, d), l1 = gemv_row(a1.x, a1.y, a1.z, d);
@@ -260,17 +270,18 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
         return V3(c.tx() + fma(w1, a1.x, w0 * a0.x), c.ty() + fma(w1, a1.y, w0 * a0.y),
                   c.tz() + fma(w1, a1.z, w0 * a0.z));
     }
+    break;
     case D3D_CONE: if (D3D_HAS(D3D_CONE)) {  // geometry.py:443-454
-        v3 l = rot_t(c, d);
         v3 dp = V3(l.x, l.y, R(0.0));
         real nrm = norm3(dp);
         if (nrm == R(0.0)) dp = V3(R(0.0), R(0.0), R(0.0));
         else dp = dp * (c.p0() / nrm);
-        v3 pt = (dot_blas(l, dp) >= l.z * c.p1()) ? dp : V3(R(0.0), R(0.0), c.p1());
-        return xform(c, pt);
+        v = (dot_blas(l, dp) >= l.z * c.p1()) ? dp : V3(R(0.0), R(0.0), c.p1());
     }
+    break;
     }
-    return V3(R(0.0), R(0.0), R(0.0));
+    if ((TM & D3D_LOCAL_FRAME_MASK) && local_frame) return xform(c, v);
+    return v;
 }
 
 template <int G, int TM = D3D_ALL_TYPES_MASK, class C>
