@@ -432,6 +432,7 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
         for (int todo = faces; todo; todo &= todo - 1) W.desc[j++] = (unsigned char)((lane << 2) | (__ffs(todo) - 1));
         __syncwarp();
         real best_dist_sq = D3D_MAX_FLOAT;
+#pragma unroll 1
         for (int base = 0; base < total; base += 32) {
             int item = base + lane;
             if (item < total) {
@@ -459,6 +460,7 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
             __syncwarp();
             // owners fold their items of this round, ascending face order
             int lo = max(first, base), hi = min(first + cnt, base + 32);
+#pragma unroll 1
             for (int it = lo; it < hi; ++it) {
                 TriResult r = W.res[it - base];
                 int f = W.desc[it] & 3;
@@ -543,7 +545,6 @@ D3D_DEV void gjk_finish(const PS &s, const SX &S, const GjkParams &prm, bool wri
 #define GJK_BLOCKS_PER_SM (GJK_PQ_LOCAL ? 4 : 3)
 #endif
 #endif
-#define GJK_CHUNK 256
 #ifndef GJK_REFILL_MIN
 #define GJK_REFILL_MIN 8
 #endif
@@ -651,7 +652,6 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
     const int first = prim ? 0 : w.counters[4];
     const int total = prim ? w.counters[4] : w.counters[2];
     int *next = &w.counters[prim ? 0 : 5];
-    int chunk_begin = 0, chunk_end = 0;
     bool exhausted = false;
     PairState<GJK_THREADS> s;
     s.state = D3D_UNKNOWN;
@@ -664,27 +664,18 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
         if (idle >= GJK_REFILL_MIN || run_mask == 0) {
             if (finished) { gjk_finish_or_park<MODE>(s, S, prm, w); finished = false; }
             if (!exhausted) {
+                // the idle lanes take the next `want` pairs of the sorted order (one atomic per
+                // refill; consecutive positions share a type bin, so the warp stays uniform)
                 unsigned need = ~run_mask;
-                int rank = __popc(need & lt_mask);
                 int want = __popc(need);
-                int handed = 0;
-                while (handed < want && !exhausted) {
-                    if (chunk_begin == chunk_end) {
-                        int start = 0;
-                        if (lane == 0) start = atomicAdd(next, GJK_CHUNK);
-                        start = __shfl_sync(0xffffffffu, start, 0) + first;
-                        if (start >= total) { exhausted = true; break; }
-                        chunk_begin = start;
-                        chunk_end = min(start + GJK_CHUNK, total);
-                    }
-                    int avail = chunk_end - chunk_begin;
-                    int give = min(avail, want - handed);
-                    if (!running && rank >= handed && rank < handed + give) {
-                        init_pair<GJK_THREADS>(s, c, pairs, __ldg(w.perm + chunk_begin + (rank - handed)), base);
-                        running = true;
-                    }
-                    chunk_begin += give;
-                    handed += give;
+                int start = 0;
+                if (lane == 0) start = atomicAdd(next, want);
+                start = __shfl_sync(0xffffffffu, start, 0) + first;
+                exhausted = start + want >= total;
+                int mine = start + __popc(need & lt_mask);
+                if (!running && mine < total) {
+                    init_pair<GJK_THREADS>(s, c, pairs, __ldg(w.perm + mine), base);
+                    running = true;
                 }
             }
             run_mask = __ballot_sync(0xffffffffu, running);
