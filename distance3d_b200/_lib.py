@@ -147,3 +147,14 @@ def debug_norm(v, mode=0):
     out = torch.empty(len(v_t), dtype=torch.float64, device=dev)
     _check(lib().d3d_debug_norm(ptr(v_t), c_i64(len(v_t)), ptr(out), c_int(mode), stream_ptr()))
     return out.cpu().numpy()
+
+
+def debug_vdiv(v, s):
+    """Test hook: rows of v[n,3] divided by s[n] with the device's vector division."""
+    torch = torch_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    v_t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)).to(dev)
+    s_t = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float64).reshape(-1)).to(dev)
+    out = torch.empty_like(v_t)
+    _check(lib().d3d_debug_vdiv(ptr(v_t), ptr(s_t), c_i64(len(v_t)), ptr(out), stream_ptr()))
+    return out.cpu().numpy()

@@ -175,6 +175,11 @@ __global__ void k_fp64_peak(double *out, int iters) {
     if (s == 123.456) out[0] = s;
 }
 
+__global__ void k_debug_vdiv(const double *v, const double *s, int64_t n, double *out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) st3(out + 3 * k, ld3(v + 3 * k) / s[k]);
+}
+
 __global__ void k_debug_norm(const double *v, int64_t n, double *out, int mode) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -221,6 +226,14 @@ int d3d_aabb(const d3d_colliders *c, double *out, void *stream) {
     if (!c || !out) return d3d_set_error("d3d_aabb: null argument");
     if (c->n == 0) return 0;
     k_aabb<<<(unsigned)((c->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*c, out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* test hook: out[k,:] = v[k,:] / s[k] through the vector division of d3d_math.cuh */
+int d3d_debug_vdiv(const double *v, const double *s, int64_t n, double *out, void *stream) {
+    if (n == 0) return 0;
+    k_debug_vdiv<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, s, n, out);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -35,6 +35,9 @@ int d3d_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * (BLAS dnrm2 on the x87 FPU; mode 0 = production path, 1 = integer emulation only). */
 int d3d_fp64_peak_probe(double *scratch, int blocks, int iters, void *stream);
 int d3d_debug_norm(const double *v, int64_t n, double *out, int mode, void *stream);
+/* out[k,:] = v[k,:] / s[k] through the device's vector division (three IEEE quotients that
+ * share one reciprocal refinement); tests pin it to host division bit for bit. */
+int d3d_debug_vdiv(const double *v, const double *s, int64_t n, double *out, void *stream);
 
 /* geometry.py:138-157 convert_box_to_vertices (called from colliders.py:161-176 on
  * construction and update_pose): writes the 8 world-frame vertices of every BOX of
