@@ -29,7 +29,7 @@ sys.path.insert(0, REPO)
 
 FLOP_PER_ITER = 350.0  # algorithmic flop per GJK iteration (primitives)
 BYTES_PER_PAIR = 496.0  # 336 B in + 160 B out
-NCU_DRAM_BYTES_PER_PAIR = (751.23e6 + 273.09e6) / 1048576  # measured, see roofline.traffic
+NCU_DRAM_BYTES_PER_PAIR = (497.15e6 + 228.49e6) / 1048576  # measured, see roofline.traffic
 
 
 def parse_args():
@@ -570,8 +570,9 @@ def main():
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of k_gjk_thread<0> from the ncu --set
-                # full capture of a 1 Mi-pair launch (profiles/r01_ncu_k_gjk_thread_final.txt:
-                # 751.2 MB + 273.1 MB), scaled to this launch; algorithmic bytes are 496 B per pair
+                # full capture of a 1 Mi-pair launch (profiles/r01_ncu_k_gjk_thread_v6_primitive_instance.txt:
+                # 497.1 MB + 228.5 MB incl. the parked simplices), scaled to this launch; algorithmic
+                # bytes are 496 B per pair
                 "traffic": n * NCU_DRAM_BYTES_PER_PAIR, "traffic_unit": "bytes per launch",
                 "kernel": "k_gjk_thread<0, primitive instance>",
                 "note": "algorithmic flop = pairs x mean_iters x 350 (SURVEY 8d); peak = FP64 FMA "
