@@ -57,14 +57,18 @@ class Lbvh:
                                                  _lib.stream_ptr()))
         return out
 
-    def overlap(self, query, capacity=None, order=None, out=None, count_visits=False, packet=None):
+    def overlap(self, query, capacity=None, order=None, out=None, count_visits=False, packet=None,
+                ordered=True):
         """All (tree index, query index) pairs with overlapping boxes.
 
-        Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  Two passes on
-        the device: the exact count is known before the pair buffer is allocated (pass
-        `out` to re-use a buffer; it is replaced when too small).  `capacity` is accepted
-        for compatibility and ignored.  `packet`: warp-packet traversal (default: on when the
-        queries are spatially ordered, i.e. `order` is given).
+        Returns ``(pairs int32[count, 2], count)`` as device tensor / int.  ordered=True
+        (default): two passes on the device, the exact count is known before the pair buffer
+        is allocated (pass `out` to re-use a buffer; it is replaced when too small) and the
+        pair order is reproducible.  ordered=False: ONE traversal that appends into a buffer
+        of `capacity` pairs (default 16 per query, or the given `out`) and is repeated with the
+        exact size if that was too small; the same set in an arbitrary order, about twice as
+        fast.  `packet`: warp-packet traversal (default: on when the queries are spatially
+        ordered, i.e. `order` is given).
         """
         if packet is None:
             packet = order is not None
@@ -75,6 +79,20 @@ class Lbvh:
         # with `order` only the listed query boxes are processed (e.g. one rank's shard)
         nq = int(order.shape[0]) if order is not None else int(query.shape[0])
         L = _lib.lib()
+        if not ordered:
+            if out is None:
+                out = torch.empty((max(int(capacity or 16 * nq), 1), 2), dtype=torch.int32,
+                                  device=self.device)
+            for _ in range(2):
+                _lib._check(L.d3d_bvh_overlap(
+                    ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
+                    ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._count),
+                    ptr(self._visits) if count_visits else None, None, c_size(0), _lib.stream_ptr()))
+                count = int(self._count.item())
+                if count <= out.shape[0]:
+                    break
+                out = torch.empty((count, 2), dtype=torch.int32, device=self.device)
+            return out[:count], count
         qbytes = L.d3d_bvh_query_workspace_bytes(c_i64(nq))
         if self._qws is None or self._qws.numel() < qbytes:
             self._qws = torch.empty(qbytes, dtype=torch.uint8, device=self.device)
@@ -93,7 +111,8 @@ class Lbvh:
         return out[:count], count
 
     def overlap_async(self, query, out, order=None, packet=None):
-        """Count + fill into a caller-provided buffer without synchronising the host.
+        """Single-pass traversal that appends into a caller-provided buffer without
+        synchronising the host (arbitrary pair order).
 
         Returns ``(out, count)`` where `count` is a device int64 tensor with the exact number of
         pairs (entries beyond ``out.shape[0]`` are dropped; check `count` when in doubt)."""
@@ -103,19 +122,16 @@ class Lbvh:
         if packet is None:
             packet = order is not None
         L = _lib.lib()
-        qbytes = L.d3d_bvh_query_workspace_bytes(c_i64(nq))
-        if self._qws is None or self._qws.numel() < qbytes:
-            self._qws = torch.empty(qbytes, dtype=torch.uint8, device=self.device)
         _lib._check(L.d3d_bvh_overlap(
             ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
             ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._count), None,
-            ptr(self._qws), c_size(self._qws.numel()), _lib.stream_ptr()))
+            None, c_size(0), _lib.stream_ptr()))
         return out, self._count
 
-    def overlap_self(self, capacity=None, out=None, count_visits=False, packet=None):
+    def overlap_self(self, capacity=None, out=None, count_visits=False, packet=None, ordered=True):
         """Tree against its own leaves, queries walked in Morton order."""
         return self.overlap(self.aabbs, capacity=capacity, order=self.leaf_order(), out=out,
-                            count_visits=count_visits, packet=packet)
+                            count_visits=count_visits, packet=packet, ordered=ordered)
 
     def visits(self):
         """Node records fetched by the last overlap(count_visits=True) call."""

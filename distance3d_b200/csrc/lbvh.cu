@@ -491,6 +491,98 @@ k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
     if (!FILL && visits && (threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)n_visited);
 }
 
+// Single-pass query: same traversals, hits are staged per warp in shared memory and flushed
+// with ONE atomic reservation per APPEND_STAGE pairs and coalesced 8-byte stores (the first
+// version of this file reserved per leaf hit and waited on that atomic 80 % of the time).
+// The pair order depends on the order of the reservations; callers that need a reproducible
+// order use the count / fill passes.  *cursor ends up as the exact number of pairs even when
+// `cap` is too small (the excess is dropped).
+#define APPEND_STAGE 512
+template <bool PACKET>
+__global__ void __launch_bounds__(128)
+k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
+                 const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
+                 unsigned long long *cursor, unsigned long long *visits) {
+    __shared__ int2 stage_all[4][APPEND_STAGE];
+    int2 *stage = stage_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool valid = t < n_query;
+    int qi = valid ? (order ? order[t] : (int)t) : 0;
+    double2 qx = make_double2(1e308, -1e308), qy = qx, qz = qx;  // empty box: never overlaps
+    if (valid) {
+        const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
+        qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
+    }
+    int node = (hdr->n > 0 && (PACKET || valid)) ? hdr->root : -1;
+    int staged = 0;  // warp-uniform
+    unsigned n_visited = 0;
+    for (;;) {
+        bool hit = false;
+        int leaf = 0;
+        if (PACKET) {
+            if (node < 0) break;  // uniform
+            const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
+            double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
+            bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
+            if (link.x < 0) {  // leaf (uniform branch)
+                hit = ov;
+                leaf = -link.x - 1;
+                node = link.z;
+            } else {
+                node = __any_sync(FULL, ov) ? link.x : link.z;
+            }
+            ++n_visited;
+        } else {
+            if (!__any_sync(FULL, node >= 0)) break;
+            if (node >= 0) {
+                const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
+                double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
+                bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
+                hit = ov && link.x < 0;
+                leaf = -link.x - 1;
+                node = (ov && link.x >= 0) ? link.x : link.z;
+                ++n_visited;
+            }
+        }
+        unsigned m = __ballot_sync(FULL, hit);
+        if (m) {
+            if (hit) stage[staged + __popc(m & lt)] = make_int2(leaf, qi);
+            staged += __popc(m);
+        }
+        if (staged > APPEND_STAGE - 32) {
+            __syncwarp();
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
+            base = __shfl_sync(FULL, base, 0);
+            for (int i = lane; i < staged; i += 32)
+                if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+            staged = 0;
+            __syncwarp();
+        }
+    }
+    if (staged) {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < staged; i += 32)
+            if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+    }
+    if (visits) {
+        if (PACKET) {
+            if (lane == 0) atomicAdd(visits, (unsigned long long)n_visited);
+        } else {
+            unsigned total = n_visited;
+            for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
+            if (lane == 0) atomicAdd(visits, (unsigned long long)total);
+        }
+    }
+}
+
 // ---- exclusive scan counts[u32] -> offsets[u64] (three small kernels) ----------
 #define SCAN_TILE 4096  // 1024 threads x 4 items
 __global__ void __launch_bounds__(1024)
@@ -719,10 +811,37 @@ int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, 
     return 0;
 }
 
+/* single pass: traverse and append (unordered output, exact *out_count); query_ws is unused and
+ * kept in the signature for the two-pass variant below */
 int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const int32_t *order,
                     int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
                     unsigned long long *out_count, unsigned long long *out_visits, void *query_ws,
                     size_t query_ws_size, void *stream_) {
+    (void)query_ws; (void)query_ws_size;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
+    if (n_query == 0 || n == 0) return 0;
+    if (!query || (cap > 0 && !out_pairs)) return d3d_set_error("d3d_bvh_overlap: null query / output");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    unsigned blocks = (unsigned)((n_query + 127) / 128);
+    if (packet)
+        k_overlap_append<true><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs,
+                                                           cap, out_count, out_visits);
+    else
+        k_overlap_append<false><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs,
+                                                            cap, out_count, out_visits);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+/* count + fill in one call: reproducible pair order (queries in the given order, leaves in
+ * depth-first order) at the price of a second traversal */
+int d3d_bvh_overlap_ordered(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                            int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                            unsigned long long *out_count, unsigned long long *out_visits,
+                            void *query_ws, size_t query_ws_size, void *stream_) {
     int rc = d3d_bvh_overlap_count(workspace, n, query, order, n_query, packet, out_count, out_visits,
                                    query_ws, query_ws_size, stream_);
     if (rc) return rc;

@@ -150,7 +150,11 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
  *                          *out_count (device, 64-bit) = exact number of pairs
  *   d3d_bvh_overlap_fill   pass 2: writes out_pairs[cap,2] (positions >= cap are dropped), pairs
  *                          grouped by query in processing order, leaves in depth-first order
- *   d3d_bvh_overlap        both passes
+ *   d3d_bvh_overlap_ordered  both passes in one call
+ *   d3d_bvh_overlap        ONE traversal: hits are staged per warp and appended to out_pairs with
+ *                          one reservation per 512 pairs; the same set of pairs in an order that
+ *                          depends on the scheduling; *out_count is exact even when cap is too
+ *                          small (the excess is dropped); query_ws may be NULL
  * `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted queries
  * traverse coherently).  packet = 1: the 32 queries of a warp traverse together (node fetched
  * once per warp; use with spatially sorted queries, best on dense scenes), packet = 0: one
@@ -168,6 +172,10 @@ int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const
                     int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
                     unsigned long long *out_count, unsigned long long *out_visits, void *query_ws,
                     size_t query_ws_size, void *stream);
+int d3d_bvh_overlap_ordered(const void *workspace, int64_t n, const double *query, const int32_t *order,
+                            int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                            unsigned long long *out_count, unsigned long long *out_visits,
+                            void *query_ws, size_t query_ws_size, void *stream);
 
 /* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
 int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);

@@ -55,6 +55,12 @@ def test_random_boxes_vs_oracle_tree(n, scale):
     # per-thread and warp-packet traversal produce the same list (same order, too)
     pairs_t, count_t = bvh.overlap_self(packet=False)
     assert count_t == count and np.array_equal(pairs_t.cpu().numpy(), pairs)
+    # single-pass append (unordered): the same set, no duplicates, in both traversal modes
+    for packet in (True, False):
+        pairs_u, count_u = bvh.overlap_self(packet=packet, ordered=False)
+        pu = pairs_u.cpu().numpy()
+        assert count_u == count and len(pu) == count
+        assert np.array_equal(pu[np.lexsort((pu[:, 1], pu[:, 0]))], pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))])
     ref_tree = O.Tree()
     ref_tree.insert_aabbs(A)
     ref = ref_tree.query(A)
@@ -95,6 +101,14 @@ def test_query_other_set_and_capacity_regrow():
     pairs, count = bvh.overlap(A2, capacity=16)           # forces the exact-size re-run
     ref = O.all_aabbs_overlap(A1, A2)
     assert count == len(ref) and as_set(pairs.cpu().numpy()) == as_set(ref)
+    # single pass: capacity too small -> exact count is still reported, second run fits
+    pairs_u, count_u = bvh.overlap(A2, capacity=16, ordered=False)
+    assert count_u == len(ref) and len(pairs_u) == count_u and as_set(pairs_u.cpu().numpy()) == as_set(ref)
+    import torch
+    small = torch.full((100, 2), -7, dtype=torch.int32, device="cuda")
+    _, cnt = bvh.overlap_async(torch.from_numpy(A2).cuda(), small)
+    assert int(cnt.item()) == len(ref)
+    assert as_set(small.cpu().numpy()) <= as_set(ref)      # the 100 written pairs are real pairs
 
 
 def test_aabbtree_api_matches_reference_semantics():
