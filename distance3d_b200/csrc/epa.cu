@@ -3,8 +3,8 @@
 // Replaces distance3d/epa.py:9-202 (epa, Polytope, LooseEdges), which is plain
 // interpreted Python in the reference.  The polytope (up to max_faces faces = 3
 // vertices + unit normal each) and the loose-edge list live in shared memory in
-// structure-of-arrays form ([12][max_faces], [6][max_loose_edges], conflict free
-// for lane-per-face access)
+// structure-of-arrays form ([12][max_faces], conflict free for lane-per-face access); the
+// loose-edge list is held in registers, entry e in lane e
 // (max_faces <= 64, max_loose_edges <= 32: one or two lanes-worth.)  Per iteration the warp
 //   A  finds the face closest to the origin (lane-strided scan + shuffle arg-min,
 //      lowest index wins ties like np.argmin),
@@ -13,7 +13,8 @@
 //   C  tests convergence,
 //   D  marks the faces that see the new point (lane per face), replays the
 //      reference's swap-with-last removal loop on a slot permutation, and maintains
-//      the loose-edge list with a lane-parallel search per edge (first match wins),
+//      the loose-edge list with a lane-parallel search per edge (first match wins; a matched
+//      entry is overwritten by the last one with six shuffles),
 //   E  builds the new faces lane-per-edge and compacts the valid ones in order.
 // The reference's quirks are reproduced on purpose: the
 // "swap" in fix_ccw_normal_direction only copies v1 over v0, degenerate new faces
@@ -48,20 +49,13 @@ struct EpaParams {
 
 struct WarpMem {
     double *faces;  // [12][max_faces]: v0 xyz, v1 xyz, v2 xyz, n xyz
-    double *loose;  // [6][max_loose]: a xyz, b xyz
     int *perm;      // [max_faces]
-    int mf, ml;
+    int mf;
     D3D_DEV v3 fget(int i, int which) const {
         return V3(faces[(3 * which) * mf + i], faces[(3 * which + 1) * mf + i], faces[(3 * which + 2) * mf + i]);
     }
     D3D_DEV void fset(int i, int which, v3 v) const {
         faces[(3 * which) * mf + i] = v.x; faces[(3 * which + 1) * mf + i] = v.y; faces[(3 * which + 2) * mf + i] = v.z;
-    }
-    D3D_DEV v3 lget(int k, int which) const {
-        return V3(loose[(3 * which) * ml + k], loose[(3 * which + 1) * ml + k], loose[(3 * which + 2) * ml + k]);
-    }
-    D3D_DEV void lset(int k, int which, v3 v) const {
-        loose[(3 * which) * ml + k] = v.x; loose[(3 * which + 1) * ml + k] = v.y; loose[(3 * which + 2) * ml + k] = v.z;
     }
 };
 
@@ -69,7 +63,7 @@ struct WarpMem {
 D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v2 - v0)); }
 
 #ifndef EPA_BLOCKS_PER_SM
-#define EPA_BLOCKS_PER_SM 7  // 72 registers, 28 warps per SM: measured 16.7 vs 12.1 Mpairs/s at 4
+#define EPA_BLOCKS_PER_SM 8  // 64 registers, 32 warps per SM; measured Mpairs/s at 5/6/7/8: 20.1/20.5/21.4/21.9
 #endif
 __global__ void __launch_bounds__(EPA_WARPS * 32, EPA_BLOCKS_PER_SM)
 k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm) {
@@ -77,12 +71,11 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
     const int mf = prm.max_faces, ml = prm.max_loose_edges;
-    size_t per_warp = (size_t)12 * mf + 6 * ml + (mf + 1) / 2 + 2;  // doubles
+    size_t per_warp = (size_t)12 * mf + (mf + 1) / 2 + 2;  // doubles
     WarpMem W;
     W.faces = smem + wid * per_warp;
-    W.loose = W.faces + 12 * mf;
-    W.perm = reinterpret_cast<int *>(W.loose + 6 * ml);
-    W.mf = mf; W.ml = ml;
+    W.perm = reinterpret_cast<int *>(W.faces + 12 * mf);
+    W.mf = mf;
     const double eps = prm.epsilon;
 
     for (;;) {
@@ -153,7 +146,10 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #pragma unroll 1
             for (int i = lane; i < n_faces; i += 32) W.perm[i] = i;
             __syncwarp();
+            // The loose-edge list lives in registers, entry e in lane e (max_loose_edges <= 32):
+            // no shared-memory traffic and no warp barriers inside the edge loop.
             int n_loose = 0;
+            v3 la = V3(0.0, 0.0, 0.0), lb = la;
             int nf = n_faces;
             {
                 int i = 0;
@@ -164,28 +160,25 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     // epa.py:167-187: edges of the removed face against the loose-edge list
 #pragma unroll 1
                     for (int j = 0; j < 3; ++j) {
-                        v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);
-                        bool match = false;
-                        if (lane < n_loose) {
-                            // np.linalg.norm(x) < eps without the square root (exactly equivalent)
-                            v3 d0 = W.lget(lane, 1) - e0, d1 = W.lget(lane, 0) - e1;
-                            match = dot_blas(d0, d0) < prm.eps_sq_thr && dot_blas(d1, d1) < prm.eps_sq_thr;
-                        }
+                        v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);  // broadcast reads
+                        // np.linalg.norm(x) < eps without the square root (exactly equivalent)
+                        v3 d0 = lb - e0, d1 = la - e1;
+                        bool match = lane < n_loose && dot_blas(d0, d0) < prm.eps_sq_thr &&
+                                     dot_blas(d1, d1) < prm.eps_sq_thr;
                         unsigned mm = __ballot_sync(FULL, match);
-                        int found = mm ? __ffs(mm) - 1 : -1;  // first matching edge wins
-                        __syncwarp();
-                        if (found >= 0) {  // overwrite_edge_with_last_edge (epa.py:200-202)
-                            if (lane == 0) {
-                                W.lset(found, 0, W.lget(n_loose - 1, 0));
-                                W.lset(found, 1, W.lget(n_loose - 1, 1));
-                            }
+                        if (mm) {  // first matching edge wins; overwrite_edge_with_last_edge (epa.py:200-202)
+                            int found = __ffs(mm) - 1, last = n_loose - 1;
+                            v3 ta = V3(__shfl_sync(FULL, la.x, last), __shfl_sync(FULL, la.y, last),
+                                       __shfl_sync(FULL, la.z, last));
+                            v3 tb = V3(__shfl_sync(FULL, lb.x, last), __shfl_sync(FULL, lb.y, last),
+                                       __shfl_sync(FULL, lb.z, last));
+                            if (lane == found) { la = ta; lb = tb; }
                             --n_loose;
                         } else {  // add_edge_to_list (epa.py:193-198)
-                            if (n_loose >= ml) { __syncwarp(); break; }
-                            if (lane == 0) { W.lset(n_loose, 0, e0); W.lset(n_loose, 1, e1); }
+                            if (n_loose >= ml) break;
+                            if (lane == n_loose) { la = e0; lb = e1; }
                             ++n_loose;
                         }
-                        __syncwarp();
                     }
                     // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i
                     if (lane == 0) W.perm[i] = W.perm[nf - 1];
@@ -214,7 +207,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 v3 v0 = V3(0, 0, 0), v1 = v0, nrm = v0;
                 bool valid = false;
                 if (have) {
-                    v0 = W.lget(e, 0); v1 = W.lget(e, 1);
+                    v0 = la; v1 = lb;
                     nrm = face_normal(v0, v1, new_point);
                     valid = !(dot_blas(nrm, nrm) < prm.half_sq_thr);
                 }
@@ -295,7 +288,7 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     prm.out_nfaces = out_nfaces; prm.out_iters = out_iters; prm.out_status = out_status;
     prm.out_faces = out_faces; prm.counter = reinterpret_cast<int *>(workspace);
     D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, stream));
-    size_t per_warp = (size_t)12 * max_faces + 6 * max_loose_edges + (max_faces + 1) / 2 + 2;
+    size_t per_warp = (size_t)12 * max_faces + (max_faces + 1) / 2 + 2;
     size_t smem = per_warp * EPA_WARPS * sizeof(double);
     D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)d3d_min64((n_pairs + EPA_WARPS - 1) / EPA_WARPS, (int64_t)d3d_sm_count() * (EPA_BLOCKS_PER_SM + 2));
