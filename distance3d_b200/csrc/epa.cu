@@ -152,11 +152,17 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             v3 la = V3(0.0, 0.0, 0.0), lb = la;
             int nf = n_faces;
             {
+                // visibility by SLOT: perm is the identity here, and removing slot i moves the
+                // face (and its bit) of slot nf-1 into slot i.  The scan jumps from one visible
+                // slot to the next instead of stepping over every face.
+                unsigned long long vis_slot = ((unsigned long long)vis_hi << 32) | vis_lo;
                 int i = 0;
-                while (i < nf) {  // uniform: every lane replays the same integer bookkeeping
+                for (;;) {  // uniform: every lane replays the same integer bookkeeping
+                    unsigned long long rest = (vis_slot >> i) << i;
+                    if (nf < 64) rest &= (1ull << nf) - 1ull;
+                    if (rest == 0ull) break;
+                    i = __ffsll((long long)rest) - 1;
                     int f = W.perm[i];
-                    bool vis = f < 32 ? ((vis_lo >> f) & 1u) : ((vis_hi >> (f - 32)) & 1u);
-                    if (!vis) { ++i; continue; }
                     // epa.py:167-187: edges of the removed face against the loose-edge list
 #pragma unroll 1
                     for (int j = 0; j < 3; ++j) {
@@ -180,10 +186,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                             ++n_loose;
                         }
                     }
-                    // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i
-                    if (lane == 0) W.perm[i] = W.perm[nf - 1];
+                    // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i.
+                    // Every lane stores the same value and later reads its own store: no barrier.
+                    W.perm[i] = W.perm[nf - 1];
+                    unsigned long long last_bit = (vis_slot >> (nf - 1)) & 1ull;
+                    vis_slot = (vis_slot & ~(1ull << i) & ~(1ull << (nf - 1))) | (i < nf - 1 ? (last_bit << i) : 0ull);
                     --nf;
-                    __syncwarp();
                 }
             }
             // apply the permutation: slot s <- original slot perm[s] (reads before writes)
