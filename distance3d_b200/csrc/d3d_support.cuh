@@ -129,6 +129,25 @@ D3D_DEV v3 box_vertex(const C &c, int i) {
               c.tz() + dot_blas(l, V3(c.r20(), c.r21(), c.r22())));
 }
 
+// Index of the first maximum (MAX) / minimum of one (value, index) candidate per lane over a
+// full warp, lowest index on ties - np.argmax / np.argmin semantics - with three integer warp
+// reductions (REDUX) on an order-preserving key instead of a five-step shuffle butterfly on
+// (double, int, flag).  +0.0 is added first so that -0.0 and +0.0 tie as they do for numpy;
+// finite values only.  Lanes with valid == false never win.
+template <bool MAX>
+D3D_DEV int warp_first_extreme(double val, int idx, bool valid) {
+    const unsigned FULL = 0xffffffffu;
+    long long b = __double_as_longlong(val + 0.0);
+    unsigned long long key = (unsigned long long)b ^ (b < 0 ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    if (!MAX) key = ~key;  // minimum of val = maximum of the complemented key
+    unsigned hi = valid ? (unsigned)(key >> 32) : 0u, lo = (unsigned)key;
+    unsigned mh = __reduce_max_sync(FULL, hi);
+    bool c = valid && hi == mh;
+    unsigned ml = __reduce_max_sync(FULL, c ? lo : 0u);
+    c = c && lo == ml;
+    return __reduce_min_sync(FULL, c ? idx : 0x7fffffff);
+}
+
 // First arg-max of V.dot(d) (colliders.py:132).  G lanes of a warp cooperate:
 // lane `lane` scans vertices lane, lane+G, ...; the reduction prefers the larger
 // value and, on ties, the lower index, so the result equals numpy's argmax.
@@ -151,6 +170,9 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
         real val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
         if (!have || val > best) { best = val; bi = i; have = true; }
     }
+#ifndef D3D_F32
+    if (G == 32) return warp_first_extreme<true>(best, bi, have);
+#endif
 #pragma unroll 1
     for (int off = G / 2; off > 0; off >>= 1) {
         real ov = __shfl_xor_sync(0xffffffffu, best, off, G);

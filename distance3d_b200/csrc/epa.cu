@@ -111,16 +111,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 double d = dot_plain(W.fget(i, 0), W.fget(i, 3));
                 if (bi == 0x7fffffff || d < best) { best = d; bi = i; }
             }
-#pragma unroll 1
-            for (int off = 16; off > 0; off >>= 1) {
-                double ob = __shfl_xor_sync(FULL, best, off);
-                int oi = __shfl_xor_sync(FULL, bi, off);
-                if (oi != 0x7fffffff && (bi == 0x7fffffff || ob < best || (ob == best && oi < bi))) {
-                    best = ob; bi = oi;
-                }
-            }
-            closest = bi;
-            double min_dist = best;
+            closest = warp_first_extreme<false>(best, bi, bi != 0x7fffffff);
+            double min_dist = __shfl_sync(FULL, best, closest & 31);  // the owner's local best IS slot `closest`
             // ---- B: support point of A - B in the face normal (epa.py:62-65)
             v3 sd = W.fget(closest, 3);
             v3 new_point = support_ni<32>(A, sd.x, sd.y, sd.z, lane) - support_ni<32>(B, -sd.x, -sd.y, -sd.z, lane);
