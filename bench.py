@@ -168,9 +168,21 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
                 tm.append(e0.elapsed_time(e1))
             modes[packet] = (min(tm), bvh.visits())
             del pairs
-        packet = modes[True][0] < modes[False][0]
-        visits = modes[packet][1]
         buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=aabb.device)
+        single = {}
+        for packet in (False, True):   # single pass: independent traversals vs 8-wide packets
+            tm = []
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=packet)
+                e1.record()
+                torch.cuda.synchronize()
+                tm.append(e0.elapsed_time(e1))
+            bvh.overlap_self(count_visits=True, packet=packet, ordered=False, out=buf)
+            single[packet] = (min(tm), bvh.visits())
+        packet = single[True][0] < single[False][0]
+        visits = single[packet][1]
         tb, tq = [], []
         for it in range(steps + 2):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -190,7 +202,8 @@ def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
         b_bytes = n * 176.0
         out[name] = {
             "center_scale": scale, "overlap_pairs": int(count), "node_visits": int(visits),
-            "traversal": "warp packet" if packet else "per thread",
+            "traversal": "8-wide packets" if packet else "per thread",
+            "single_pass_ms_per_thread_mode": single[False][0], "single_pass_ms_packet_mode": single[True][0],
             "query": "d3d_bvh_overlap: one traversal, warp-staged append (unordered pairs)",
             "ordered_two_pass_ms_per_thread_mode": modes[False][0],
             "ordered_two_pass_ms_packet_mode": modes[True][0],

@@ -80,13 +80,14 @@ class Lbvh:
         nq = int(order.shape[0]) if order is not None else int(query.shape[0])
         L = _lib.lib()
         if not ordered:
+            width = int(packet)  # True / False or an explicit packet width 2, 4, 8, 16, 32
             if out is None:
                 out = torch.empty((max(int(capacity or 16 * nq), 1), 2), dtype=torch.int32,
                                   device=self.device)
             for _ in range(2):
                 _lib._check(L.d3d_bvh_overlap(
                     ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
-                    ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._count),
+                    ctypes.c_int(width), ptr(out), c_i64(out.shape[0]), ptr(self._count),
                     ptr(self._visits) if count_visits else None, None, c_size(0), _lib.stream_ptr()))
                 count = int(self._count.item())
                 if count <= out.shape[0]:
@@ -124,7 +125,7 @@ class Lbvh:
         L = _lib.lib()
         _lib._check(L.d3d_bvh_overlap(
             ptr(self.workspace), c_i64(self.n), ptr(query), ptr(order), c_i64(nq),
-            ctypes.c_int(1 if packet else 0), ptr(out), c_i64(out.shape[0]), ptr(self._count), None,
+            ctypes.c_int(int(packet)), ptr(out), c_i64(out.shape[0]), ptr(self._count), None,
             None, c_size(0), _lib.stream_ptr()))
         return out, self._count
 

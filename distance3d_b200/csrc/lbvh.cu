@@ -491,14 +491,24 @@ k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
     if (!FILL && visits && (threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)n_visited);
 }
 
-// Single-pass query: same traversals, hits are staged per warp in shared memory and flushed
-// with ONE atomic reservation per APPEND_STAGE pairs and coalesced 8-byte stores (the first
-// version of this file reserved per leaf hit and waited on that atomic 80 % of the time).
-// The pair order depends on the order of the reservations; callers that need a reproducible
-// order use the count / fill passes.  *cursor ends up as the exact number of pairs even when
-// `cap` is too small (the excess is dropped).
+// Single-pass query: hits are staged per warp in shared memory and flushed with ONE atomic
+// reservation per APPEND_STAGE pairs and coalesced 8-byte stores (the first version of this
+// file reserved per leaf hit and waited on that atomic 80 % of the time).  The pair order
+// depends on the order of the reservations; callers that need a reproducible order use the
+// count / fill passes.  *cursor ends up as the exact number of pairs even when `cap` is too
+// small (the excess is dropped).
+//
+// PW = packet width: groups of PW neighbouring queries (Morton order) walk the tree together
+// and descend when ANY query of the group overlaps.  PW = 1 is the independent traversal,
+// PW = 32 the full-warp packet; in between, the union of the nodes a group must see shrinks
+// faster than the number of groups per warp grows (dense capsule set: 8-wide groups need
+// ~2x fewer warp steps than 32-wide ones), while the PW lanes of a group still fetch one node.
 #define APPEND_STAGE 512
-template <bool PACKET>
+#ifndef D3D_BVH_PACKET_WIDTH
+#define D3D_BVH_PACKET_WIDTH 8  // width used for packet = 1; 1 M capsules, ms dense / sparse at
+// widths 1, 2, 4, 8, 16, 32: 34.8 23.0 16.7 14.0 15.5 14.9 / 0.61 0.54 0.48 0.47 0.58 0.65
+#endif
+template <int PW>
 __global__ void __launch_bounds__(128)
 k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
                  const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
@@ -507,6 +517,7 @@ k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
     int2 *stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
+    const unsigned group_mask = (PW == 32) ? FULL : (((1u << PW) - 1u) << (lane & ~(PW - 1)));
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool valid = t < n_query;
     int qi = valid ? (order ? order[t] : (int)t) : 0;
@@ -515,38 +526,27 @@ k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
         const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
         qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
     }
-    int node = (hdr->n > 0 && (PACKET || valid)) ? hdr->root : -1;
+    // group-uniform; a group with no valid query at all never starts
+    bool group_valid = PW == 1 ? valid : (__ballot_sync(FULL, valid) & group_mask) != 0;
+    int node = (hdr->n > 0 && group_valid) ? hdr->root : -1;
     int staged = 0;  // warp-uniform
     unsigned n_visited = 0;
-    for (;;) {
-        bool hit = false;
-        int leaf = 0;
-        if (PACKET) {
-            if (node < 0) break;  // uniform
+    while (__any_sync(FULL, node >= 0)) {
+        bool ov = false, hit = false;
+        int4 link = make_int4(0, 0, -1, 0);
+        if (node >= 0) {
             const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
             double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-            int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
-            bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
-            if (link.x < 0) {  // leaf (uniform branch)
-                hit = ov;
-                leaf = -link.x - 1;
-                node = link.z;
-            } else {
-                node = __any_sync(FULL, ov) ? link.x : link.z;
-            }
+            link = __ldg(reinterpret_cast<const int4 *>(p + 3));  // left right rope parent
+            // aabb_tree.py:520-527 (closed intervals)
+            ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
             ++n_visited;
-        } else {
-            if (!__any_sync(FULL, node >= 0)) break;
-            if (node >= 0) {
-                const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
-                double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
-                bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
-                hit = ov && link.x < 0;
-                leaf = -link.x - 1;
-                node = (ov && link.x >= 0) ? link.x : link.z;
-                ++n_visited;
-            }
+        }
+        bool any = PW == 1 ? ov : (__ballot_sync(FULL, ov) & group_mask) != 0;
+        int leaf = -link.x - 1;
+        if (node >= 0) {
+            hit = ov && link.x < 0;
+            node = (any && link.x >= 0) ? link.x : link.z;
         }
         unsigned m = __ballot_sync(FULL, hit);
         if (m) {
@@ -572,14 +572,10 @@ k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
         for (int i = lane; i < staged; i += 32)
             if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
     }
-    if (visits) {
-        if (PACKET) {
-            if (lane == 0) atomicAdd(visits, (unsigned long long)n_visited);
-        } else {
-            unsigned total = n_visited;
-            for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
-            if (lane == 0) atomicAdd(visits, (unsigned long long)total);
-        }
+    if (visits) {  // node records fetched: one per group and step
+        unsigned total = (lane & (PW - 1)) == 0 ? n_visited : 0u;
+        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
+        if (lane == 0) atomicAdd(visits, (unsigned long long)total);
     }
 }
 
@@ -826,12 +822,20 @@ int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const
     if (!query || (cap > 0 && !out_pairs)) return d3d_set_error("d3d_bvh_overlap: null query / output");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
     unsigned blocks = (unsigned)((n_query + 127) / 128);
-    if (packet)
-        k_overlap_append<true><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs,
-                                                           cap, out_count, out_visits);
-    else
-        k_overlap_append<false><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs,
-                                                            cap, out_count, out_visits);
+#define D3D_APPEND(PW)                                                                              \
+    k_overlap_append<PW><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs, \
+                                                     cap, out_count, out_visits)
+    switch (packet) {  // 0 / 1 = per thread / default packet; 2, 4, 8, 16, 32 = explicit width
+    case 0: D3D_APPEND(1); break;
+    case 1: D3D_APPEND(D3D_BVH_PACKET_WIDTH); break;
+    case 2: D3D_APPEND(2); break;
+    case 4: D3D_APPEND(4); break;
+    case 8: D3D_APPEND(8); break;
+    case 16: D3D_APPEND(16); break;
+    case 32: D3D_APPEND(32); break;
+    default: return d3d_set_error("d3d_bvh_overlap: packet must be 0, 1, 2, 4, 8, 16 or 32");
+    }
+#undef D3D_APPEND
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -154,7 +154,8 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
  *   d3d_bvh_overlap        ONE traversal: hits are staged per warp and appended to out_pairs with
  *                          one reservation per 512 pairs; the same set of pairs in an order that
  *                          depends on the scheduling; *out_count is exact even when cap is too
- *                          small (the excess is dropped); query_ws may be NULL
+ *                          small (the excess is dropped); query_ws may be NULL; here packet may
+ *                          also be an explicit group width 2, 4, 8, 16, 32 (1 = the default, 8)
  * `order` (optional, int32[n_query]) = processing order of the queries (spatially sorted queries
  * traverse coherently).  packet = 1: the 32 queries of a warp traverse together (node fetched
  * once per warp; use with spatially sorted queries, best on dense scenes), packet = 0: one
