@@ -179,8 +179,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                         }
                     }
                     // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i.
-                    // Every lane stores the same value and later reads its own store: no barrier.
-                    W.perm[i] = W.perm[nf - 1];
+                    // Every lane stores the same value; the barriers only order the uniform
+                    // reads and writes of the other lanes (racecheck-clean).
+                    int moved = W.perm[nf - 1];
+                    __syncwarp();
+                    W.perm[i] = moved;
+                    __syncwarp();
                     unsigned long long last_bit = (vis_slot >> (nf - 1)) & 1ull;
                     vis_slot = (vis_slot & ~(1ull << i) & ~(1ull << (nf - 1))) | (i < nf - 1 ? (last_bit << i) : 0ull);
                     --nf;

@@ -17,6 +17,9 @@ mpr.mpr_batch(cs, pairs)
 A = _lib.aabb_device(cs.device())
 bvh = aabb_tree.Lbvh(A)
 bvh.overlap_self(packet=True); bvh.overlap_self(packet=False)
+for w in (0, 1, 2, 4, 16, 32):
+    bvh.overlap_self(packet=w, ordered=False)
+bvh.overlap(A[:100], capacity=8, ordered=False)
 aabb_tree.brute_force_pairs(A[:200], A[200:500])
 pipeline.collide(cs, shard=False)
 data = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "data")
@@ -26,5 +29,6 @@ b = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
 b.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
 self_collision.RobotModel(tm, b).detect_batch(rs.uniform(-3, 3, size=(500, 6)))
 _lib.debug_norm(rs.randn(5000, 3))
+_lib.debug_vdiv(rs.randn(5000, 3), rs.randn(5000))
 torch.cuda.synchronize()
 print("sanitize run complete")
