@@ -548,6 +548,12 @@ D3D_DEV void gjk_finish(const PS &s, const SX &S, const GjkParams &prm, bool wri
 #ifndef GJK_REFILL_MIN
 #define GJK_REFILL_MIN 8
 #endif
+#ifndef GJK_CHUNK
+#define GJK_CHUNK 0  // pairs per warp-private chunk of the sorted order; 0 = one global cursor.
+// Measured (C1 mix, Mpairs/s at 1 Mi / 4 Mi pairs): cursor 277 / 335, chunks of 128: 284 / 332,
+// 256: 269 / 334, 512: 209 / 312 - chunks keep a warp inside one type bin but unbalance small
+// batches; the global cursor is the default.
+#endif
 // refill when at least this many lanes of the warp are idle
 
 // ---------------------------------------------------------------------------
@@ -653,6 +659,9 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
     const int total = prim ? w.counters[4] : w.counters[2];
     int *next = &w.counters[prim ? 0 : 5];
     bool exhausted = false;
+#if GJK_CHUNK > 0
+    int chunk_pos = 0, chunk_end = 0;
+#endif
     PairState<GJK_THREADS> s;
     s.state = D3D_UNKNOWN;
     bool running = false;   // lane owns a pair that still iterates
@@ -664,16 +673,40 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
         if (idle >= GJK_REFILL_MIN || run_mask == 0) {
             if (finished) { gjk_finish_or_park<MODE>(s, S, prm, w); finished = false; }
             if (!exhausted) {
-                // the idle lanes take the next `want` pairs of the sorted order (one atomic per
-                // refill; consecutive positions share a type bin, so the warp stays uniform)
                 unsigned need = ~run_mask;
-                int want = __popc(need);
+                int want = __popc(need), rank = __popc(need & lt_mask);
+                int mine = -1;
+#if GJK_CHUNK > 0
+                // warp-private chunk of the sorted order: the lanes of a warp hold neighbouring
+                // pairs (one type bin) even when the bins are small next to the number of
+                // pairs in flight on the whole device
+                int avail = chunk_end - chunk_pos;
+                if (rank < avail) mine = chunk_pos + rank;
+                if (want > avail) {
+                    int start = 0;
+                    if (lane == 0) start = atomicAdd(next, GJK_CHUNK);
+                    start = __shfl_sync(0xffffffffu, start, 0) + first;
+                    if (start >= total) {
+                        exhausted = true;
+                        chunk_pos = chunk_end = 0;
+                    } else {
+                        int end = min(start + GJK_CHUNK, total);
+                        if (rank >= avail && start + (rank - avail) < end) mine = start + (rank - avail);
+                        chunk_pos = min(start + (want - avail), end);
+                        chunk_end = end;
+                    }
+                } else {
+                    chunk_pos += want;
+                }
+#else
+                // the idle lanes take the next `want` pairs of the sorted order (one atomic per refill)
                 int start = 0;
                 if (lane == 0) start = atomicAdd(next, want);
                 start = __shfl_sync(0xffffffffu, start, 0) + first;
                 exhausted = start + want >= total;
-                int mine = start + __popc(need & lt_mask);
-                if (!running && mine < total) {
+                if (start + rank < total) mine = start + rank;
+#endif
+                if (!running && mine >= 0) {
                     init_pair<GJK_THREADS>(s, c, pairs, __ldg(w.perm + mine), base);
                     running = true;
                 }

@@ -2,7 +2,7 @@ import sys, time, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path
 import numpy as np, torch
 from distance3d_b200 import gjk, random as R
 names=sys.argv[1].split(",") if len(sys.argv)>1 else ["sphere","ellipsoid","capsule","cylinder","box"]
-n=1<<20
+n=int(os.environ.get("D3D_N", 1<<20))
 DTYPE=os.environ.get("D3D_DTYPE","f64")
 def run(cs,pairs,label):
     dc=cs.device(); pd=torch.from_numpy(pairs).cuda()
