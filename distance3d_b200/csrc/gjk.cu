@@ -773,11 +773,14 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs, sms * GJK_BLOCKS_PER_SM * GJK_THREADS * 8);
     k_bin_scatter<<<(int)d3d_min64((n_pairs + 256 * BIN_TILE_ITEMS - 1) / (256 * BIN_TILE_ITEMS), (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, w);
     size_t smem = sizeof(real) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
-    static bool attr_set = false;  // per MODE instance of this function
-    if (!attr_set) {
+    // function attributes are per device: remember which devices have been set up
+    static bool attr_set[64] = {false};  // per MODE instance of this function
+    int dev = 0;
+    D3D_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_PRIMITIVE_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_ALL_TYPES_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
     // ranges are read on the device; an instance whose range is empty exits at once
