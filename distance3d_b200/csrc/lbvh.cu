@@ -520,7 +520,9 @@ k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
 // PW = 32 the full-warp packet; in between, the union of the nodes a group must see shrinks
 // faster than the number of groups per warp grows (dense capsule set: 8-wide groups need
 // ~2x fewer warp steps than 32-wide ones), while the PW lanes of a group still fetch one node.
-#define APPEND_STAGE 512
+#ifndef APPEND_STAGE
+#define APPEND_STAGE 512  // pairs per warp; dense / sparse ms at 128, 256, 512, 1024: 14.6 14.3 14.2 20.2 / 0.50 0.50 0.47 0.66
+#endif
 #ifndef D3D_BVH_PACKET_WIDTH
 #define D3D_BVH_PACKET_WIDTH 8  // width used for packet = 1; 1 M capsules, ms dense / sparse at
 // widths 1, 2, 4, 8, 16, 32: 34.8 23.0 16.7 14.0 15.5 14.9 / 0.61 0.54 0.48 0.47 0.58 0.65
