@@ -173,3 +173,20 @@ def test_c_abi_argument_checks_without_a_gpu():
     assert b"out of range" in lib.d3d_last_error_string()
     assert lib.d3d_bvh_build(dummy, i64(1000), ctypes.cast(dummy, vp), ctypes.c_size_t(512), None) == -1
     assert b"workspace too small" in lib.d3d_last_error_string()
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` times the CPU oracle only and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--pairs", "20000", "--cpu-sample", "20000"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "gjk_distance_pairs_per_s"
+    assert line["value"] > 0 and line["unit"] == "pairs/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
