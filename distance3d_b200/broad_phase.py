@@ -12,6 +12,7 @@ import numpy as np
 from . import _lib
 from .aabb_tree import AabbTree
 from .colliders import Sphere, Box, Cylinder, MeshGraph
+from .io import load_mesh
 from .pack import pack_colliders
 from . import urdf
 from .urdf_utils import self_collision_whitelists
@@ -73,9 +74,14 @@ class BoundingVolumeHierarchy:
         if isinstance(obj, urdf.Cylinder):
             return Cylinder(cylinder2origin=A2B, radius=obj.radius, length=obj.length)
         assert isinstance(obj, urdf.Mesh)
-        # mesh file I/O (reference io.py:5-46, Open3D / trimesh) is out of scope;
-        # like the reference's loader failures this surfaces as a warning, not an error
-        raise RuntimeError("mesh colliders from URDF files are not supported (%s)" % obj.filename)
+        if obj.filename is None:
+            raise RuntimeError("mesh collider in frame '%s' has no file (no mesh_path / package_dir "
+                               "was given to load_urdf)" % obj.frame)
+        try:
+            vertices, triangles = load_mesh(obj.filename, obj.scale)
+        except OSError as e:  # like the reference's loader failures: a warning, not an error
+            raise RuntimeError("mesh collider '%s' could not be loaded: %s" % (obj.filename, e))
+        return MeshGraph(A2B, vertices, triangles)
 
     def add_collider(self, frame, collider):
         """Add a collider located in `frame` (broad_phase.py:129-142)."""

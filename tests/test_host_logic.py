@@ -190,3 +190,64 @@ def test_bench_reference_arm_runs_without_a_gpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+MESH_URDF = """<?xml version="1.0"?>
+<robot name="mesh_bot">
+  <link name="base"><collision><origin xyz="0 0 0.1" rpy="0 0 0"/>
+    <geometry><mesh filename="part.stl" scale="1 2 0.5"/></geometry></collision></link>
+  <link name="arm"><collision><origin xyz="0 0 0" rpy="0 0 0"/>
+    <geometry><mesh filename="part.stl"/></geometry></collision></link>
+  <link name="tip"><collision><geometry><mesh filename="missing.stl"/></geometry></collision></link>
+  <joint name="j1" type="revolute"><parent link="base"/><child link="arm"/>
+    <origin xyz="0 0 1" rpy="0 0 0"/><axis xyz="0 1 0"/></joint>
+  <joint name="j2" type="revolute"><parent link="arm"/><child link="tip"/>
+    <origin xyz="0 0 1" rpy="0 0 0"/><axis xyz="0 1 0"/></joint>
+</robot>"""
+
+
+def test_mesh_io_round_trips_and_urdf_mesh_colliders(tmp_path):
+    """distance3d/io.py:5-46 load_mesh + broad_phase.py:93-127 _make_collider for <mesh>."""
+    import warnings
+    from distance3d_b200 import io, mesh, broad_phase
+    from distance3d_b200.urdf import UrdfTransformManager
+    rs = np.random.RandomState(5)
+    V = rs.randn(30, 3)
+    V -= V.mean(axis=0)
+    T = mesh.make_convex_mesh(V)
+    used = np.unique(T)
+    for binary, expect in ((True, V.astype(np.float32).astype(np.float64)), (False, V)):
+        f = str(tmp_path / ("b.stl" if binary else "a.stl"))
+        io.save_stl(f, V, T, binary=binary)
+        V2, T2 = io.load_mesh(f, scale=2.0)
+        assert len(V2) == len(used) and T2.shape == T.shape          # duplicated corners are merged
+        np.testing.assert_array_equal(V2[T2], 2.0 * expect[T])         # same triangles, same order
+    obj = tmp_path / "m.obj"
+    obj.write_text("# quad\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1/1 2/2 3/3 4/4\nf -4 -3 -2\n")
+    Vo, To = io.load_mesh(str(obj))
+    assert Vo.shape == (4, 3) and To.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+    with pytest.raises(OSError):
+        io.load_mesh(str(tmp_path / "x.ply"))
+    # URDF <mesh> -> MeshGraph in the collision frame, scaled per axis
+    io.save_stl(str(tmp_path / "part.stl"), V, T, binary=False)
+    tm = UrdfTransformManager()
+    tm.load_urdf(MESH_URDF, mesh_path=str(tmp_path))
+    bvh = broad_phase.BoundingVolumeHierarchy.__new__(broad_phase.BoundingVolumeHierarchy)
+    tm.add_transform("mesh_bot", "origin", np.eye(4))
+    made = {}
+    for o in tm.collision_objects:
+        try:
+            made[o.frame] = bvh._make_collider(tm, o, False)
+        except RuntimeError as e:                     # the missing file surfaces like in the reference
+            assert "missing.stl" in str(e)
+            made[o.frame] = None
+    frames = sorted(made)
+    assert len(frames) == 3 and sum(v is None for v in made.values()) == 1
+    base = made["collision:base/0"]
+    assert isinstance(base, C.MeshGraph)
+    np.testing.assert_array_equal(base.vertices[base.triangles], (V * [1.0, 2.0, 0.5])[T])
+    np.testing.assert_allclose(base.mesh2origin[:3, 3], [0.0, 0.0, 0.1])
+    arm = made["collision:arm/0"]
+    np.testing.assert_allclose(arm.mesh2origin[:3, 3], [0.0, 0.0, 1.0])
+    packed = pack.pack_colliders([base, arm])
+    assert packed.type.tolist() == [pack.MESH, pack.MESH] and packed.vert_len.tolist() == [len(used)] * 2

@@ -102,3 +102,51 @@ def test_bvh_from_colliders_translation_invariance():
     pairs1 = [((f, c), (f2, c2)) for (f, c), (f2, c2) in pairs if f != f2]
     pairs2 = bvh.aabb_overlapping_with_self()
     assert sorted((a[0], b[0]) for a, b in pairs1) == sorted((a[0], b[0]) for a, b in pairs2)
+
+
+MESH_URDF = """<?xml version="1.0"?>
+<robot name="mesh_bot">
+  <link name="base"><collision><geometry><mesh filename="part.stl" scale="1 2 0.5"/></geometry></collision></link>
+  <link name="arm"><collision><geometry><mesh filename="part.stl"/></geometry></collision></link>
+  <link name="tip"><collision><origin xyz="0.2 0 0" rpy="0 0.3 0"/>
+    <geometry><mesh filename="part.stl" scale="0.5 0.5 0.5"/></geometry></collision></link>
+  <link name="ghost"><collision><geometry><mesh filename="missing.stl"/></geometry></collision></link>
+  <joint name="j1" type="revolute"><parent link="base"/><child link="arm"/>
+    <origin xyz="0 0 2.5" rpy="0 0 0"/><axis xyz="0 1 0"/></joint>
+  <joint name="j2" type="revolute"><parent link="arm"/><child link="tip"/>
+    <origin xyz="0 0 2.5" rpy="0 0 0"/><axis xyz="0 1 0"/></joint>
+  <joint name="j3" type="fixed"><parent link="tip"/><child link="ghost"/></joint>
+</robot>"""
+
+
+def test_urdf_mesh_colliders_through_the_bvh(tmp_path):
+    """<mesh> geometry -> io.load_mesh -> MeshGraph -> BVH / self-collision; the
+    missing file is a warning (broad_phase.py:76-81), results agree with the CPU oracle."""
+    from distance3d_b200 import io, mesh, pack
+    from oracle import cpu_oracle as O
+    rs = np.random.RandomState(9)
+    V = rs.randn(40, 3)
+    V -= V.mean(axis=0)
+    io.save_stl(str(tmp_path / "part.stl"), V, mesh.make_convex_mesh(V), binary=True)
+    tm = UrdfTransformManager()
+    tm.load_urdf(MESH_URDF, mesh_path=str(tmp_path))
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "mesh_bot")
+    with pytest.warns(UserWarning, match="missing.stl"):
+        bvh.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
+    frames = ["collision:base/0", "collision:arm/0", "collision:tip/0"]
+    assert sorted(bvh.get_collider_frames()) == sorted(frames)
+    assert all(isinstance(c, colliders.MeshGraph) for c in bvh.get_colliders())
+    seen = set()
+    for q1, q2 in ((0.0, 0.0), (2.6, 2.9), (1.2, -2.0), (3.0, 3.0), (-2.7, -2.8)):
+        tm.set_joint("j1", q1)
+        tm.set_joint("j2", q2)
+        bvh.update_collider_poses()
+        got = self_collision.detect(bvh)
+        # only base <-> tip is not white-listed (parent / child links are skipped)
+        cs = pack.pack_colliders([bvh.colliders_["collision:base/0"], bvh.colliders_["collision:tip/0"]])
+        hit = bool(O.gjk_intersection(cs, np.array([[0, 1]], dtype=np.int32))["hit"][0])
+        assert got["collision:base/0"] == hit and got["collision:tip/0"] == hit
+        assert got["collision:arm/0"] is False or got["collision:arm/0"] == False  # noqa: E712
+        assert self_collision.detect_any(bvh) == hit
+        seen.add(hit)
+    assert seen == {True, False}
