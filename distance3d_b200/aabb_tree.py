@@ -180,18 +180,21 @@ def brute_force_pairs(aabbs1, aabbs2, capacity=None):
 def all_aabbs_overlap(aabbs1, aabbs2):
     """Brute-force overlap of two box lists (reference: aabb_tree.py:465-500).
 
-    Returns ``(unique indices 1, unique indices 2, pairs)``; pairs are in the
-    reference's row-major order, as an int array of shape (k, 2).
+    Returns ``(unique indices 1, unique indices 2, pairs)``; pairs is the reference's list
+    of ``(i, j)`` tuples in row-major order (`brute_force_pairs` keeps them on the device).
     """
     pairs, _ = brute_force_pairs(aabbs1, aabbs2)
     pairs = pairs.cpu().numpy().astype(np.int64)
-    return np.unique(pairs[:, 0]), np.unique(pairs[:, 1]), pairs
+    return np.unique(pairs[:, 0]), np.unique(pairs[:, 1]), list(map(tuple, pairs.tolist()))
 
 
 def aabb_overlap(aabb1, aabb2):
-    """Closed-interval overlap of two boxes (reference: aabb_tree.py:503-527)."""
-    _, _, pairs = all_aabbs_overlap(np.asarray(aabb1)[np.newaxis], np.asarray(aabb2)[np.newaxis])
-    return len(pairs) > 0
+    """Closed-interval overlap of two boxes (reference: aabb_tree.py:503-527): six
+    comparisons of host scalars, evaluated where the two boxes are (the batched forms are
+    `brute_force_pairs` and `Lbvh.overlap`)."""
+    a = np.asarray(aabb1, dtype=np.float64)
+    b = np.asarray(aabb2, dtype=np.float64)
+    return bool(np.all(a[:, 0] <= b[:, 1]) and np.all(a[:, 1] >= b[:, 0]))
 
 
 class AabbTree:
@@ -242,12 +245,12 @@ class AabbTree:
         """Overlaps with another tree (reference: aabb_tree.py:121-159).
 
         Returns ``(is_overlapping, unique indices of self, unique indices of other,
-        pairs)`` with pairs as an int array (k, 2) of (index in self, index in other),
-        sorted by (other, self).
+        pairs)``; pairs is the reference's list of ``(index in self, index in other)``
+        tuples, here sorted by (other, self) - the reference's order is that of its tree
+        traversal and not part of the contract.  `Lbvh.overlap` keeps the pairs on the device.
         """
         if len(self) == 0 or len(other) == 0:
-            empty = np.empty((0, 2), dtype=np.int64)
-            return False, np.array([]), np.array([]), empty
+            return False, np.array([]), np.array([]), []
         bvh = self._tree()
         if other is self:
             pairs, _ = bvh.overlap_self()
@@ -255,7 +258,8 @@ class AabbTree:
             pairs, _ = bvh.overlap(other.aabbs)
         pairs = pairs.cpu().numpy().astype(np.int64)
         pairs = pairs[np.lexsort((pairs[:, 0], pairs[:, 1]))]
-        return len(pairs) > 0, np.unique(pairs[:, 0]), np.unique(pairs[:, 1]), pairs
+        return (len(pairs) > 0, np.unique(pairs[:, 0]), np.unique(pairs[:, 1]),
+                list(map(tuple, pairs.tolist())))
 
     def overlaps_aabb(self, aabb):
         """Leaves overlapping one box (reference: aabb_tree.py:161-181)."""

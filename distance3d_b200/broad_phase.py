@@ -79,7 +79,8 @@ class BoundingVolumeHierarchy:
                                "was given to load_urdf)" % obj.frame)
         try:
             vertices, triangles = load_mesh(obj.filename, obj.scale)
-        except OSError as e:  # like the reference's loader failures: a warning, not an error
+        except (OSError, ValueError, IndexError) as e:  # unreadable or malformed file: a warning
+            # (fill_tree_with_colliders), the other colliders of the robot are still loaded
             raise RuntimeError("mesh collider '%s' could not be loaded: %s" % (obj.filename, e))
         return MeshGraph(A2B, vertices, triangles)
 

@@ -44,7 +44,9 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        if force or _stale(obj, [src] + headers):
+        # *_f32.cu only #include their fp64 twin: every .cu is a dependency of theirs
+        deps = [src] + headers + (sources if src.endswith("_f32.cu") else [])
+        if force or _stale(obj, deps):
             flags = list(NVCC_FLAGS)
             if src.endswith("_f32.cu"):
                 flags.remove("-fmad=false")  # the fp32 mode has no bit-level contract

@@ -21,7 +21,7 @@ class ConvexCollider:
     def _set(self):
         # attributes may be mutated freely (as in the reference), so the
         # one-collider record is re-packed on every scalar query
-        return _pack.pack_colliders([self])
+        return _pack.pack_colliders([self], track_mesh_state=True)
 
     def _dirty(self):
         pass
@@ -34,7 +34,10 @@ class ConvexCollider:
         """Extreme point along `search_direction` (computed on the GPU)."""
         from . import _lib
         d = np.ascontiguousarray(search_direction, dtype=np.float64).reshape(1, 3)
-        return _lib.support(self._set(), np.zeros(1, dtype=np.int32), d)[0]
+        cs = self._set()
+        out = _lib.support(cs, np.zeros(1, dtype=np.int32), d)[0]
+        cs.commit_mesh_state()  # MeshGraph (also inside a Margin) caches its last vertex
+        return out
 
     def aabb(self):
         """Axis-aligned bounding box, shape (3, 2) (computed on the GPU)."""
@@ -113,9 +116,12 @@ class Box(ConvexHullVertices):
 class MeshGraph(ConvexCollider):
     """Convex mesh in its own frame (reference: colliders.py:187-240).
 
-    The reference climbs the triangle graph from a cached start vertex
-    (mesh.py:12-139); the GPU takes the arg-max over all vertices, which is the
-    same point except on plateaus of width 10*EPSILON (mesh.py:9).
+    The support map climbs the triangle graph (mesh.py:12-139): six axis-extreme shortcut
+    vertices, then neighbour rounds with the 10*EPSILON plateau rule, starting from the
+    vertex the previous support call ended on.  The adjacency record is built once here
+    (mesh.build_mesh_graph) and uploaded with the collider; like the reference object,
+    this one remembers its last vertex across scalar calls (`_first_idx`, mesh.py:85).
+    In batched calls every pair starts from the packed start vertex.
     """
 
     def __init__(self, mesh2origin, vertices, triangles, artist=None):
@@ -123,6 +129,14 @@ class MeshGraph(ConvexCollider):
         self.mesh2origin = mesh2origin
         self.vertices = vertices
         self.triangles = triangles
+        self._graph = None
+        self._first_idx = None  # None = min(triangles), the fresh object's start
+
+    def graph_record(self):
+        if self._graph is None:
+            from .mesh import build_mesh_graph
+            self._graph = build_mesh_graph(self.vertices, self.triangles)
+        return self._graph
 
     def first_vertex(self):
         return self.mesh2origin[:3, 3] + np.dot(self.mesh2origin[:3, :3], self.vertices[0])

@@ -47,6 +47,7 @@ __global__ void k_support(d3d_colliders c, const int32_t *idx, const double *dir
     if (t >= n) return;
     Collider col = load_collider(c, idx[t]);
     st3(out + 3 * t, support<1>(col, ld3(dirs + 3 * t), 0));
+    if (c.mesh_last && col.type == D3D_MESH) c.mesh_last[idx[t]] = col.cur;  // mesh.py:85
 }
 
 __global__ void k_center(d3d_colliders c, double *out) {

@@ -18,6 +18,11 @@ struct Collider {
     const double *V;  // vertex range in the pool (box / hull: world frame, mesh: local)
     real m_margin;
     real m[15];     // r00 r01 r02 tx  r10 r11 r12 ty  r20 r21 r22 tz  p0 p1 p2
+    const int32_t *g;  // MeshGraph adjacency record (d3d_types.h) or nullptr
+    mutable int cur;   // MeshGraph: vertex the last support call ended on (mesh.py:85)
+    D3D_DEV const int32_t *graph() const { return g; }
+    D3D_DEV int mesh_cur() const { return cur; }
+    D3D_DEV void set_mesh_cur(int v, int) const { cur = v; }
     D3D_DEV real r00() const { return m[0]; }
     D3D_DEV real r01() const { return m[1]; }
     D3D_DEV real r02() const { return m[2]; }
@@ -46,7 +51,18 @@ struct ColliderSmem {
     int nv;
     const double *V;
     const real *base;
+    const int32_t *gpool;  // d3d_colliders::graph
     D3D_DEV real f(int i) const { return base[i * STRIDE]; }
+    // MeshGraph keeps its hill-climbing state in the parameter fields it does not use:
+    // field 12 = current vertex, field 13 = offset of the adjacency record (-1: none)
+    D3D_DEV const int32_t *graph() const {
+        int off = (int)f(13);
+        return off < 0 ? nullptr : gpool + off;
+    }
+    D3D_DEV int mesh_cur() const { return (int)f(12); }
+    D3D_DEV void set_mesh_cur(int v, int lane) const {
+        if (STRIDE != 1 || lane == 0) const_cast<real *>(base)[12 * STRIDE] = (real)v;
+    }
     D3D_DEV real r00() const { return f(0); }
     D3D_DEV real r01() const { return f(1); }
     D3D_DEV real r02() const { return f(2); }
@@ -65,10 +81,24 @@ struct ColliderSmem {
     D3D_DEV real margin() const { return f(15); }
 };
 
+// MeshGraph: offset of the adjacency record and the vertex a pair starts from.
+D3D_DEV void mesh_graph_of(const d3d_colliders &c, int64_t i, int &off, int &start) {
+    off = c.graph_off ? __ldg(c.graph_off + i) : -1;
+    start = c.mesh_start ? __ldg(c.mesh_start + i) : -1;
+    if (start < 0) start = off >= 0 ? __ldg(c.graph + off) : 0;
+}
+
 // 128-bit vectorised loads of the 4x4 pose (rows 0..2) and the parameters.
 D3D_DEV Collider load_collider(const d3d_colliders &c, int64_t i) {
     Collider o;
     o.type = __ldg(c.type + i);
+    o.g = nullptr;
+    o.cur = 0;
+    if (o.type == D3D_MESH) {
+        int off;
+        mesh_graph_of(c, i, off, o.cur);
+        if (off >= 0) o.g = c.graph + off;
+    }
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
     o.m_margin = c.margin ? __ldg(c.margin + i) : R(0.0);
@@ -92,6 +122,7 @@ D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, r
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
     o.base = base;
+    o.gpool = c.graph;
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -104,6 +135,12 @@ D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, r
     base[13 * STRIDE] = __ldg(p + 1);
     base[14 * STRIDE] = __ldg(p + 2);
     base[15 * STRIDE] = c.margin ? __ldg(c.margin + i) : R(0.0);
+    if (o.type == D3D_MESH) {
+        int off, start;
+        mesh_graph_of(c, i, off, start);
+        base[12 * STRIDE] = (real)start;
+        base[13 * STRIDE] = (real)off;
+    }
     return o;
 }
 
@@ -183,6 +220,39 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
         }
     }
     return bi;
+}
+
+// mesh.py:90-139 hill_climb_mesh_extreme: from `start`, first the six axis-extreme shortcut
+// vertices, then rounds over the neighbour list of the vertex the round started on; a
+// candidate replaces the current best when ddot(d, v_c - v_best) > 10 EPS (mesh.py:9), the
+// comparison base moving with every acceptance.  Strictly sequential - in the warp-per-pair
+// kernels every lane runs it redundantly (broadcast loads).  The reference has no bound on
+// the number of rounds; exact arithmetic needs at most nv, the cap only guards a GPU hang.
+static __device__ __noinline__ int hill_climb(const double *V, int nv, const int32_t *g, real lx,
+                                              real ly, real lz, int start) {
+    const real eps = R(10.0) * D3D_EPS;
+    const v3 l = V3(lx, ly, lz);
+    int best = start;
+    v3 vb = ld3(V + 3 * best);
+#pragma unroll 1
+    for (int k = 1; k <= 6; ++k) {
+        int cidx = __ldg(g + k);
+        v3 vc = ld3(V + 3 * cidx);
+        if (dot_blas(l, vc - vb) > eps) { best = cidx; vb = vc; }
+    }
+    bool converged = false;
+#pragma unroll 1
+    for (int round = 0; !converged && round < 2 * nv + 16; ++round) {
+        converged = true;
+        const int lo = __ldg(g + 7 + best), hi = __ldg(g + 8 + best);
+#pragma unroll 1
+        for (int j = lo; j < hi; ++j) {
+            int cidx = __ldg(g + j);
+            v3 vc = ld3(V + 3 * cidx);
+            if (dot_blas(l, vc - vb) > eps) { best = cidx; vb = vc; converged = false; }
+        }
+    }
+    return best;
 }
 
 // utils.py:78-122
@@ -265,8 +335,16 @@ D3D_DEV v3 support_unmargined(const C &c, v3 d, int lane) {
     case D3D_HULL:  // colliders.py:131-132
         if (D3D_HAS(D3D_HULL)) return ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, d, lane));
         break;
-    case D3D_MESH: if (D3D_HAS(D3D_MESH)) {  // mesh.py:182-189 (arg-max form)
-        v = ld3(c.V + 3 * argmax_dot<G>(c.V, c.nv, l, lane));
+    case D3D_MESH: if (D3D_HAS(D3D_MESH)) {  // mesh.py:79-87; without a graph mesh.py:182-189
+        const int32_t *g = c.graph();
+        int idx;
+        if (g) {
+            idx = hill_climb(c.V, c.nv, g, l.x, l.y, l.z, c.mesh_cur());
+            c.set_mesh_cur(idx, lane);
+        } else {
+            idx = argmax_dot<G>(c.V, c.nv, l, lane);
+        }
+        v = ld3(c.V + 3 * idx);
     }
     break;
     case D3D_DISK: if (D3D_HAS(D3D_DISK)) {  // geometry.py:375-383

@@ -34,6 +34,7 @@ struct EpaParams {
     double eps_sq_thr;   // smallest t with sqrt(t) >= epsilon:  sqrt(s) < epsilon  <=>  s < t
     double half_sq_thr;  // same for 0.5
     const double *Y;
+    const int32_t *npoints;
     double *out_mtv;
     uint8_t *out_success;
     int32_t *out_nfaces;
@@ -83,6 +84,16 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         if (lane == 0) k = atomicAdd(prm.counter, 1);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_pairs) break;
+        if (prm.npoints && __ldg(prm.npoints + k) != 4) {  // undefined in the reference (np.empty rows)
+            if (lane == 0) {
+                st3(prm.out_mtv + 3 * (int64_t)k, V3(0.0, 0.0, 0.0));
+                prm.out_success[k] = 0;
+                if (prm.out_nfaces) prm.out_nfaces[k] = 0;
+                if (prm.out_iters) prm.out_iters[k] = 0;
+                if (prm.out_status) prm.out_status[k] = D3D_EPA_BAD_SIMPLEX;
+            }
+            continue;
+        }
         int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
         Collider A = load_collider(c, pr.x), B = load_collider(c, pr.y);
 
@@ -244,6 +255,10 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         }
         if (lane == 0) {
             st3(prm.out_mtv + 3 * (int64_t)k, mtv);
+            if (c.mesh_last) {  // mesh.py:85
+                if (A.type == D3D_MESH) c.mesh_last[pr.x] = A.cur;
+                if (B.type == D3D_MESH) c.mesh_last[pr.y] = B.cur;
+            }
             prm.out_success[k] = success ? 1 : 0;
             if (prm.out_nfaces) prm.out_nfaces[k] = n_faces;
             if (prm.out_iters) prm.out_iters[k] = it;
@@ -275,7 +290,7 @@ extern "C" {
 size_t d3d_epa_workspace_bytes(int64_t n_pairs) { (void)n_pairs; return 256; }
 
 int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
-            int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
+            const int32_t *npoints, int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
             uint8_t *out_success, int32_t *out_nfaces, int32_t *out_iters, int32_t *out_status,
             double *out_faces, void *workspace, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -288,7 +303,7 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     EpaParams prm;
     prm.max_iter = max_iter; prm.max_loose_edges = max_loose_edges; prm.max_faces = max_faces;
     prm.epsilon = epsilon; prm.eps_sq_thr = sqrt_threshold(epsilon); prm.half_sq_thr = sqrt_threshold(0.5);
-    prm.Y = Y; prm.out_mtv = out_mtv; prm.out_success = out_success;
+    prm.Y = Y; prm.npoints = npoints; prm.out_mtv = out_mtv; prm.out_success = out_success;
     prm.out_nfaces = out_nfaces; prm.out_iters = out_iters; prm.out_status = out_status;
     prm.out_faces = out_faces; prm.counter = reinterpret_cast<int *>(workspace);
     D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, stream));

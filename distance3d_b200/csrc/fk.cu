@@ -121,9 +121,131 @@ __global__ void k_scatter_hits(const int32_t *__restrict__ pairs, const uint8_t 
     mask[pr.y] = 1;
 }
 
+// ---------------------------------------------------------------------------
+// self_collision.detect with the reference's ORDER (self_collision.py:22-36).  With
+// white-lists that are not symmetric (a link with several child links white-lists only one
+// of them, urdf_utils.py:79-81) the reference's result depends on the order in which
+// `aabb_overlapping_colliders` lists the candidates of a frame: the first intersecting one is
+// flagged together with the frame, then the loop breaks.  That order is the depth-first
+// order of the reference's incremental AABB tree (aabb_tree.py:194-341 insertion, :381-403
+// query: children pushed left then right, popped right first), rebuilt for every pose update
+// by inserting the colliders one at a time (broad_phase.py:144-151).  One thread per joint
+// configuration rebuilds that tree over its K boxes and replays the loop on the precomputed
+// intersection bits.
+#define D3D_DETECT_MAX_K 64
+
+__global__ void k_scatter_hit_bits(const int32_t *__restrict__ pairs, const uint8_t *__restrict__ hit,
+                                   const unsigned long long *count, int64_t cap, int group_size,
+                                   unsigned long long *bits) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t n = (int64_t)*count;
+    if (n > cap) n = cap;
+    if (t >= n || !hit[t]) return;
+    int2 pr = reinterpret_cast<const int2 *>(pairs)[t];
+    atomicOr(bits + pr.x, 1ull << (pr.y % group_size));
+    atomicOr(bits + pr.y, 1ull << (pr.x % group_size));
+}
+
+struct Box6 { double v[6]; };  // lo_x hi_x lo_y hi_y lo_z hi_z (the (3,2) layout)
+
+__device__ __forceinline__ Box6 merge_boxes(const Box6 &a, const Box6 &b) {  // aabb_tree.py:536-551
+    Box6 o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.v[2 * k] = a.v[2 * k] < b.v[2 * k] ? a.v[2 * k] : b.v[2 * k];
+        o.v[2 * k + 1] = a.v[2 * k + 1] > b.v[2 * k + 1] ? a.v[2 * k + 1] : b.v[2 * k + 1];
+    }
+    return o;
+}
+__device__ __forceinline__ double box_volume(const Box6 &m) {
+    return (m.v[1] - m.v[0]) * (m.v[3] - m.v[2]) * (m.v[5] - m.v[4]);
+}
+__device__ __forceinline__ bool boxes_overlap(const Box6 &a, const Box6 &b) {  // aabb_tree.py:503-527
+    return a.v[0] <= b.v[1] && a.v[1] >= b.v[0] && a.v[2] <= b.v[3] && a.v[3] >= b.v[2] &&
+           a.v[4] <= b.v[5] && a.v[5] >= b.v[4];
+}
+
+template <int MAXK>
+__global__ void __launch_bounds__(64)
+k_detect_ordered(const double *__restrict__ aabb, int64_t n_groups, int K,
+                 const unsigned long long *__restrict__ bits,
+                 const unsigned long long *__restrict__ whitelist, uint8_t *mask) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    // leaves 0..K-1, branches K..2K-2
+    Box6 box[2 * MAXK - 1];
+    signed char parent[2 * MAXK - 1], left[2 * MAXK - 1], right[2 * MAXK - 1];
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) box[i].v[c] = __ldg(aabb + 6 * (g * K + i) + c);
+    int root = -1, filled = K;
+    for (int leaf = 0; leaf < K; ++leaf) {
+        left[leaf] = right[leaf] = -1;
+        if (root < 0) { root = leaf; parent[leaf] = -1; continue; }
+        int t = root;
+        while (t >= K) {  // descend into the child whose merged box is smaller, ties go right
+            double cl = box_volume(merge_boxes(box[leaf], box[left[t]]));
+            double cr = box_volume(merge_boxes(box[leaf], box[right[t]]));
+            t = (cl < cr) ? left[t] : right[t];
+        }
+        int sib = t, old = parent[sib], np_ = filled++;
+        parent[np_] = (signed char)old; left[np_] = (signed char)sib; right[np_] = (signed char)leaf;
+        box[np_] = merge_boxes(box[leaf], box[sib]);
+        parent[leaf] = parent[sib] = (signed char)np_;
+        if (old < 0) root = np_;
+        else if (left[old] == sib) left[old] = (signed char)np_;
+        else right[old] = (signed char)np_;
+        for (int u = parent[np_]; u >= 0; u = parent[u]) box[u] = merge_boxes(box[left[u]], box[right[u]]);
+    }
+    unsigned long long marked = 0;
+    signed char stack[2 * MAXK];
+    for (int f = 0; f < K; ++f) {
+        if ((marked >> f) & 1) continue;  // contact was detected before
+        const unsigned long long allowed = ~__ldg(whitelist + f);
+        const unsigned long long hits = __ldg(bits + g * K + f) | (1ull << f);  // a collider intersects itself
+        int sp = 0;
+        stack[sp++] = (signed char)root;
+        while (sp) {
+            int n = stack[--sp];
+            if (!boxes_overlap(box[n], box[f])) continue;
+            if (n < K) {
+                if (((allowed >> n) & 1) && ((hits >> n) & 1)) {
+                    marked |= (1ull << f) | (1ull << n);
+                    break;
+                }
+            } else {
+                stack[sp++] = left[n];
+                stack[sp++] = right[n];
+            }
+        }
+    }
+    for (int f = 0; f < K; ++f) mask[g * K + f] = (uint8_t)((marked >> f) & 1);
+}
+
 }  // namespace
 
 extern "C" {
+
+int d3d_detect_ordered(const double *aabb, int64_t n_groups, int group_size, const int32_t *pairs,
+                       const uint8_t *hit, const unsigned long long *count, int64_t cap,
+                       const unsigned long long *whitelist, unsigned long long *hit_bits,
+                       uint8_t *mask, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_groups == 0 || group_size == 0) return 0;
+    if (group_size > D3D_DETECT_MAX_K) return d3d_set_error("d3d_detect_ordered: more than 64 colliders per group");
+    if (!aabb || !whitelist || !hit_bits || !mask || (cap > 0 && (!pairs || !hit || !count)))
+        return d3d_set_error("d3d_detect_ordered: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(hit_bits, 0, sizeof(unsigned long long) * n_groups * group_size, stream));
+    if (cap > 0)
+        k_scatter_hit_bits<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(pairs, hit, count, cap, group_size, hit_bits);
+    unsigned blocks = (unsigned)((n_groups + 63) / 64);
+    if (group_size <= 16)
+        k_detect_ordered<16><<<blocks, 64, 0, stream>>>(aabb, n_groups, group_size, hit_bits, whitelist, mask);
+    else
+        k_detect_ordered<D3D_DETECT_MAX_K><<<blocks, 64, 0, stream>>>(aabb, n_groups, group_size, hit_bits, whitelist, mask);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 
 int d3d_fk_urdf(int n_frames, int n_joints, const double *joint_axis, const double *joint_limits,
                 const int32_t *joint_type, const int32_t *chain_off, const double *chain_fixed,

@@ -207,6 +207,8 @@ struct GjkParams {
     int32_t *out_iters;
     int32_t *out_status;
     uint8_t *out_hit;
+    const int32_t *graph;  // d3d_colliders::graph (MeshGraph adjacency pool)
+    int32_t *mesh_last;    // d3d_colliders::mesh_last or nullptr
 };
 
 template <int STRIDE>
@@ -237,9 +239,9 @@ D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32
 // the switch is warp-uniform almost always.
 template <int G, int STRIDE, int TM>
 static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const real *base,
-                                               real dx, real dy, real dz, int lane) {
+                                               const int32_t *gpool, real dx, real dy, real dz, int lane) {
     ColliderSmem<STRIDE> c;
-    c.type = type; c.nv = nv; c.V = V; c.base = base;
+    c.type = type; c.nv = nv; c.V = V; c.base = base; c.gpool = gpool;
     return support<G, TM>(c, V3(dx, dy, dz), lane);
 }
 
@@ -262,8 +264,8 @@ template <int MODE, int G, int STRIDE, int TM>
 D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return false; }
     ++s.iters;
-    v3 p = support_call<G, STRIDE, TM>(s.A.type, s.A.nv, s.A.V, s.A.base, s.sd.x, s.sd.y, s.sd.z, lane);
-    v3 q = support_call<G, STRIDE, TM>(s.B.type, s.B.nv, s.B.V, s.B.base, -s.sd.x, -s.sd.y, -s.sd.z, lane);
+    v3 p = support_call<G, STRIDE, TM>(s.A.type, s.A.nv, s.A.V, s.A.base, prm.graph, s.sd.x, s.sd.y, s.sd.z, lane);
+    v3 q = support_call<G, STRIDE, TM>(s.B.type, s.B.nv, s.B.V, s.B.base, prm.graph, -s.sd.x, -s.sd.y, -s.sd.z, lane);
     v3 w = p - q;
     real dot = dot_blas(s.sd, w);
     if (MODE == 0) {
@@ -482,6 +484,15 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
     return false;
 }
 
+// MeshGraph vertex caching across calls (mesh.py:85): report the vertex each mesh ended on.
+template <int STRIDE>
+static __device__ __noinline__ void write_mesh_last(const PairState<STRIDE> &s, const int32_t *pairs,
+                                                    int32_t *mesh_last) {
+    int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + s.k);
+    if (s.A.type == D3D_MESH) mesh_last[pr.x] = s.A.mesh_cur();
+    if (s.B.type == D3D_MESH) mesh_last[pr.y] = s.B.mesh_cur();
+}
+
 // Closest points, sanity check and output (_gjk_jolt.py:209-221, 667-687).  PS: PairState or
 // FinState, SX: Simplex or SimplexFin.
 template <int MODE, class PS, class SX>
@@ -671,7 +682,11 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
         unsigned run_mask = __ballot_sync(0xffffffffu, running);
         int idle = 32 - __popc(run_mask);
         if (idle >= GJK_REFILL_MIN || run_mask == 0) {
-            if (finished) { gjk_finish_or_park<MODE>(s, S, prm, w); finished = false; }
+            if (finished) {
+                if (((TM >> D3D_MESH) & 1) && prm.mesh_last) write_mesh_last(s, pairs, prm.mesh_last);
+                gjk_finish_or_park<MODE>(s, S, prm, w);
+                finished = false;
+            }
             if (!exhausted) {
                 unsigned need = ~run_mask;
                 int want = __popc(need), rank = __popc(need & lt_mask);
@@ -749,6 +764,7 @@ k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, G
             gjk_step<MODE, 32, 1>(s, S, prm, lane);
             __syncwarp();
         }
+        if (prm.mesh_last && lane == 0) write_mesh_last(s, pairs, prm.mesh_last);
         gjk_finish<MODE>(s, S, prm, lane == 0);
         __syncwarp();
     }
@@ -824,6 +840,7 @@ int D3D_GJK_SYM(d3d_gjk_distance)(const d3d_colliders *c, const int32_t *pairs, 
     prm.out_dist = out_dist; prm.out_a = out_a; prm.out_b = out_b; prm.out_Y = out_Y;
     prm.out_npoints = out_npoints; prm.out_iters = out_iters; prm.out_status = out_status;
     prm.out_hit = nullptr;
+    prm.graph = c->graph; prm.mesh_last = c->mesh_last;
     return launch_gjk<0>(c, pairs, n_pairs, prm, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -835,6 +852,7 @@ int D3D_GJK_SYM(d3d_gjk_intersection)(const d3d_colliders *c, const int32_t *pai
     GjkParams prm = {};
     prm.tolerance_sq = tolerance * tolerance;
     prm.out_hit = out_hit; prm.out_iters = out_iters; prm.out_status = out_status;
+    prm.graph = c->graph; prm.mesh_last = c->mesh_last;
     return launch_gjk<1>(c, pairs, n_pairs, prm, workspace, ws_bytes, (cudaStream_t)stream);
 }
 

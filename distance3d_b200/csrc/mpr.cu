@@ -215,6 +215,10 @@ k_mpr(d3d_colliders c, const int32_t *__restrict__ pairs, const int32_t *__restr
     }
     if (status == D3D_UNKNOWN) status = hit ? D3D_INTERSECTION : D3D_NO_INTERSECTION;
     prm.out_hit[k] = (uint8_t)hit;
+    if (c.mesh_last) {  // mesh.py:85
+        if (A.type == D3D_MESH) c.mesh_last[pr.x] = A.cur;
+        if (B.type == D3D_MESH) c.mesh_last[pr.y] = B.cur;
+    }
     if (prm.out_status) prm.out_status[k] = status;
     if (prm.want_pen) {
         prm.out_depth[k] = depth;

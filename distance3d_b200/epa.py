@@ -28,12 +28,14 @@ class EpaResult:
 
 
 def epa_batch(colliders, pairs, simplices, max_iter=64, max_loose_edges=32, max_faces=64,
-              epsilon=1e-8, want_faces=False):
+              epsilon=1e-8, want_faces=False, n_points=None):
     """Minimum translation vectors for many intersecting pairs (device tensors).
 
     `simplices` f64[P,4,3]: GJK simplex of each pair; EPA is defined only where GJK
     ended with a full 4-point simplex.  status = 7 where the
-    reference would raise its `max_faces` AssertionError (epa.py:128).
+    reference would raise its `max_faces` AssertionError (epa.py:128).  `n_points` int32[P]
+    (optional, GjkResult.n_points): pairs with fewer than 4 simplex points are skipped with
+    status = 8 instead of running on rows GJK never wrote.
     """
     torch = _lib.torch_cuda()
     dc = _lib.as_device_colliders(colliders)
@@ -48,10 +50,12 @@ def epa_batch(colliders, pairs, simplices, max_iter=64, max_loose_edges=32, max_
     res = EpaResult(torch.empty((n, 3), **f64), torch.empty(n, dtype=torch.uint8, device=dc.device),
                     torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **i32),
                     torch.empty((n, max_faces, 4, 3), **f64) if want_faces else None)
+    if n_points is not None:
+        n_points = n_points.to(device=dc.device, dtype=torch.int32).contiguous()
     L = _lib.lib()
     ws = workspace(256, dc.device, "epa")
     _lib._check(L.d3d_epa(
-        ctypes.byref(dc.struct), ptr(pairs), c_i64(n), ptr(Y), c_int(max_iter),
+        ctypes.byref(dc.struct), ptr(pairs), c_i64(n), ptr(Y), ptr(n_points), c_int(max_iter),
         c_int(max_loose_edges), c_int(max_faces), c_dbl(epsilon), ptr(res.mtv), ptr(res.success),
         ptr(res.n_faces), ptr(res.iters), ptr(res.status), ptr(res.faces), ptr(ws),
         c_size(ws.numel()), _lib.stream_ptr()))
@@ -66,9 +70,11 @@ def epa(simplex, collider1, collider2, max_iter=64, max_loose_edges=32, max_face
     to the second collider (or subtracted from the first), the polytope faces
     ``(n_faces, 4, 3)`` and whether EPA converged.
     """
-    res = epa_batch(pack_colliders([collider1, collider2]), np.array([[0, 1]], dtype=np.int32),
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    res = epa_batch(cs, np.array([[0, 1]], dtype=np.int32),
                     np.asarray(simplex, dtype=np.float64).reshape(1, 4, 3), max_iter,
                     max_loose_edges, max_faces, epsilon, want_faces=True).cpu()
+    cs.commit_mesh_state()
     if int(res["status"][0]) == STATUS_EPA_MAX_FACES:
         raise AssertionError("self.n_faces < self.max_faces")  # epa.py:128
     n_faces = int(res["n_faces"][0])

@@ -39,11 +39,17 @@ _workspaces = {}
 
 
 def workspace(n_bytes, device, tag="gjk"):
-    """Grow-only scratch buffer per (device, tag)."""
+    """Grow-only scratch buffer per (device, CUDA stream, tag): calls issued on different
+    streams may run concurrently and must not share binning scratch or work counters; a
+    buffer that is replaced stays alive until the work queued on its stream is done
+    (record_stream)."""
     torch = _lib.torch_cuda()
-    key = (device.index, tag)
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < n_bytes:
+        if buf is not None:
+            buf.record_stream(stream)
         buf = torch.empty(int(n_bytes * 1.25) + 4096, dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
@@ -150,8 +156,9 @@ def gjk_distance_jolt(collider1, collider2, tolerance=1e-10, max_distance_square
     Returns ``(distance, closest_point1, closest_point2, simplex)`` or
     ``(MAX_FLOAT, None, None, None)`` when the pair was clipped.
     """
-    res = gjk_distance_batch(pack_colliders([collider1, collider2]), _PAIR01, tolerance,
-                             max_distance_squared, sanity_check).cpu()
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    res = gjk_distance_batch(cs, _PAIR01, tolerance, max_distance_squared, sanity_check).cpu()
+    cs.commit_mesh_state()
     status = int(res["status"][0])
     if status == STATUS_CLIPPED:
         return MAX_FLOAT, None, None, None
@@ -162,15 +169,17 @@ def gjk_distance_jolt(collider1, collider2, tolerance=1e-10, max_distance_square
 def gjk_distance_jolt_iterations(collider1, collider2, tolerance=1e-10,
                                  max_distance_squared=100000.0):
     """Number of GJK iterations (reference: _gjk_jolt.py:714-785)."""
-    res = gjk_distance_batch(pack_colliders([collider1, collider2]), _PAIR01, tolerance,
-                             max_distance_squared, float("inf")).cpu()
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    res = gjk_distance_batch(cs, _PAIR01, tolerance, max_distance_squared, float("inf")).cpu()
+    cs.commit_mesh_state()
     return int(res["iters"][0])
 
 
 def gjk_intersection_jolt(collider1, collider2, tolerance=1e-10):
     """Do two convex colliders intersect? (reference: _gjk_jolt.py:29-80)."""
-    hit, _, status = gjk_intersection_batch(pack_colliders([collider1, collider2]), _PAIR01,
-                                            tolerance)
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    hit, _, status = gjk_intersection_batch(cs, _PAIR01, tolerance)
+    cs.commit_mesh_state()
     _raise_for_status(int(status[0]))
     return bool(hit[0])
 

@@ -31,8 +31,9 @@ def support_function(collider1, collider2, search_direction):
     from . import _lib
     from .pack import pack_colliders
     d = np.asarray(search_direction, dtype=float)
-    out = _lib.support(pack_colliders([collider1, collider2]), np.array([0, 1], dtype=np.int32),
-                       np.stack((d, -d)))
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    out = _lib.support(cs, np.array([0, 1], dtype=np.int32), np.stack((d, -d)))
+    cs.commit_mesh_state()
     return make_support_point(out[0], out[1])
 
 

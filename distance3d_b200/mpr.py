@@ -38,8 +38,9 @@ _PAIR01 = np.array([[0, 1]], dtype=np.int32)
 
 def mpr_intersection(collider1, collider2, mpr_tolerance=0.0001, max_iterations=100):
     """Intersection test with MPR (reference: mpr.py:21-50)."""
-    out = mpr_batch(pack_colliders([collider1, collider2]), _PAIR01, mpr_tolerance,
-                    max_iterations, penetration=False)
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    out = mpr_batch(cs, _PAIR01, mpr_tolerance, max_iterations, penetration=False)
+    cs.commit_mesh_state()
     return bool(out["hit"][0])
 
 
@@ -49,8 +50,9 @@ def mpr_penetration(collider1, collider2, mpr_tolerance=0.0001, max_iterations=1
     Returns ``(intersection, depth, penetration_direction, contact_position)``;
     the last three are None when the colliders do not intersect.
     """
-    out = mpr_batch(pack_colliders([collider1, collider2]), _PAIR01, mpr_tolerance,
-                    max_iterations, penetration=True)
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    out = mpr_batch(cs, _PAIR01, mpr_tolerance, max_iterations, penetration=True)
+    cs.commit_mesh_state()
     if not bool(out["hit"][0]):
         return False, None, None, None
     return (True, float(out["depth"][0]), out["dir"][0].cpu().numpy(), out["pos"][0].cpu().numpy())

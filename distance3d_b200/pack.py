@@ -13,6 +13,9 @@ HBM and is indexed by the kernels:
     verts     f64[M,3]     box: 8 world vertices (written on the device by
                            d3d_prepare); hull: world frame; mesh: local frame
     margin    f64[N]       optional Margin wrapper
+    graph_off int32[N]     MeshGraph: offset of the adjacency record in `graph` (-1: none)
+    graph     int32[G]     adjacency records (distance3d_b200.mesh.build_mesh_graph)
+    mesh_start int32[N]    MeshGraph: cached start vertex of the object (-1: record default)
 
 `ColliderSet` holds the host copy (numpy) and, lazily, the device copy (torch
 tensors on the current CUDA device).
@@ -37,6 +40,10 @@ class CColliders(ctypes.Structure):
         ("vert_len", ctypes.c_void_p),
         ("verts", ctypes.c_void_p),
         ("margin", ctypes.c_void_p),
+        ("graph_off", ctypes.c_void_p),
+        ("graph", ctypes.c_void_p),
+        ("mesh_start", ctypes.c_void_p),
+        ("mesh_last", ctypes.c_void_p),
     ]
 
 
@@ -49,7 +56,7 @@ class ColliderSet:
     """
 
     def __init__(self, type_, pose, param, vert_off, vert_len, verts, margin=None,
-                 boxes_prepared=False):
+                 boxes_prepared=False, graph_off=None, graph=None, mesh_start=None):
         n = len(type_)
         self.type = np.ascontiguousarray(type_, dtype=np.int32)
         self.pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(n, 4, 4)
@@ -61,6 +68,15 @@ class ColliderSet:
             self.verts = np.zeros((1, 3))  # never hand out a null pool pointer
         self.margin = None if margin is None else np.ascontiguousarray(margin, dtype=np.float64)
         self.boxes_prepared = boxes_prepared
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        self.graph_off, self.graph, self.mesh_start = i32(graph_off), i32(graph), i32(mesh_start)
+        if self.graph_off is None:
+            self.graph = None
+        hv = (self.type == HULL) | (self.type == MESH)
+        if np.any(hv & (self.vert_len <= 0)):
+            raise ValueError("ConvexHullVertices / MeshGraph colliders need at least one vertex")
+        # scalar API: the MeshGraph objects whose cached start vertex follows the calls
+        self.mesh_objects = None
         self._device = {}
 
     from_arrays = classmethod(lambda cls, *a, **k: cls(*a, **k))
@@ -83,6 +99,10 @@ class ColliderSet:
         s.vert_len = self.vert_len.ctypes.data
         s.verts = self.verts.ctypes.data
         s.margin = None if self.margin is None else self.margin.ctypes.data
+        s.graph_off = None if self.graph_off is None else self.graph_off.ctypes.data
+        s.graph = None if self.graph is None else self.graph.ctypes.data
+        s.mesh_start = None if self.mesh_start is None else self.mesh_start.ctypes.data
+        s.mesh_last = None
         return s
 
     def device(self, device=None):
@@ -115,7 +135,20 @@ class ColliderSet:
             verts[vert_off[k]:vert_off[k] + l] = self.verts[o:o + l]
         return ColliderSet(self.type[idx], self.pose[idx], self.param[idx], vert_off, vert_len,
                            verts, None if self.margin is None else self.margin[idx],
-                           boxes_prepared=self.boxes_prepared)
+                           boxes_prepared=self.boxes_prepared,
+                           graph_off=None if self.graph_off is None else self.graph_off[idx],
+                           graph=self.graph,
+                           mesh_start=None if self.mesh_start is None else self.mesh_start[idx])
+
+    def commit_mesh_state(self, device=None):
+        """Scalar API: copy the vertex every MeshGraph ended on back into the objects
+        (`first_idx` caching of the reference, mesh.py:85)."""
+        if not self.mesh_objects:
+            return
+        last = self.device(device).mesh_last.cpu().numpy()
+        for i, obj in self.mesh_objects:
+            if last[i] >= 0:
+                obj._first_idx = int(last[i])
 
 
 class DeviceColliders:
@@ -123,12 +156,17 @@ class DeviceColliders:
 
     def __init__(self, cs, device):
         import torch
-        to = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+        to = lambda a: None if a is None else torch.from_numpy(a).to(device)  # noqa: E731
+        mesh_last = None
+        if cs.mesh_objects:
+            mesh_last = torch.full((len(cs),), -1, dtype=torch.int32, device=device)
         self._init(to(cs.type), to(cs.pose), to(cs.param), to(cs.vert_off), to(cs.vert_len),
-                   to(cs.verts), None if cs.margin is None else to(cs.margin))
+                   to(cs.verts), to(cs.margin), to(cs.graph_off), to(cs.graph), to(cs.mesh_start),
+                   mesh_last)
 
     @classmethod
-    def from_tensors(cls, type_, pose, param, vert_off=None, vert_len=None, verts=None, margin=None):
+    def from_tensors(cls, type_, pose, param, vert_off=None, vert_len=None, verts=None, margin=None,
+                     graph_off=None, graph=None, mesh_start=None):
         """Wrap device tensors that already live in HBM (no host round trip)."""
         import torch
         self = cls.__new__(cls)
@@ -142,10 +180,11 @@ class DeviceColliders:
             verts = torch.zeros((1, 3), dtype=torch.float64, device=dev)
         self._init(type_.to(torch.int32).contiguous(), pose.reshape(n, 4, 4).contiguous(),
                    param.reshape(n, 3).contiguous(), vert_off.contiguous(), vert_len.contiguous(),
-                   verts.reshape(-1, 3).contiguous(), margin)
+                   verts.reshape(-1, 3).contiguous(), margin, graph_off, graph, mesh_start)
         return self
 
-    def _init(self, type_, pose, param, vert_off, vert_len, verts, margin):
+    def _init(self, type_, pose, param, vert_off, vert_len, verts, margin, graph_off=None,
+              graph=None, mesh_start=None, mesh_last=None):
         from . import _lib
         self.device = type_.device
         self.n = int(type_.shape[0])
@@ -160,8 +199,51 @@ class DeviceColliders:
         self.struct.vert_len = self.vert_len.data_ptr()
         self.struct.verts = self.verts.data_ptr()
         self.struct.margin = None if self.margin is None else self.margin.data_ptr()
+        if graph_off is None:
+            graph = None
+        self.graph_off, self.graph, self.mesh_start, self.mesh_last = graph_off, graph, mesh_start, mesh_last
+        for name in ("graph_off", "graph", "mesh_start", "mesh_last"):
+            t = getattr(self, name)
+            if t is not None and t.dtype != torch_int32():
+                raise TypeError("%s must be an int32 tensor" % name)
+            setattr(self.struct, name, None if t is None else t.data_ptr())
         # box vertices are generated on the device (geometry.py:138-157)
         _lib.prepare(self)
+
+
+def concat_sets(sets):
+    """Concatenate ColliderSets (vertex and adjacency pools are appended and re-based)."""
+    n_v = n_g = 0
+    vo, go = [], []
+    any_graph = any(s.graph_off is not None for s in sets)
+    any_margin = any(s.margin is not None for s in sets)
+    for s in sets:
+        vo.append(s.vert_off.astype(np.int64) + n_v)
+        n_v += len(s.verts)
+        if any_graph:
+            if s.graph_off is None:
+                go.append(np.full(len(s), -1, dtype=np.int64))
+            else:
+                go.append(np.where(s.graph_off >= 0, s.graph_off.astype(np.int64) + n_g, -1))
+                n_g += len(s.graph)
+    cat = lambda name: np.concatenate([getattr(s, name) for s in sets])  # noqa: E731
+    graph = None
+    if any_graph:
+        # row pointers are relative to their record: the records are appended unchanged
+        graph = np.concatenate([s.graph for s in sets if s.graph_off is not None])
+    return ColliderSet(
+        cat("type"), cat("pose"), cat("param"), np.concatenate(vo), cat("vert_len"), cat("verts"),
+        np.concatenate([s.margin if s.margin is not None else np.zeros(len(s)) for s in sets])
+        if any_margin else None,
+        graph_off=np.concatenate(go) if any_graph else None, graph=graph,
+        mesh_start=np.concatenate([s.mesh_start if s.mesh_start is not None
+                                   else np.full(len(s), -1, dtype=np.int32) for s in sets])
+        if any_graph else None)
+
+
+def torch_int32():
+    import torch
+    return torch.int32
 
 
 def _pose_from_center(center):
@@ -170,8 +252,11 @@ def _pose_from_center(center):
     return T
 
 
-def pack_colliders(colliders):
-    """Pack a sequence of collider objects into a :class:`ColliderSet`."""
+def pack_colliders(colliders, track_mesh_state=False):
+    """Pack a sequence of collider objects into a :class:`ColliderSet`.
+
+    track_mesh_state: scalar-API mode - the set remembers its MeshGraph objects so that
+    `commit_mesh_state` can carry their cached start vertex from call to call."""
     from . import colliders as C
     n = len(colliders)
     type_ = np.zeros(n, dtype=np.int32)
@@ -184,6 +269,10 @@ def pack_colliders(colliders):
     any_margin = False
     chunks = []
     n_verts = 0
+    graph_off = np.full(n, -1, dtype=np.int32)
+    mesh_start = np.full(n, -1, dtype=np.int32)
+    graph_chunks, graph_at, n_graph = [], {}, 0
+    mesh_objects = []
 
     def add_vertices(i, V):
         nonlocal n_verts
@@ -210,6 +299,15 @@ def pack_colliders(colliders):
             type_[i] = MESH
             pose[i] = c.mesh2origin
             add_vertices(i, c.vertices)
+            g = c.graph_record()
+            if id(g) not in graph_at:  # colliders that share a mesh share its record
+                graph_at[id(g)] = n_graph
+                graph_chunks.append(g)
+                n_graph += len(g)
+            graph_off[i] = graph_at[id(g)]
+            if c._first_idx is not None:
+                mesh_start[i] = c._first_idx
+            mesh_objects.append((i, c))
         elif isinstance(c, C.Sphere):
             type_[i] = SPHERE
             pose[i] = _pose_from_center(c.c)
@@ -244,5 +342,11 @@ def pack_colliders(colliders):
         else:
             raise TypeError("Unsupported collider type %r" % type(c))
     verts = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, 3))
-    return ColliderSet(type_, pose, param, vert_off, vert_len, verts,
-                       margin if any_margin else None)
+    cs = ColliderSet(type_, pose, param, vert_off, vert_len, verts,
+                     margin if any_margin else None,
+                     graph_off=graph_off if graph_chunks else None,
+                     graph=np.concatenate(graph_chunks) if graph_chunks else None,
+                     mesh_start=mesh_start if graph_chunks else None)
+    if track_mesh_state and mesh_objects:
+        cs.mesh_objects = mesh_objects
+    return cs

@@ -220,6 +220,32 @@ def random_collider_set(rs, n, names=PRIMITIVES, center_scale=1.0, size_scale=1.
     return _pack.ColliderSet(type_, pose, param, vert_off, vert_len, verts)
 
 
+def random_meshgraph_set(rs, n_meshes, n_mesh_colliders, n_other, hull_vertices=(10, 30),
+                          names=PRIMITIVES, center_scale=1.0):
+    """`n_mesh_colliders` MeshGraph colliders that share `n_meshes` random convex meshes
+    (randn_convex shapes with a vertex count uniform in `hull_vertices`, each collider with
+    its own pose) followed by `n_other` colliders drawn from `names`, packed."""
+    from . import colliders as C
+    meshes = []
+    for _ in range(n_meshes):
+        nv = int(rs.randint(hull_vertices[0], hull_vertices[1] + 1))
+        _, V, tri = randn_convex(rs, n_vertices=nv)
+        meshes.append(C.MeshGraph(np.eye(4), V, tri))
+    poses = random_transforms(rs, n_mesh_colliders)
+    poses[:, :3, 3] *= center_scale
+    cols = []
+    for k in range(n_mesh_colliders):
+        src = meshes[k % n_meshes]
+        m = C.MeshGraph(poses[k], src.vertices, src.triangles)
+        m._graph = src.graph_record()  # one adjacency record per mesh
+        cols.append(m)
+    mesh_set = _pack.pack_colliders(cols)
+    if n_other == 0:
+        return mesh_set
+    return _pack.concat_sets([mesh_set, random_collider_set(rs, n_other, names=names,
+                                                            center_scale=center_scale)])
+
+
 def random_pairs(rs, n_colliders, n_pairs):
     """Random (i, j) index pairs, i != j."""
     a = rs.randint(n_colliders, size=n_pairs)

@@ -15,19 +15,36 @@ from .pack import DeviceColliders, pack_colliders
 
 
 def _candidate_pattern(frames, whitelists):
-    """Unordered frame pairs (i < j) that are not white-listed in either direction."""
-    pattern = []
+    """Frame pairs (i < j) the narrow phase has to test, and the white-list bit masks.
+
+    The reference filters the candidates of frame i by whitelists[i] only
+    (self_collision.py:27-28), so a pair is dropped only when BOTH frames white-list each
+    other.  Returns (pattern int32[C,2], wl uint64[K] with bit j of wl[i] = j white-listed
+    for i, symmetric flag).  White-lists of a serial chain are symmetric; a link with several
+    child links white-lists only one of them (urdf_utils.py:79-81) and is not.
+    """
+    K = len(frames)
+    index = {f: i for i, f in enumerate(frames)}
+    wl = np.zeros(K, dtype=np.uint64)
     for i, fi in enumerate(frames):
-        for j in range(i + 1, len(frames)):
-            fj = frames[j]
-            if fj in whitelists.get(fi, ()) or fi in whitelists.get(fj, ()):
-                continue
-            pattern.append((i, j))
-    return np.array(pattern, dtype=np.int32).reshape(-1, 2)
+        for fj in whitelists.get(fi, ()):
+            if fj in index and index[fj] < 64:
+                wl[i] |= np.uint64(1) << np.uint64(index[fj])
+    listed = lambda i, j: bool((int(wl[i]) >> j) & 1) if j < 64 else frames[j] in whitelists.get(frames[i], ())  # noqa: E731
+    pattern = [(i, j) for i in range(K) for j in range(i + 1, K)
+               if not (listed(i, j) and listed(j, i))]
+    symmetric = all(listed(i, j) == listed(j, i) for i in range(K) for j in range(i + 1, K)) \
+        and all(listed(i, i) for i in range(K))
+    return np.array(pattern, dtype=np.int32).reshape(-1, 2), wl, symmetric
 
 
-def _contact_mask(dc, n_groups, group_size, pattern_t):
-    """uint8 mask [n_groups * group_size]: collider takes part in an intersecting candidate pair."""
+def _contact_mask(dc, n_groups, group_size, pattern_t, wl_t=None, symmetric=True):
+    """uint8 mask [n_groups * group_size] of self_collision.detect, the number of narrow-phase
+    candidates and the number of pairs whose GJK run ended in an error status.
+
+    Symmetric white-lists: a collider is flagged iff it takes part in an intersecting
+    candidate pair (the reference's loop order cannot matter then).  Otherwise the
+    reference's ordered loop is replayed on the device (d3d_detect_ordered)."""
     torch = _lib.torch_cuda()
     L = _lib.lib()
     dev = dc.device
@@ -42,11 +59,29 @@ def _contact_mask(dc, n_groups, group_size, pattern_t):
                                    _lib.stream_ptr()))
     n_cand = int(count.item())
     mask = torch.zeros(dc.n, dtype=torch.uint8, device=dev)
+    hit = status = None
     if n_cand:
-        hit, _, _ = gjk.gjk_intersection_batch(dc, pairs[:n_cand])
-        _lib._check(L.d3d_scatter_hits(ptr(pairs), ptr(hit), ptr(count), c_i64(n_cand), ptr(mask),
-                                       _lib.stream_ptr()))
-    return mask, n_cand
+        hit, _, status = gjk.gjk_intersection_batch(dc, pairs[:n_cand])
+    if symmetric:
+        if n_cand:
+            _lib._check(L.d3d_scatter_hits(ptr(pairs), ptr(hit), ptr(count), c_i64(n_cand), ptr(mask),
+                                           _lib.stream_ptr()))
+    else:
+        if group_size > 64:
+            raise NotImplementedError("ordered self-collision replay supports up to 64 colliders")
+        bits = torch.empty(dc.n, dtype=torch.int64, device=dev)
+        _lib._check(L.d3d_detect_ordered(ptr(aabb), c_i64(n_groups), c_int(group_size), ptr(pairs),
+                                         ptr(hit), ptr(count), c_i64(n_cand), ptr(wl_t), ptr(bits),
+                                         ptr(mask), _lib.stream_ptr()))
+    n_bad = (status >= gjk.STATUS_SANITY_FAILED).sum() if n_cand else None
+    return mask, n_cand, n_bad
+
+
+def _raise_for_bad(n_bad):
+    n = sum(int(b.item()) for b in n_bad if b is not None)
+    if n:
+        raise RuntimeError("%d candidate pairs ended GJK without a verdict (monotonicity "
+                           "assertion or iteration cap); their contacts are undefined" % n)
 
 
 def detect(bvh):
@@ -58,15 +93,18 @@ def detect(bvh):
         return {}
     cs = pack_colliders(list(bvh.colliders_.values()))
     dc = cs.device()
-    pattern = _candidate_pattern(frames, bvh.self_collision_whitelists_)
+    pattern, wl, symmetric = _candidate_pattern(frames, bvh.self_collision_whitelists_)
     pattern_t = torch.from_numpy(pattern).to(dc.device)
-    mask, _ = _contact_mask(dc, 1, len(frames), pattern_t)
+    wl_t = torch.from_numpy(wl.view(np.int64)).to(dc.device)
+    mask, _, n_bad = _contact_mask(dc, 1, len(frames), pattern_t, wl_t, symmetric)
+    _raise_for_bad([n_bad])
     mask = mask.cpu().numpy().astype(bool)
     return {frame: bool(m) for frame, m in zip(frames, mask)}
 
 
 def detect_any(bvh):
-    """Is there any self collision? (reference: self_collision.py:39-64)."""
+    """Is there any self collision? (reference: self_collision.py:39-64: every frame tests all
+    of its candidates, so the answer does not depend on their order)."""
     return any(detect(bvh).values())
 
 
@@ -96,8 +134,9 @@ class RobotModel:
         self.n_joints = len(self.joint_names)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         self.kin = {k: t(v) for k, v in kin.items() if k != "joint_names"}
-        self.pattern = _candidate_pattern(self.frames, bvh.self_collision_whitelists_)
+        self.pattern, wl, self.symmetric = _candidate_pattern(self.frames, bvh.self_collision_whitelists_)
         self.pattern_t = t(self.pattern)
+        self.wl_t = t(wl.view(np.int64))
         self.type_t = t(self.template.type)
         self.param_t = t(self.template.param)
         self.device = dev
@@ -134,10 +173,14 @@ class RobotModel:
         B = q.shape[0]
         out = torch.empty((B, self.n_frames), dtype=torch.uint8, device=self.device)
         n_cand = 0
+        bad = []
         for s in range(0, B, chunk):
             poses = self.forward_kinematics(q[s:s + chunk])
             dc = self.colliders_for(poses)
-            mask, nc = _contact_mask(dc, poses.shape[0], self.n_frames, self.pattern_t)
+            mask, nc, n_bad = _contact_mask(dc, poses.shape[0], self.n_frames, self.pattern_t,
+                                            self.wl_t, self.symmetric)
             out[s:s + chunk] = mask.reshape(-1, self.n_frames)
             n_cand += nc
+            bad.append(n_bad)
+        _raise_for_bad(bad)
         return out, n_cand

@@ -1,5 +1,4 @@
 """URDF helpers (reference: distance3d/urdf_utils.py:7-118)."""
-import re
 import warnings
 
 import numpy as np
@@ -21,49 +20,56 @@ def fast_transform_manager_initialization(tm, frames, base):
 
 
 def self_collision_whitelists(tm):
-    """Collision frames of the own, parent and child link per collision object
-    (urdf_utils.py:39-64)."""
-    whitelist = {}
+    """Frames a collision object may touch: every collision object of its own link, of the
+    parent link and of the child link (urdf_utils.py:39-64)."""
     info = LinkInfo(tm)
+    whitelist = {}
     for obj in tm.collision_objects:
         link = info.link(obj.frame)
-        whitelist[obj.frame] = (
-            info.collision_frames_attached_to_link(link)
-            + info.collision_frames_attached_to_link(info.parent_link(link))
-            + info.collision_frames_attached_to_link(info.child_link(link)))
+        whitelist[obj.frame] = [
+            frame for l in (link, info.parent_link(link), info.child_link(link))
+            for frame in info.collision_frames_attached_to_link(l)]
     return whitelist
 
 
 class LinkInfo:
-    """Link relations of a UrdfTransformManager (urdf_utils.py:67-118).
+    """Link relations read off the transform graph of a UrdfTransformManager.
 
-    Like the reference this relies on the insertion order of `tm.transforms`:
-    frames attached to links are registered before any joint, so the last
-    (child, parent) entry seen for a parent is its child LINK.
+    Every edge `(child, parent)` of `tm.transforms` is either a collision / visual /
+    inertial frame hanging off its link or a joint between two links.  The collision frames
+    are known (`tm.collision_objects`), so their edge names the owning link directly; the
+    remaining edges give each link its parent and its children.  One behaviour of the
+    reference (urdf_utils.py:67-118) is kept on purpose because the white-lists and with
+    them the self-collision masks depend on it: a link with several child links white-lists
+    only the LAST one registered (the reference overwrites `child_links[parent]` edge by
+    edge, joints come after the link-attached frames).
     """
 
     def __init__(self, tm):
         self.tm = tm
+        collision_frames = {obj.frame for obj in tm.collision_objects}
+        self.owner = {}        # collision frame -> link
+        self.attached = {}     # link -> its collision frames, registration order
         self.parent_links = {}
-        self.child_links = {}
+        self.child_links = {}  # link -> last registered child
         for child, parent in tm.transforms:
+            if child in collision_frames:
+                self.owner[child] = parent
+                self.attached.setdefault(parent, []).append(child)
             self.parent_links[child] = parent
             self.child_links[parent] = child
-        self.prog_match_link = re.compile(r"collision:(.*)\/.*")
 
     def link(self, frame):
-        result = self.prog_match_link.match(frame)
-        if result is None:
+        if frame not in self.owner:
             warnings.warn(f"Couldn't extract link of collision object at frame '{frame}'")
             return None
-        return result.group(1)
+        return self.owner[frame]
 
     def child_link(self, link_frame):
-        return self.child_links.get(link_frame, None)
+        return self.child_links.get(link_frame)
 
     def parent_link(self, link_frame):
-        return self.parent_links.get(link_frame, None)
+        return self.parent_links.get(link_frame)
 
     def collision_frames_attached_to_link(self, link_frame):
-        prog = re.compile(f"collision:{link_frame}" + r"\/.*")
-        return [node for node in self.tm.nodes if isinstance(node, str) and prog.match(node)]
+        return list(self.attached.get(link_frame, ()))

@@ -98,7 +98,10 @@ int d3d_gjk_intersection_f32(const d3d_colliders *c, const int32_t *pairs, int64
                              int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
 
 /* epa.py:9-78 epa(simplex, collider1, collider2, max_iter, max_loose_edges, max_faces, epsilon)
- * for pairs[k] with GJK simplex Y[k,4,3] (out_Y of d3d_gjk_distance, 4 valid rows required):
+ * for pairs[k] with GJK simplex Y[k,4,3] (out_Y of d3d_gjk_distance).  The reference reads all
+ * four rows of the simplex although GJK may have ended with fewer valid points (its result is
+ * then undefined, rows of np.empty); npoints[k] (out_npoints of d3d_gjk_distance, may be NULL
+ * = all 4) marks those pairs: they are skipped with status D3D_EPA_BAD_SIMPLEX, mtv 0.
  *   out_mtv[k,3]   minimum translation vector (depth = |mtv|, normal = mtv / |mtv|)
  *   out_success[k] 1 = converged before max_iter
  *   out_nfaces[k], out_iters[k] (may be NULL); out_faces[k,max_faces,4,3] (may be NULL)
@@ -107,7 +110,7 @@ int d3d_gjk_intersection_f32(const d3d_colliders *c, const int32_t *pairs, int64
  * Limits: 4 <= max_faces <= 64, 1 <= max_loose_edges <= 32 (the reference's defaults). */
 size_t d3d_epa_workspace_bytes(int64_t n_pairs);
 int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
-            int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
+            const int32_t *npoints, int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
             uint8_t *out_success, int32_t *out_nfaces, int32_t *out_iters, int32_t *out_status,
             double *out_faces, void *workspace, size_t ws_bytes, void *stream);
 
@@ -210,6 +213,21 @@ int d3d_filter_pairs(const double *aabb, int64_t n_groups, int group_size, const
  * with hit[t] != 0. */
 int d3d_scatter_hits(const int32_t *pairs, const uint8_t *hit, const unsigned long long *count,
                      int64_t cap, uint8_t *mask, void *stream);
+
+/* self_collision.py:22-36 with the reference's candidate ORDER, for white-lists that are not
+ * symmetric (urdf_utils.py:79-81): per group the reference's incremental AABB tree
+ * (aabb_tree.py:194-341, one insert per collider as in broad_phase.py:144-151) is rebuilt
+ * over the group's boxes and the detect loop is replayed - frames in order, candidates in the
+ * tree's depth-first query order (aabb_tree.py:381-403) minus whitelist[frame], the first
+ * intersecting candidate flags both frames.  pairs/hit/count: output of d3d_filter_pairs and
+ * d3d_gjk_intersection over every pair that is not white-listed in BOTH directions;
+ * whitelist[group_size]: bit j of entry i = frame j is white-listed for frame i;
+ * hit_bits[n_groups*group_size]: scratch; mask[n_groups*group_size]: output.
+ * group_size <= 64. */
+int d3d_detect_ordered(const double *aabb, int64_t n_groups, int group_size, const int32_t *pairs,
+                       const uint8_t *hit, const unsigned long long *count, int64_t cap,
+                       const unsigned long long *whitelist, unsigned long long *hit_bits,
+                       uint8_t *mask, void *stream);
 
 #ifdef __cplusplus
 }

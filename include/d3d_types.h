@@ -36,7 +36,24 @@ enum {
  *        cylinder (r,L,-); disk (r,-,-); ellipse (r0,r1,-); cone (r,h,-).
  * vert_off/vert_len: range into verts[M,3] (box: 8 world-frame vertices written
  *        by d3d_prepare; hull: world frame; mesh: local frame).
- * margin: optional per-collider Margin (colliders.py:606), NULL = none.      */
+ * margin: optional per-collider Margin (colliders.py:606), NULL = none.
+ *
+ * MeshGraph support = hill climbing over the triangle graph (mesh.py:12-139).
+ * graph_off[i] >= 0 points at the mesh's adjacency record in the int32 pool
+ * `graph` (meshes that share vertices may share the record):
+ *     g[0]          first_idx = min(triangles)                      (mesh.py:29)
+ *     g[1..6]       shortcut vertices: argmax x,y,z, argmin x,y,z   (mesh.py:44-47)
+ *     g[7..7+nv]    row pointers (nv+1 entries, relative to g): the neighbours of
+ *                   vertex v are g[g[7+v]] .. g[g[7+v+1]-1], in the order the
+ *                   reference iterates `connections[v]`             (mesh.py:49-52)
+ * graph_off == NULL or graph_off[i] < 0: arg-max over all vertices
+ * (MeshSupportFunction, mesh.py:142-191).
+ * mesh_start: optional start vertex per collider (the reference object's cached
+ *        `first_idx`, mesh.py:85); NULL or < 0 = g[0].  Every pair starts from it
+ *        and carries the vertex from one support call to the next, as a fresh
+ *        reference object does within one gjk / epa / mpr call.
+ * mesh_last: optional OUTPUT, vertex a pair ended on (written per collider; only
+ *        meaningful when a collider occurs in one pair - the scalar API).      */
 typedef struct d3d_colliders {
     int64_t n;
     const int32_t *type;     /* [n]    */
@@ -46,6 +63,10 @@ typedef struct d3d_colliders {
     const int32_t *vert_len; /* [n]    */
     const double *verts;     /* [M,3]  */
     const double *margin;    /* [n] or NULL */
+    const int32_t *graph_off;  /* [n] or NULL */
+    const int32_t *graph;      /* [G] adjacency pool or NULL */
+    const int32_t *mesh_start; /* [n] or NULL */
+    int32_t *mesh_last;        /* [n] or NULL (output) */
 } d3d_colliders;
 
 /* Per-pair status codes; 0..3 are the reference's GjkState values

@@ -69,12 +69,23 @@ def _ready(cs):
     return cs.host_struct()
 
 
-def support(cs, idx, d):
+def support(cs, idx, d, start=None, return_index=False):
+    """support_function of collider idx.  MeshGraph: `start` = cached vertex of the
+    object before the call (None: fresh object); return_index also returns the vertex the
+    climb ended on (the object's new cache, mesh.py:85)."""
     s = _ready(cs)
     out = np.zeros(3)
     d = np.ascontiguousarray(d, dtype=np.float64)
+    keep = []
+    if start is not None:
+        ms = np.full(len(cs), -1, dtype=np.int32)
+        ms[idx] = start
+        keep.append(ms)
+        s.mesh_start = ms.ctypes.data
+    last = np.full(len(cs), -1, dtype=np.int32)
+    s.mesh_last = last.ctypes.data
     lib().d3do_support(ctypes.byref(s), c_i64(int(idx)), _p(d), _p(out))
-    return out
+    return (out, int(last[idx])) if return_index else out
 
 
 def center(cs, idx):
@@ -259,3 +270,41 @@ def self_collision_masks(template, kin, pattern, q, n_threads=1):
     mask[pairs[hit, 0]] = 1
     mask[pairs[hit, 1]] = 1
     return mask.reshape(B, K), len(pairs)
+
+
+def self_collision_masks_ordered(template, kin, whitelist, q, n_threads=1):
+    """self_collision.detect (self_collision.py:22-36) replayed literally for every joint
+    configuration, candidate order included: the BVH is rebuilt by inserting the colliders
+    one at a time into the reference's incremental tree (broad_phase.py:144-151), the
+    candidates of a frame are the tree's overlaps in query order (aabb_tree.py:381-403)
+    minus its white-list, the first intersecting candidate flags both frames.
+    `whitelist` uint8[K,K]: whitelist[i, j] = frame j is white-listed for frame i."""
+    from distance3d_b200.pack import ColliderSet
+    poses = fk(kin, q, n_threads)
+    B, K = poses.shape[:2]
+    z = np.zeros(K, dtype=np.int32)
+    masks = np.zeros((B, K), dtype=np.uint8)
+    for b in range(B):
+        cs = ColliderSet(template.type, poses[b], template.param, z, z, np.zeros((0, 3)))
+        boxes = aabb(cs)
+        tree = Tree()
+        leaf_of = []
+        for k in range(K):
+            leaf_of.append(tree.filled_len)
+            tree.insert_aabbs(boxes[k:k + 1])
+        collider_of = {leaf: k for k, leaf in enumerate(leaf_of)}
+        contacts = {}
+        for f in range(K):
+            if f in contacts:
+                continue
+            cand = [collider_of[int(leaf)] for leaf, _ in tree.query(boxes[f:f + 1])]
+            contacts[f] = False
+            for g2 in cand:
+                if whitelist[f, g2]:
+                    continue
+                if f == g2 or gjk_intersection(cs, [[f, g2]])["hit"][0]:
+                    contacts[f] = True
+                    contacts[g2] = True
+                    break
+        masks[b] = [contacts[f] for f in range(K)]
+    return masks

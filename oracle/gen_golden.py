@@ -32,8 +32,9 @@ ALL = ["sphere", "ellipsoid", "capsule", "cylinder", "box", "mesh", "cone", "dis
 
 def set_arrays(cs, prefix="cs_"):
     d = {prefix + k: getattr(cs, k) for k in ("type", "pose", "param", "vert_off", "vert_len", "verts")}
-    if cs.margin is not None:
-        d[prefix + "margin"] = cs.margin
+    for k in ("margin", "graph_off", "graph", "mesh_start"):
+        if getattr(cs, k) is not None:
+            d[prefix + k] = getattr(cs, k)
     return d
 
 
@@ -58,8 +59,148 @@ def run_gjk(cols, pairs):
     return dict(dist=dist, a=a, b=b, Y=Y, status=status, iters=iters, hit=hit)
 
 
+def fresh(c):
+    """New reference object for the same shape: a MeshGraph carries hidden state (the
+    vertex its last support call ended on, mesh.py:85), so every reference call of the
+    MeshGraph fixture gets objects in their initial state and the fixture does not
+    depend on the order of the calls."""
+    from distance3d import colliders as RC
+    if isinstance(c, RC.MeshGraph):
+        return RC.MeshGraph(c.mesh2origin.copy(), c.vertices, c.triangles)
+    return c
+
+
+def meshgraph_fixture():
+    """MeshGraph: hill climbing with vertex caching (mesh.py:12-139)."""
+    from distance3d import colliders as RC
+    from distance3d_b200.mesh import build_mesh_graph
+    rsm = np.random.RandomState(99)
+    meshes = []
+    for k in range(48):  # 8 .. 200 vertices; close together so that EPA / MPR get hits
+        nv = int(rsm.choice([8, 12, 20, 30, 60, 120, 200]))
+        meshes += refbridge.random_reference_colliders(
+            rsm, 1, ["mesh"], hull_as_vertices=False, mesh=dict(n_vertices=nv, center_scale=[0.5, 1.5][k % 2]))
+    names = ["sphere", "capsule", "box", "cylinder", "ellipsoid"]
+    others = refbridge.random_reference_colliders(
+        rsm, 32, names, **{n: dict(center_scale=1.2) for n in names})
+    cols = meshes + others
+    # the adjacency record built by the product equals the reference object's tables
+    for c in meshes:
+        g = build_mesh_graph(c.vertices, c.triangles)
+        sf = c._support_function
+        assert g[0] == sf.first_idx and list(g[1:7]) == list(sf.shortcut_connections)
+        for v in range(len(c.vertices)):
+            mine = list(g[g[7 + v]:g[8 + v]])
+            assert mine == (list(sf.connections[v]) if v in sf.connections else []), v
+    cs = refbridge.to_set(cols)
+    n_pairs = 400
+    pairs = np.stack([rsm.randint(0, 48, n_pairs), rsm.randint(0, 80, n_pairs)], axis=1).astype(np.int32)
+    swap = rsm.rand(n_pairs) < 0.3  # the mesh is not always collider 1
+    pairs[swap] = pairs[swap][:, ::-1]
+    n = n_pairs
+    dist = np.zeros(n); a = np.zeros((n, 3)); b = np.zeros((n, 3)); Y = np.zeros((n, 4, 3))
+    status = np.zeros(n, dtype=np.int32); iters = np.zeros(n, dtype=np.int32)
+    hit = np.zeros(n, dtype=np.uint8)
+    mtv = np.zeros((n, 3)); esuccess = np.zeros(n, dtype=np.uint8); nfaces = np.zeros(n, dtype=np.int32)
+    estatus = np.full(n, -1, dtype=np.int32)
+    mhit = np.zeros(n, dtype=np.uint8); mhit_i = np.zeros(n, dtype=np.uint8)
+    depth = np.zeros(n); pdir = np.zeros((n, 3)); pos = np.zeros((n, 3))
+    for k, (i, j) in enumerate(pairs):
+        d, pa, pb, yy = gjk.gjk(fresh(cols[i]), fresh(cols[j]))
+        iters[k] = gjk_distance_jolt_iterations(fresh(cols[i]), fresh(cols[j]))
+        if pa is None:
+            dist[k] = MAX_FLOAT; status[k] = 3
+        else:
+            dist[k] = d; a[k] = pa; b[k] = pb; Y[k] = yy
+            status[k] = 1 if d == 0.0 else 0
+        hit[k] = gjk.gjk_intersection(fresh(cols[i]), fresh(cols[j]))
+        if status[k] == 1:
+            try:
+                m, faces, ok = epa.epa(Y[k].copy(), fresh(cols[i]), fresh(cols[j]))
+                estatus[k] = 1; mtv[k] = m; esuccess[k] = ok; nfaces[k] = len(faces)
+            except AssertionError:
+                estatus[k] = 7
+        h, dpt, dr, ps = mpr.mpr_penetration(fresh(cols[i]), fresh(cols[j]))
+        mhit[k] = h
+        mhit_i[k] = mpr.mpr_intersection(fresh(cols[i]), fresh(cols[j]))
+        if h:
+            depth[k] = dpt; pdir[k] = dr; pos[k] = ps
+    # one object, a sequence of support calls: the start vertex is carried from call to call
+    seq_dirs = rsm.randn(48, 12, 3)
+    seq_dirs[:, 5] = seq_dirs[:, 4] * (1.0 + 1e-15)  # nearly repeated direction
+    seq_pts = np.zeros((48, 12, 3)); seq_idx = np.zeros((48, 12), dtype=np.int32)
+    for m_i, c in enumerate(meshes):
+        obj = fresh(c)
+        for t in range(12):
+            seq_pts[m_i, t] = obj.support_function(np.ascontiguousarray(seq_dirs[m_i, t]))
+            seq_idx[m_i, t] = obj._support_function.first_idx
+    tri_len = np.array([len(c.triangles) for c in meshes], dtype=np.int32)
+    print("meshgraph: %d intersecting, %d epa ok, %d epa max_faces, %d mpr hits, iters mean %.1f" % (
+        (status == 1).sum(), (estatus == 1).sum(), (estatus == 7).sum(), mhit.sum(), iters.mean()))
+    np.savez_compressed(
+        os.path.join(OUT, "meshgraph.npz"), pairs=pairs, dist=dist, a=a, b=b, Y=Y, status=status,
+        iters=iters, hit=hit, epa_mtv=mtv, epa_success=esuccess, epa_n_faces=nfaces,
+        epa_status=estatus, mpr_hit=mhit, mpr_hit_intersection=mhit_i, mpr_depth=depth,
+        mpr_dir=pdir, mpr_pos=pos, seq_dirs=seq_dirs, seq_pts=seq_pts, seq_idx=seq_idx,
+        triangles=np.concatenate([np.asarray(c.triangles) for c in meshes]).astype(np.int32),
+        tri_len=tri_len, **set_arrays(cs))
+
+
+def branched_fixture():
+    """Self-collision of a branched robot with the reference's detect(): white-lists are
+    not symmetric there (urdf_utils.py:79-81 keeps one child per link)."""
+    from pytransform3d.urdf import UrdfTransformManager
+    import distance3d.broad_phase
+    from distance3d import self_collision
+    urdf_path = os.path.join(refbridge.REPO, "tests", "data", "robot_branched.urdf")
+    tm = UrdfTransformManager()
+    with open(urdf_path) as f:
+        tm.load_urdf(f.read(), mesh_path=os.path.dirname(urdf_path))
+    bvh = distance3d.broad_phase.BoundingVolumeHierarchy(tm, "robot_branched")
+    bvh.fill_tree_with_colliders(tm, make_artists=False, fill_self_collision_whitelists=True)
+    joints = ["j_shoulder_l", "j_arm_l", "j_shoulder_r", "j_arm_r", "j_head"]
+    rsq = np.random.RandomState(17)
+    q = rsq.uniform(-np.pi, np.pi, size=(300, len(joints)))
+    q[0] = 0.0
+    frames = list(bvh.colliders_.keys())
+    wl = bvh.self_collision_whitelists_
+    masks = np.zeros((len(q), len(frames)), dtype=np.uint8)
+    either = np.zeros_like(masks)   # pair tested unless BOTH sides white-list it, a hit marks both
+    anyhit = np.zeros(len(q), dtype=np.uint8)
+    for b in range(len(q)):
+        for j, name in enumerate(joints):
+            tm.set_joint(name, q[b, j])
+        bvh.update_collider_poses()
+        contacts = self_collision.detect(bvh)
+        masks[b] = [contacts[fr] for fr in frames]
+        anyhit[b] = self_collision.detect_any(bvh)
+        for i, fi in enumerate(frames):
+            for j2 in range(i + 1, len(frames)):
+                fj = frames[j2]
+                if fj in wl[fi] and fi in wl[fj]:
+                    continue
+                ci, cj = bvh.colliders_[fi], bvh.colliders_[fj]
+                a1, a2 = ci.aabb(), cj.aabb()
+                if np.all((a1[:, 0] <= a2[:, 1]) & (a1[:, 1] >= a2[:, 0])) and gjk.gjk_intersection(ci, cj):
+                    either[b, i] = either[b, j2] = 1
+    asym = [(fi, fj) for fi in frames for fj in frames if fj in wl[fi] and fi not in wl[fj]]
+    print("branched: %d frames, %d asymmetric white-list entries, colliding configs %d/%d, "
+          "detect() vs pairwise rule: %d differing mask bits" % (
+              len(frames), len(asym), (masks.sum(1) > 0).sum(), len(q), (masks != either).sum()))
+    np.savez_compressed(os.path.join(OUT, "self_collision_branched.npz"), q=q, mask=masks,
+                        any=anyhit, frames=np.array(frames), joints=np.array(joints),
+                        wl_keys=np.array(frames),
+                        wl=np.array([[int(fj in wl[fi]) for fj in frames] for fi in frames], dtype=np.uint8))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-meshgraph" in sys.argv:
+        meshgraph_fixture()
+        return
+    if "--only-branched" in sys.argv:
+        branched_fixture()
+        return
     rs = np.random.RandomState(2024)
 
     # ---- GJK on all 9 collider types (+ Margin) ---------------------------
@@ -188,16 +329,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "self_collision.npz"), q=q, mask=masks, poses=poses,
                         frames=np.array(frames))
 
-    # ---- MeshGraph (hill climbing with vertex caching in the reference) -----
-    rsm = np.random.RandomState(99)
-    meshes = refbridge.random_reference_colliders(rsm, 40, ["mesh"], hull_as_vertices=False,
-                                                  mesh=dict(n_vertices=30))
-    others = refbridge.random_reference_colliders(rsm, 40, ["sphere", "capsule", "box", "cylinder"])
-    cols5 = meshes + others
-    cs5 = refbridge.to_set(cols5)
-    pairs5 = np.stack([rsm.randint(0, 40, 300), rsm.randint(0, 80, 300)], axis=1).astype(np.int32)
-    g5 = run_gjk(cols5, pairs5)
-    np.savez_compressed(os.path.join(OUT, "meshgraph.npz"), pairs=pairs5, **set_arrays(cs5), **g5)
+    meshgraph_fixture()
+    branched_fixture()
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -7,7 +7,11 @@
 #include "d3d_oracle.h"
 #include "vec.h"
 
-v3 d3do_support_v(const d3d_colliders *c, int64_t i, v3 d);
+v3 d3do_support_s(const d3d_colliders *c, int64_t i, v3 d, int32_t *cur);
+void d3do_pair_begin(const d3d_colliders *c, int64_t ia, int64_t ib, int32_t *cur);
+void d3do_pair_end(const d3d_colliders *c, int64_t ia, int64_t ib, const int32_t *cur);
+/* MeshGraph vertex of collider A / B of the pair this thread is working on */
+static _Thread_local int32_t mesh_cur[2];
 
 typedef struct { v3 v[3]; v3 n; } face_t;
 typedef struct { v3 a, b; } edge_t;
@@ -46,7 +50,7 @@ static void epa_one(const d3d_colliders *c, int64_t ia, int64_t ib, const double
             if (i == 0 || d < min_dist) { min_dist = d; closest = i; }
         }
         v3 sd = faces[closest].n;
-        v3 new_point = vsub(d3do_support_v(c, ia, sd), d3do_support_v(c, ib, vneg(sd)));
+        v3 new_point = vsub(d3do_support_s(c, ia, sd, &mesh_cur[0]), d3do_support_s(c, ib, vneg(sd), &mesh_cur[1]));
         double proj = vdot(new_point, sd);
         if (proj - min_dist < epsilon) { /* epa.py:67-70 */
             vstore(out_mtv, vscale(faces[closest].n, proj));
@@ -116,9 +120,11 @@ void d3do_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, con
         edge_t *loose = malloc(sizeof(edge_t) * (size_t)(max_loose_edges + 1));
 #pragma omp for schedule(dynamic, 64)
         for (int64_t k = 0; k < n_pairs; ++k) {
+            d3do_pair_begin(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
             epa_one(c, pairs[2 * k], pairs[2 * k + 1], Y + 12 * k, max_iter, max_loose_edges,
                     max_faces, epsilon, faces, loose, out_mtv + 3 * k, out_success + k,
                     out_nfaces + k, out_iters + k, out_status + k);
+            d3do_pair_end(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
             if (out_faces) {
                 double *o = out_faces + (size_t)k * max_faces * 12;
                 for (int i = 0; i < max_faces; ++i) {

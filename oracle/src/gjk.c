@@ -4,7 +4,11 @@
 #include "d3d_oracle.h"
 #include "vec.h"
 
-v3 d3do_support_v(const d3d_colliders *c, int64_t i, v3 d);
+v3 d3do_support_s(const d3d_colliders *c, int64_t i, v3 d, int32_t *cur);
+void d3do_pair_begin(const d3d_colliders *c, int64_t ia, int64_t ib, int32_t *cur);
+void d3do_pair_end(const d3d_colliders *c, int64_t ia, int64_t ib, const int32_t *cur);
+/* MeshGraph vertex of collider A / B of the pair this thread is working on */
+static _Thread_local int32_t mesh_cur[2];
 
 #define EPS D3D_EPS
 #define EPS_SQR (D3D_EPS * D3D_EPS)
@@ -251,8 +255,8 @@ static void gjk_distance_one(const d3d_colliders *c, int64_t ia, int64_t ib, dou
     while (state == D3D_UNKNOWN) {
         if (iters >= D3D_GJK_ITER_CAP) { state = D3D_ITER_CAP; break; }
         ++iters;
-        v3 p = d3do_support_v(c, ia, sd);
-        v3 q = d3do_support_v(c, ib, vneg(sd));
+        v3 p = d3do_support_s(c, ia, sd, &mesh_cur[0]);
+        v3 q = d3do_support_s(c, ib, vneg(sd), &mesh_cur[1]);
         /* _distance_loop */
         v3 w = vsub(p, q);
         double dot = vdot(sd, w);
@@ -322,10 +326,13 @@ void d3do_gjk_distance(const d3d_colliders *c, const int32_t *pairs, int64_t n_p
                        int n_threads) {
     if (n_threads < 1) n_threads = 1;
 #pragma omp parallel for schedule(dynamic, 256) num_threads(n_threads)
-    for (int64_t k = 0; k < n_pairs; ++k)
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        d3do_pair_begin(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
         gjk_distance_one(c, pairs[2 * k], pairs[2 * k + 1], tolerance, max_distance_squared,
                          sanity_check, out_dist + k, out_a + 3 * k, out_b + 3 * k, out_Y + 12 * k,
                          out_npoints + k, out_iters + k, out_status + k);
+        d3do_pair_end(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
+    }
 }
 
 /* one pair of _gjk_jolt.py:29-135 */
@@ -341,8 +348,8 @@ static void gjk_intersection_one(const d3d_colliders *c, int64_t ia, int64_t ib,
     while (state == D3D_UNKNOWN) {
         if (iters >= D3D_GJK_ITER_CAP) { state = D3D_ITER_CAP; break; }
         ++iters;
-        v3 p = d3do_support_v(c, ia, sd);
-        v3 q = d3do_support_v(c, ib, vneg(sd));
+        v3 p = d3do_support_s(c, ia, sd, &mesh_cur[0]);
+        v3 q = d3do_support_s(c, ib, vneg(sd), &mesh_cur[1]);
         v3 w = vsub(p, q);
         if (vdot(sd, w) < -EPS) { state = D3D_NO_INTERSECTION; break; }
         Y[n_points++] = w;
@@ -372,9 +379,12 @@ void d3do_gjk_intersection(const d3d_colliders *c, const int32_t *pairs, int64_t
                            int32_t *out_status, int n_threads) {
     if (n_threads < 1) n_threads = 1;
 #pragma omp parallel for schedule(dynamic, 256) num_threads(n_threads)
-    for (int64_t k = 0; k < n_pairs; ++k)
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        d3do_pair_begin(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
         gjk_intersection_one(c, pairs[2 * k], pairs[2 * k + 1], tolerance, out_hit + k,
                              out_iters + k, out_status + k);
+        d3do_pair_end(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
+    }
 }
 
 int d3do_max_threads(void) { return omp_get_max_threads(); }

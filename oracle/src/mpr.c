@@ -5,7 +5,11 @@
 #include "d3d_oracle.h"
 #include "vec.h"
 
-v3 d3do_support_v(const d3d_colliders *c, int64_t i, v3 d);
+v3 d3do_support_s(const d3d_colliders *c, int64_t i, v3 d, int32_t *cur);
+void d3do_pair_begin(const d3d_colliders *c, int64_t ia, int64_t ib, int32_t *cur);
+void d3do_pair_end(const d3d_colliders *c, int64_t ia, int64_t ib, const int32_t *cur);
+/* MeshGraph vertex of collider A / B of the pair this thread is working on */
+static _Thread_local int32_t mesh_cur[2];
 v3 d3do_center_v(const d3d_colliders *c, int64_t i);
 
 #define EPS D3D_EPS
@@ -17,8 +21,8 @@ enum { ORIGIN_OUTSIDE = -1, PORTAL_BUILT = 0, ORIGIN_ON_V1 = 1, ORIGIN_ON_SEGMEN
 /* minkowski.py:23-55 */
 static void mink_support(const d3d_colliders *c, int64_t ia, int64_t ib, v3 d, v3 *v, v3 *v1,
                          v3 *v2) {
-    *v1 = d3do_support_v(c, ia, d);
-    *v2 = d3do_support_v(c, ib, vneg(d));
+    *v1 = d3do_support_s(c, ia, d, &mesh_cur[0]);
+    *v2 = d3do_support_s(c, ib, vneg(d), &mesh_cur[1]);
     *v = vsub(*v1, *v2);
 }
 
@@ -234,7 +238,10 @@ void d3do_mpr(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, dou
               double *out_dir, double *out_pos, int32_t *out_status, int n_threads) {
     if (n_threads < 1) n_threads = 1;
 #pragma omp parallel for schedule(dynamic, 256) num_threads(n_threads)
-    for (int64_t k = 0; k < n_pairs; ++k)
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        d3do_pair_begin(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
         mpr_one(c, pairs[2 * k], pairs[2 * k + 1], tol, max_iterations, want_penetration,
                 out_hit + k, out_depth + k, out_dir + 3 * k, out_pos + 3 * k, out_status + k);
+        d3do_pair_end(c, pairs[2 * k], pairs[2 * k + 1], mesh_cur);
+    }
 }

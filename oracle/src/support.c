@@ -53,7 +53,50 @@ static int64_t argmax_dot(const double *V, int64_t n, v3 d) {
     return best;
 }
 
-static v3 support_unmargined(const d3d_colliders *c, int64_t i, v3 d) {
+/* mesh.py:90-139 hill_climb_mesh_extreme; g = adjacency record (include/d3d_types.h).
+ * `search_direction.dot(vertex_diff)` is a BLAS ddot. */
+static int64_t hill_climb(const double *V, const int32_t *g, v3 l, int64_t start) {
+    const double eps = 10.0 * D3D_EPS; /* PROJECTION_LENGTH_EPSILON, mesh.py:9 */
+    int64_t best = start;
+    for (int k = 1; k <= 6; ++k) { /* shortcut_connections, mesh.py:44-47, 121-127 */
+        int64_t ci = g[k];
+        if (vdot(l, vsub(vload(V + 3 * ci), vload(V + 3 * best))) > eps) best = ci;
+    }
+    int converged = 0;
+    while (!converged) { /* mesh.py:129-137 */
+        converged = 1;
+        int32_t lo = g[7 + best], hi = g[8 + best]; /* the list of the vertex the round starts on */
+        for (int32_t j = lo; j < hi; ++j) {
+            int64_t ci = g[j];
+            if (vdot(l, vsub(vload(V + 3 * ci), vload(V + 3 * best))) > eps) {
+                best = ci;
+                converged = 0;
+            }
+        }
+    }
+    return best;
+}
+
+/* first_idx of a fresh reference object (mesh.py:29) unless the caller supplies one */
+int32_t d3do_mesh_start(const d3d_colliders *c, int64_t i) {
+    if (c->type[i] != D3D_MESH) return 0;
+    if (c->mesh_start != 0 && c->mesh_start[i] >= 0) return c->mesh_start[i];
+    if (c->graph_off != 0 && c->graph_off[i] >= 0) return c->graph[c->graph_off[i]];
+    return 0;
+}
+
+/* per-pair MeshGraph state: cur[0] for collider ia, cur[1] for ib (see d3d_types.h) */
+void d3do_pair_begin(const d3d_colliders *c, int64_t ia, int64_t ib, int32_t *cur) {
+    cur[0] = d3do_mesh_start(c, ia);
+    cur[1] = d3do_mesh_start(c, ib);
+}
+void d3do_pair_end(const d3d_colliders *c, int64_t ia, int64_t ib, const int32_t *cur) {
+    if (c->mesh_last == 0) return;
+    if (c->type[ia] == D3D_MESH) c->mesh_last[ia] = cur[0];
+    if (c->type[ib] == D3D_MESH) c->mesh_last[ib] = cur[1];
+}
+
+static v3 support_unmargined(const d3d_colliders *c, int64_t i, v3 d, int32_t *cur) {
     const double *T = c->pose + 16 * i;
     const double *p = c->param + 3 * i;
     switch (c->type[i]) {
@@ -93,10 +136,17 @@ static v3 support_unmargined(const d3d_colliders *c, int64_t i, v3 d) {
         const double *V = c->verts + 3 * (int64_t)c->vert_off[i];
         return vload(V + 3 * argmax_dot(V, c->vert_len[i], d));
     }
-    case D3D_MESH: { /* mesh.py:182-189 (brute-force form; see DESIGN.md on hill climbing) */
+    case D3D_MESH: { /* mesh.py:79-87 (hill climbing); without a graph mesh.py:182-189 */
         const double *V = c->verts + 3 * (int64_t)c->vert_off[i];
         v3 l = rot_t_apply(T, d);
-        return transform_point(T, vload(V + 3 * argmax_dot(V, c->vert_len[i], l)));
+        int64_t idx;
+        if (c->graph_off != 0 && c->graph_off[i] >= 0) {
+            idx = hill_climb(V, c->graph + c->graph_off[i], l, *cur);
+            *cur = (int32_t)idx; /* vertex caching, mesh.py:85 */
+        } else {
+            idx = argmax_dot(V, c->vert_len[i], l);
+        }
+        return transform_point(T, vload(V + 3 * idx));
     }
     case D3D_DISK: { /* geometry.py:375-383 */
         v3 center = V3(T[3], T[7], T[11]);
@@ -141,15 +191,17 @@ static v3 support_unmargined(const d3d_colliders *c, int64_t i, v3 d) {
     return V3(0, 0, 0);
 }
 
-v3 d3do_support_v(const d3d_colliders *c, int64_t i, v3 d) {
-    v3 s = support_unmargined(c, i, d);
+v3 d3do_support_s(const d3d_colliders *c, int64_t i, v3 d, int32_t *cur) {
+    v3 s = support_unmargined(c, i, d, cur);
     if (c->margin != 0 && c->margin[i] != 0.0) /* colliders.py:629-631 */
         s = vadd(s, vscale(vnormalized(d), c->margin[i]));
     return s;
 }
 
 void d3do_support(const d3d_colliders *c, int64_t idx, const double *d, double *out) {
-    vstore(out, d3do_support_v(c, idx, vload(d)));
+    int32_t cur = d3do_mesh_start(c, idx);
+    vstore(out, d3do_support_s(c, idx, vload(d), &cur));
+    if (c->mesh_last != 0 && c->type[idx] == D3D_MESH) c->mesh_last[idx] = cur;
 }
 
 /* colliders.py center() */

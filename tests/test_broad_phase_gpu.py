@@ -36,12 +36,12 @@ def test_golden_capsules_tree_pairs():
     tree = aabb_tree.AabbTree()
     tree.insert_aabbs(_lib.aabb(cs))
     ok, i1, i2, pairs = tree.overlaps_aabb_tree(tree)
-    assert ok
+    assert ok and isinstance(pairs, list) and isinstance(pairs[0], tuple)   # aabb_tree.py:374-376
     assert as_set(pairs) == as_set(g["tree_pairs"])          # the real reference's pair set
     assert len(pairs) == len(g["tree_pairs"])                 # no duplicates
     np.testing.assert_array_equal(i1, np.unique(g["tree_pairs"][:, 0]))
     _, _, bp = aabb_tree.all_aabbs_overlap(g["aabb"][:300], g["aabb"][300:700])
-    np.testing.assert_array_equal(bp, g["brute_pairs"])        # same row-major list
+    assert isinstance(bp, list) and bp == list(map(tuple, g["brute_pairs"].tolist()))  # same row-major list
 
 
 @pytest.mark.parametrize("n,scale", [(1, 1.0), (2, 1.0), (3, 0.1), (257, 1.0), (5000, 3.0), (60000, 8.0)])

@@ -82,3 +82,24 @@ def test_scalar_epa_known_answer():
     # moving collider 2 by mtv (plus a little) separates the shapes
     c2b = C.ConvexHullVertices(EPA_VERTICES2 + mtv * (1.0 + 1e-3))
     assert gjk.gjk(c1, c2b)[0] > 0.0
+
+
+def test_undefined_simplices_are_reported_not_run():
+    """GJK may end with fewer than 4 simplex points; the reference's epa() then reads rows of an
+    np.empty array (undefined).  With `n_points` those pairs get status 8 and the rest is
+    unchanged."""
+    import torch
+    rs = np.random.RandomState(5)
+    cs = d3random.random_collider_set(rs, 800, center_scale=0.3)
+    pairs = d3random.random_pairs(rs, len(cs), 6000)
+    g = gjk.gjk_distance_batch(cs, pairs)
+    hits = torch.nonzero(g.dist == 0.0).flatten()
+    sub = pairs[hits.cpu().numpy()]
+    npts = g.n_points[hits]
+    assert int((npts < 4).sum()) > 0 and int((npts == 4).sum()) > 100
+    res = epa.epa_batch(cs, sub, g.simplex[hits], n_points=npts).cpu()
+    bad = npts.cpu().numpy() != 4
+    assert np.all(res["status"][bad] == gjk.STATUS_EPA_BAD_SIMPLEX)
+    assert not res["mtv"][bad].any() and not res["success"][bad].any()
+    full = epa.epa_batch(cs, sub[~bad], g.simplex[hits][torch.from_numpy(~bad).cuda()]).cpu()
+    assert np.array_equal(res["mtv"][~bad], full["mtv"]) and np.array_equal(res["status"][~bad], full["status"])

@@ -150,19 +150,96 @@ def test_scalar_api_matches_reference_semantics():
     np.testing.assert_allclose(box.support_function(np.array([1.0, 1.0, 1.0])), [0.5, 0.5, 0.5])
 
 
-def test_meshgraph_brute_force_support_vs_reference_hill_climbing():
-    """MeshGraph: the reference climbs the triangle graph from a cached vertex
-    (mesh.py:12-139); the GPU takes the arg-max over all vertices.  Same point except on
-    10*EPS plateaus, so results agree to the stated tolerance."""
+def test_meshgraph_hill_climbing_bit_exact_vs_reference_outputs():
+    """MeshGraph support = hill climbing over the triangle graph from the vertex the
+    previous support call ended on (mesh.py:12-139).  The fixture holds the outputs of the
+    real reference with a fresh object per call; everything is bit-exact (contract: 1e-9)."""
+    from distance3d_b200 import epa as d3epa, mpr as d3mpr
     cs, g = load_golden("meshgraph.npz")
     res = gjk.gjk_distance_batch(cs, g["pairs"]).cpu()
     ok = g["status"] <= 1
-    assert np.max(np.abs(res["dist"][ok] - g["dist"][ok])) < TOL
-    assert np.max(np.abs(res["closest_a"][ok] - g["a"][ok])) < 1e-7
-    hit, _, _ = gjk.gjk_intersection_batch(cs, g["pairs"])
-    near = g["dist"] < 1e-12
-    assert np.array_equal(hit.cpu().numpy()[ok & ~near], g["hit"][ok & ~near])
-    compare_distance(cs, g["pairs"], exact_types=EXACT)   # bit-exact against the oracle
+    assert np.max(np.abs(res["dist"][ok] - g["dist"][ok])) < TOL        # the stated tolerance
+    assert np.max(np.abs(res["closest_a"][ok] - g["a"][ok])) < TOL
+    assert np.max(np.abs(res["closest_b"][ok] - g["b"][ok])) < TOL
+    assert np.array_equal(res["status"], g["status"])
+    assert np.array_equal(res["dist"][ok], g["dist"][ok])               # and in fact bit-exact
+    assert np.array_equal(res["closest_a"][ok], g["a"][ok])
+    assert np.array_equal(res["closest_b"][ok], g["b"][ok])
+    assert np.array_equal(res["iters"], g["iters"])
+    for k in np.where(ok)[0]:
+        n = res["n_points"][k]
+        assert np.array_equal(res["simplex"][k, :n], g["Y"][k, :n])
+    hit, it, _ = gjk.gjk_intersection_batch(cs, g["pairs"], want_iters=True)
+    assert np.array_equal(hit.cpu().numpy(), g["hit"])
+    compare_distance(cs, g["pairs"], exact_types=EXACT)
+    # EPA and MPR climb the same graph
+    sel = np.where(g["epa_status"] >= 0)[0]
+    e = d3epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel]).cpu()
+    asserted = g["epa_status"][sel] == 7
+    assert np.array_equal(e["status"] == 7, asserted)
+    assert np.array_equal(e["mtv"][~asserted], g["epa_mtv"][sel][~asserted])
+    assert np.array_equal(e["success"][~asserted], g["epa_success"][sel][~asserted])
+    assert np.array_equal(e["n_faces"][~asserted], g["epa_n_faces"][sel][~asserted])
+    m = d3mpr.mpr_batch(cs, g["pairs"], penetration=True)
+    mh = m["hit"].cpu().numpy()
+    assert np.array_equal(mh, g["mpr_hit"])
+    h = mh.astype(bool)
+    assert np.array_equal(m["depth"].cpu().numpy()[h], g["mpr_depth"][h])
+    assert np.array_equal(m["dir"].cpu().numpy()[h], g["mpr_dir"][h])
+    assert np.array_equal(m["pos"].cpu().numpy()[h], g["mpr_pos"][h])
+    mi = d3mpr.mpr_batch(cs, g["pairs"], penetration=False)
+    assert np.array_equal(mi["hit"].cpu().numpy(), g["mpr_hit_intersection"])
+
+
+def test_meshgraph_object_caches_its_vertex_across_scalar_calls():
+    """colliders.MeshGraph keeps the vertex of its last support call like the reference
+    object (mesh.py:85): a sequence of support_function calls on ONE object reproduces the
+    reference's sequence of points and cached indices."""
+    from distance3d_b200 import colliders as C, mesh as d3mesh
+    cs, g = load_golden("meshgraph.npz")
+    t0 = 0
+    for m in range(12):
+        nt = g["tri_len"][m]
+        tri = g["triangles"][t0:t0 + nt]
+        o, l = cs.vert_off[m], cs.vert_len[m]
+        obj = C.MeshGraph(cs.pose[m].copy(), cs.verts[o:o + l].copy(), tri)
+        sf = d3mesh.MeshHillClimbingSupportFunction(cs.pose[m].copy(), cs.verts[o:o + l].copy(), tri)
+        for t in range(g["seq_dirs"].shape[1]):
+            assert np.array_equal(obj.support_function(g["seq_dirs"][m, t]), g["seq_pts"][m, t])
+            assert obj._first_idx == g["seq_idx"][m, t]
+            idx, pt = sf(g["seq_dirs"][m, t])
+            assert idx == g["seq_idx"][m, t] and np.array_equal(pt, g["seq_pts"][m, t])
+        t0 += nt
+    t0 = sum(g["tri_len"][:12])
+    # gjk() on objects: first call = fresh objects = the fixture; the second call starts from
+    # the cached vertices and still agrees to the contract tolerance
+    k = int(np.where((cs.type[g["pairs"][:, 0]] == 6) & (cs.type[g["pairs"][:, 1]] == 6)
+                     & (g["status"] == 0))[0][0])
+    objs = []
+    for i in g["pairs"][k]:
+        t0 = int(np.sum(g["tri_len"][:i]))
+        o, l = cs.vert_off[i], cs.vert_len[i]
+        objs.append(C.MeshGraph(cs.pose[i].copy(), cs.verts[o:o + l].copy(),
+                                g["triangles"][t0:t0 + g["tri_len"][i]]))
+    d, a, b, _ = gjk.gjk(*objs)
+    assert d == g["dist"][k] and np.array_equal(a, g["a"][k]) and np.array_equal(b, g["b"][k])
+    assert objs[0]._first_idx is not None and objs[1]._first_idx is not None
+    d2, a2, b2, _ = gjk.gjk(*objs)
+    assert abs(d2 - d) < TOL and np.max(np.abs(a2 - a)) < 1e-6
+
+
+def test_meshgraph_random_batches_thread_and_warp_kernels():
+    """Random MeshGraph colliders (shared meshes, 8-200 vertices, so both the thread and the
+    warp kernel climb) against the oracle, bit-exact; arg-max fallback without a graph."""
+    rs = np.random.RandomState(21)
+    cs = d3random.random_meshgraph_set(rs, 40, 400, 200, hull_vertices=(8, 200), center_scale=1.2)
+    pairs = d3random.random_pairs(rs, len(cs), 20000)
+    res, ref = compare_distance(cs, pairs, exact_types=EXACT)
+    assert 0.1 < np.mean(ref["dist"] == 0.0) < 0.9
+    hit, _, _ = gjk.gjk_intersection_batch(cs, pairs)
+    assert np.array_equal(hit.cpu().numpy(), O.gjk_intersection(cs, pairs, n_threads=O.max_threads())["hit"])
+    nog = P.ColliderSet(cs.type, cs.pose, cs.param, cs.vert_off, cs.vert_len, cs.verts)
+    compare_distance(nog, pairs[:4000], exact_types=EXACT)
 
 
 def test_streamed_host_pipeline_equals_batch_call():

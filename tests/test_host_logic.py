@@ -156,7 +156,7 @@ def test_c_abi_argument_checks_without_a_gpu():
     # empty batches are a no-op
     assert lib.d3d_gjk_distance(None, None, i64(0), dbl(1e-10), dbl(1e5), dbl(1e-8), None, None, None,
                                 None, None, None, None, None, ctypes.c_size_t(0), None) == 0
-    assert lib.d3d_epa(None, None, i64(0), None, 64, 32, 64, dbl(1e-8), None, None, None, None, None,
+    assert lib.d3d_epa(None, None, i64(0), None, None, 64, 32, 64, dbl(1e-8), None, None, None, None, None,
                        None, None, ctypes.c_size_t(0), None) == 0
     # null arguments / bad limits
     assert lib.d3d_gjk_distance(None, None, i64(5), dbl(1e-10), dbl(1e5), dbl(1e-8), None, None, None,
@@ -165,7 +165,7 @@ def test_c_abi_argument_checks_without_a_gpu():
     cs = pack.pack_colliders([C.Sphere(np.zeros(3), 1.0)]).host_struct()
     dummy = (ctypes.c_double * 64)()
     pairs = (ctypes.c_int32 * 2)(0, 0)
-    rc = lib.d3d_epa(ctypes.byref(cs), pairs, i64(1), dummy, 64, 32, 65, dbl(1e-8), dummy,
+    rc = lib.d3d_epa(ctypes.byref(cs), pairs, i64(1), dummy, None, 64, 32, 65, dbl(1e-8), dummy,
                      ctypes.cast(dummy, vp), None, None, None, None, ctypes.cast(dummy, vp),
                      ctypes.c_size_t(512), None)
     assert rc == -1 and b"max_faces" in lib.d3d_last_error_string()

@@ -123,10 +123,94 @@ def test_self_collision_masks_equal_reference_detect():
     tm.add_transform("robot_arm", "origin", np.eye(4))
     frames = [str(f) for f in g["frames"]]
     template = pack.pack_colliders([C.Cylinder(np.eye(4), o.radius, o.length) for o in tm.collision_objects])
-    pattern = _candidate_pattern(frames, self_collision_whitelists(tm))
+    pattern, wl, symmetric = _candidate_pattern(frames, self_collision_whitelists(tm))
+    assert symmetric and len(pattern) == 17
     kin = tm.compile_kinematics(frames, "origin")
     poses = O.fk(kin, g["q"])
     assert np.max(np.abs(poses - g["poses"])) < 1e-14
     masks, n_cand = O.self_collision_masks(template, kin, pattern, g["q"])
     np.testing.assert_array_equal(masks, g["mask"])
     assert n_cand > 100
+    wl_matrix = (wl[:, None] >> np.arange(len(frames), dtype=np.uint64)[None, :]) & np.uint64(1)
+    ordered = O.self_collision_masks_ordered(template, kin, wl_matrix, g["q"][:40])
+    np.testing.assert_array_equal(ordered, g["mask"][:40])  # order cannot matter for a chain
+
+
+def _branched_robot():
+    import os
+    from distance3d_b200 import colliders as C, pack
+    from distance3d_b200.urdf import UrdfTransformManager, Cylinder
+    from util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "self_collision_branched.npz"))
+    data = os.path.join(os.path.dirname(GOLDEN), "data")
+    tm = UrdfTransformManager()
+    with open(os.path.join(data, "robot_branched.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=data)
+    tm.add_transform("robot_branched", "origin", np.eye(4))
+    template = pack.pack_colliders([
+        C.Cylinder(np.eye(4), o.radius, o.length) if isinstance(o, Cylinder)
+        else C.Sphere(np.zeros(3), o.radius) for o in tm.collision_objects])
+    return g, tm, template
+
+
+def test_branched_robot_whitelists_and_ordered_detect_equal_reference():
+    """A link with several children white-lists only the last one (urdf_utils.py:79-81): the
+    white-lists are asymmetric and the reference's detect() depends on the order of its
+    AABB-tree candidates.  The fixture holds the reference's white-lists and masks."""
+    from distance3d_b200.urdf_utils import self_collision_whitelists
+    from distance3d_b200.self_collision import _candidate_pattern
+    g, tm, template = _branched_robot()
+    frames = [str(f) for f in g["frames"]]
+    assert [o.frame for o in tm.collision_objects] == frames
+    wl = self_collision_whitelists(tm)
+    wl_matrix = np.array([[int(fj in wl[fi]) for fj in frames] for fi in frames], dtype=np.uint8)
+    np.testing.assert_array_equal(wl_matrix, g["wl"])
+    pattern, bits, symmetric = _candidate_pattern(frames, wl)
+    assert not symmetric
+    assert (0, 1) in map(tuple, pattern)  # torso vs left shoulder: white-listed one way only
+    kin = tm.compile_kinematics(frames, "origin")
+    assert list(kin["joint_names"]) == [str(j) for j in g["joints"]]
+    masks = O.self_collision_masks_ordered(template, kin, wl_matrix, g["q"])
+    np.testing.assert_array_equal(masks, g["mask"])
+    np.testing.assert_array_equal(masks.any(axis=1), g["any"].astype(bool))
+
+
+def test_meshgraph_hill_climbing_bit_exact():
+    """MeshGraph support = hill climbing from a cached vertex (mesh.py:12-139).  The fixture
+    was generated with a fresh reference object per call, so it is order independent."""
+    cs, g = load_golden("meshgraph.npz")
+    assert cs.graph_off is not None and (cs.graph_off[cs.type == 6] >= 0).all()
+    # the adjacency records of the fixture are what build_mesh_graph makes of the triangles
+    from distance3d_b200.mesh import build_mesh_graph
+    t0 = 0
+    for m, nt in enumerate(g["tri_len"]):
+        tri = g["triangles"][t0:t0 + nt]
+        t0 += nt
+        o, l = cs.vert_off[m], cs.vert_len[m]
+        rec = build_mesh_graph(cs.verts[o:o + l], tri)
+        np.testing.assert_array_equal(rec, cs.graph[cs.graph_off[m]:cs.graph_off[m] + len(rec)])
+    res = _check_gjk(cs, g)
+    assert (res["dist"] == 0.0).sum() > 100 and (res["dist"] > 0.0).sum() > 100
+    # EPA
+    sel = np.where(g["epa_status"] >= 0)[0]
+    e = O.epa(cs, g["pairs"][sel], g["Y"][sel])
+    asserted = g["epa_status"][sel] == 7
+    np.testing.assert_array_equal(e["status"] == 7, asserted)
+    np.testing.assert_array_equal(e["mtv"][~asserted], g["epa_mtv"][sel][~asserted])
+    np.testing.assert_array_equal(e["success"][~asserted], g["epa_success"][sel][~asserted])
+    np.testing.assert_array_equal(e["n_faces"][~asserted], g["epa_n_faces"][sel][~asserted])
+    # MPR
+    m = O.mpr(cs, g["pairs"], penetration=True)
+    np.testing.assert_array_equal(m["hit"], g["mpr_hit"])
+    h = m["hit"].astype(bool)
+    np.testing.assert_array_equal(m["depth"][h], g["mpr_depth"][h])
+    np.testing.assert_array_equal(m["dir"][h], g["mpr_dir"][h])
+    np.testing.assert_array_equal(m["pos"][h], g["mpr_pos"][h])
+    np.testing.assert_array_equal(O.mpr(cs, g["pairs"], penetration=False)["hit"], g["mpr_hit_intersection"])
+    # one object, consecutive support calls: the vertex is carried from call to call
+    for mi in range(len(g["seq_dirs"])):
+        start = None
+        for t in range(g["seq_dirs"].shape[1]):
+            pt, start = O.support(cs, mi, g["seq_dirs"][mi, t], start=start, return_index=True)
+            np.testing.assert_array_equal(pt, g["seq_pts"][mi, t])
+            assert start == g["seq_idx"][mi, t]

@@ -65,6 +65,32 @@ def test_batched_fk_and_contact_masks_vs_reference_outputs():
     assert np.array_equal(mask2.cpu().numpy(), np.tile(g["mask"], (3, 1)))
 
 
+def test_branched_robot_asymmetric_whitelists_equal_reference_detect():
+    """Torso with two arms and a head: the reference's white-lists are asymmetric there and its
+    detect() result depends on the candidate order of its AABB tree; the device replays that
+    order (d3d_detect_ordered).  Fixture: reference detect() over 300 joint configurations."""
+    g = np.load(os.path.join(GOLDEN, "self_collision_branched.npz"))
+    tm = UrdfTransformManager()
+    with open(os.path.join(DATA, "robot_branched.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=DATA)
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "robot_branched")
+    bvh.fill_tree_with_colliders(tm, make_artists=False, fill_self_collision_whitelists=True)
+    model = self_collision.RobotModel(tm, bvh)
+    assert model.frames == [str(f) for f in g["frames"]] and not model.symmetric
+    assert list(model.joint_names) == [str(j) for j in g["joints"]]
+    mask, _ = model.detect_batch(g["q"])
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    mask2, _ = model.detect_batch(np.tile(g["q"], (2, 1)), chunk=128)
+    assert np.array_equal(mask2.cpu().numpy(), np.tile(g["mask"], (2, 1)))
+    for b in (0, 5, 17, 123):  # scalar API on the same configurations
+        for name, v in zip(model.joint_names, g["q"][b]):
+            tm.set_joint(name, v)
+        bvh.update_collider_poses()
+        contacts = self_collision.detect(bvh)
+        assert [int(contacts[f]) for f in model.frames] == list(g["mask"][b])
+        assert self_collision.detect_any(bvh) == bool(g["any"][b])
+
+
 def test_bvh_from_colliders_translation_invariance():
     # distance3d/test/test_broad_phase.py:32-101
     from distance3d_b200 import random as d3random
