@@ -144,6 +144,37 @@ D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, r
     return o;
 }
 
+// Warp-per-pair kernels: ONE record per warp in shared memory (STRIDE = 1).  Every lane reads
+// the collider (same addresses, one broadcast transaction) and keeps type / nv / V in
+// registers; lane 0 stores the record.  The caller synchronises the warp before the first use.
+D3D_DEV ColliderSmem<1> stage_collider_warp(const d3d_colliders &c, int64_t i, real *base, int lane) {
+    ColliderSmem<1> o;
+    o.type = __ldg(c.type + i);
+    o.nv = __ldg(c.vert_len + i);
+    o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
+    o.base = base;
+    o.gpool = c.graph;
+    const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
+    const double *p = c.param + 3 * i;
+    if (lane < 6) {
+        double2 a = __ldg(T + lane);
+        base[2 * lane] = a.x;
+        base[2 * lane + 1] = a.y;
+    } else if (lane < 9) {
+        base[12 + (lane - 6)] = __ldg(p + (lane - 6));
+    } else if (lane == 9) {
+        base[15] = c.margin ? __ldg(c.margin + i) : R(0.0);
+    }
+    __syncwarp();
+    if (o.type == D3D_MESH && lane == 0) {
+        int off, start;
+        mesh_graph_of(c, i, off, start);
+        base[12] = (real)start;
+        base[13] = (real)off;
+    }
+    return o;
+}
+
 // np.dot(pose[:3,:3].T, d)  (dgemv convention)
 template <class C>
 D3D_DEV v3 rot_t(const C &c, v3 d) {
@@ -391,8 +422,18 @@ D3D_DEV v3 support(const C &c, v3 d, int lane) {
     return s;
 }
 
+// One shared out-of-line copy of the ten-way support switch for a kernel whose collider records
+// live in shared memory (GJK thread / warp kernels, EPA): both colliders of a pair go through it.
+template <int G, int STRIDE, int TM>
+static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const real *base,
+                                               const int32_t *gpool, real dx, real dy, real dz, int lane) {
+    ColliderSmem<STRIDE> c;
+    c.type = type; c.nv = nv; c.V = V; c.base = base; c.gpool = gpool;
+    return support<G, TM>(c, V3(dx, dy, dz), lane);
+}
+
 // Out-of-line instance of the ten-way support switch for kernels that keep their collider
-// records in registers / local memory (EPA, MPR): one copy of the code instead of one per call
+// records in registers / local memory (MPR): one copy of the code instead of one per call
 // site (the MPR kernel shrank from 209 KB to a fraction of that; these kernels are
 // instruction-fetch bound).
 template <int G, int TM = D3D_ALL_TYPES_MASK>

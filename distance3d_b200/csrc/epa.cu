@@ -42,20 +42,94 @@ struct EpaParams {
     int32_t *out_status;
     double *out_faces;
     int *counter;
+    const int *perm;  // processing order: pairs grouped by (typeA, typeB)
 };
+
+// ---------------------------------------------------------------------------
+// Processing order.  EPA pairs arrive in candidate order; with 32 warps per SM each inside a
+// different arm of the ten-way support switch the instruction cache thrashes
+// (profiles/r01_ncu_k_epa_v2_occupancy7.txt: 5.4 stall cycles per issue waiting for
+// instructions).  A counting sort by (typeA, typeB) - the same idea as in gjk.cu - makes
+// co-resident warps run the same support code; pairs without a full simplex go last.
+#define EPA_NBINS (D3D_NUM_TYPES * D3D_NUM_TYPES + 1)
+struct EpaOrder {
+    int *hist;     // [128]
+    int *cursor;   // [128]
+    uint8_t *keys; // [P]
+    int *perm;     // [P]
+};
+
+__global__ void k_epa_keys(d3d_colliders c, const int32_t *__restrict__ pairs, const int32_t *npoints,
+                           int64_t n, EpaOrder w) {
+    __shared__ int sh[EPA_NBINS];
+    for (int i = threadIdx.x; i < EPA_NBINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
+        int key = __ldg(c.type + pr.x) * D3D_NUM_TYPES + __ldg(c.type + pr.y);
+        if (npoints && __ldg(npoints + k) != 4) key = EPA_NBINS - 1;
+        w.keys[k] = (uint8_t)key;
+        atomicAdd(&sh[key], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < EPA_NBINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&w.hist[i], sh[i]);
+}
+
+__global__ void k_epa_scan(EpaOrder w) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < EPA_NBINS; ++i) { w.cursor[i] = acc; acc += w.hist[i]; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_epa_scatter(int64_t n, EpaOrder w) {
+    __shared__ int hist[EPA_NBINS];
+    const int64_t tile = 256 * 8;
+    for (int64_t t0 = blockIdx.x * tile; t0 < n; t0 += (int64_t)gridDim.x * tile) {
+        for (int i = threadIdx.x; i < EPA_NBINS; i += 256) hist[i] = 0;
+        __syncthreads();
+        int key[8], rank[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int64_t k = t0 + j * 256 + threadIdx.x;
+            key[j] = k < n ? w.keys[k] : -1;
+            if (key[j] >= 0) rank[j] = atomicAdd(&hist[key[j]], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < EPA_NBINS; i += 256) {
+            int h = hist[i];
+            hist[i] = h ? atomicAdd(&w.cursor[i], h) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (key[j] >= 0) w.perm[hist[key[j]] + rank[j]] = (int)(t0 + j * 256 + threadIdx.x);
+        __syncthreads();
+    }
+}
+
+inline size_t epa_au(size_t x) { return (x + 255) / 256 * 256; }
+inline size_t epa_ws_bytes(int64_t n) { return 2048 + epa_au((size_t)n) + epa_au((size_t)n * 4); }
 
 #ifndef EPA_WARPS
 #define EPA_WARPS 4
 #endif
 
+// MF > 0: max_faces known at compile time (the reference's default 64: constant offsets in
+// every face access, 10 % of the kernel's instructions were address arithmetic); MF = 0: run time.
+template <int MF>
 struct WarpMem {
     double *faces;  // [12][max_faces]: v0 xyz, v1 xyz, v2 xyz, n xyz
     int *perm;      // [max_faces]
-    int mf;
+    int mf_rt;
+    D3D_DEV int mfv() const { return MF ? MF : mf_rt; }
     D3D_DEV v3 fget(int i, int which) const {
+        const int mf = mfv();
         return V3(faces[(3 * which) * mf + i], faces[(3 * which + 1) * mf + i], faces[(3 * which + 2) * mf + i]);
     }
     D3D_DEV void fset(int i, int which, v3 v) const {
+        const int mf = mfv();
         faces[(3 * which) * mf + i] = v.x; faces[(3 * which + 1) * mf + i] = v.y; faces[(3 * which + 2) * mf + i] = v.z;
     }
 };
@@ -66,24 +140,33 @@ D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v
 #ifndef EPA_BLOCKS_PER_SM
 #define EPA_BLOCKS_PER_SM 8  // 64 registers, 32 warps per SM; measured Mpairs/s at 5/6/7/8: 20.1/20.5/21.4/21.9
 #endif
+template <int MF>
 __global__ void __launch_bounds__(EPA_WARPS * 32, EPA_BLOCKS_PER_SM)
 k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
-    const int mf = prm.max_faces, ml = prm.max_loose_edges;
-    size_t per_warp = (size_t)12 * mf + (mf + 1) / 2 + 2;  // doubles
-    WarpMem W;
+    const int mf = MF ? MF : prm.max_faces, ml = prm.max_loose_edges;
+    size_t per_warp = (size_t)12 * mf + (mf + 1) / 2 + 2 + 2 * D3D_COLLIDER_FIELDS;  // doubles
+    WarpMem<MF> W;
     W.faces = smem + wid * per_warp;
     W.perm = reinterpret_cast<int *>(W.faces + 12 * mf);
-    W.mf = mf;
+    // The two collider records live in shared memory, one copy per warp.  Kept per lane they
+    // went to local memory behind the out-of-line support switch (300 B x 32 lanes x 32 warps
+    // per SM, more than the L1: profiles/r02_ncu_k_epa_v3_binned.txt shows 2e8 local
+    // accesses, a 45 % L1 hit rate and 5.9 stall cycles per issue on the scoreboard).
+    double *recA = W.faces + 12 * mf + (mf + 1) / 2 + 2, *recB = recA + D3D_COLLIDER_FIELDS;
+    W.mf_rt = mf;
     const double eps = prm.epsilon;
 
     for (;;) {
         int k = 0;
-        if (lane == 0) k = atomicAdd(prm.counter, 1);
+        if (lane == 0) {
+            k = atomicAdd(prm.counter, 1);
+            k = k < n_pairs ? __ldg(prm.perm + k) : -1;
+        }
         k = __shfl_sync(FULL, k, 0);
-        if (k >= n_pairs) break;
+        if (k < 0) break;
         if (prm.npoints && __ldg(prm.npoints + k) != 4) {  // undefined in the reference (np.empty rows)
             if (lane == 0) {
                 st3(prm.out_mtv + 3 * (int64_t)k, V3(0.0, 0.0, 0.0));
@@ -95,7 +178,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             continue;
         }
         int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
-        Collider A = load_collider(c, pr.x), B = load_collider(c, pr.y);
+        __syncwarp();  // the previous pair's records are no longer read
+        ColliderSmem<1> A = stage_collider_warp(c, pr.x, recA, lane), B = stage_collider_warp(c, pr.y, recB, lane);
 
         // epa.py:83-97: zero-initialised polytope, faces ABC, ACD, ADB, BDC
 #pragma unroll 1
@@ -126,7 +210,9 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             double min_dist = __shfl_sync(FULL, best, closest & 31);  // the owner's local best IS slot `closest`
             // ---- B: support point of A - B in the face normal (epa.py:62-65)
             v3 sd = W.fget(closest, 3);
-            v3 new_point = support_ni<32>(A, sd.x, sd.y, sd.z, lane) - support_ni<32>(B, -sd.x, -sd.y, -sd.z, lane);
+            v3 new_point = support_call<32, 1, D3D_ALL_TYPES_MASK>(A.type, A.nv, A.V, recA, c.graph, sd.x, sd.y, sd.z, lane) -
+                           support_call<32, 1, D3D_ALL_TYPES_MASK>(B.type, B.nv, B.V, recB, c.graph, -sd.x, -sd.y, -sd.z, lane);
+            __syncwarp();  // MeshGraph: lane 0 stored the vertex the climb ended on
             // ---- C: convergence (epa.py:67-70)
             double proj = dot_blas(new_point, sd);
             if (proj - min_dist < eps) {
@@ -167,9 +253,10 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     i = __ffsll((long long)rest) - 1;
                     int f = W.perm[i];
                     // epa.py:167-187: edges of the removed face against the loose-edge list
+                    v3 fv0 = W.fget(f, 0), fv1 = W.fget(f, 1), fv2 = W.fget(f, 2);  // broadcast reads
 #pragma unroll 1
                     for (int j = 0; j < 3; ++j) {
-                        v3 e0 = W.fget(f, j), e1 = W.fget(f, (j + 1) % 3);  // broadcast reads
+                        v3 e0 = j == 0 ? fv0 : (j == 1 ? fv1 : fv2), e1 = j == 0 ? fv1 : (j == 1 ? fv2 : fv0);
                         // np.linalg.norm(x) < eps without the square root (exactly equivalent)
                         v3 d0 = lb - e0, d1 = la - e1;
                         bool match = lane < n_loose && dot_blas(d0, d0) < prm.eps_sq_thr &&
@@ -256,8 +343,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         if (lane == 0) {
             st3(prm.out_mtv + 3 * (int64_t)k, mtv);
             if (c.mesh_last) {  // mesh.py:85
-                if (A.type == D3D_MESH) c.mesh_last[pr.x] = A.cur;
-                if (B.type == D3D_MESH) c.mesh_last[pr.y] = B.cur;
+                if (A.type == D3D_MESH) c.mesh_last[pr.x] = A.mesh_cur();
+                if (B.type == D3D_MESH) c.mesh_last[pr.y] = B.mesh_cur();
             }
             prm.out_success[k] = success ? 1 : 0;
             if (prm.out_nfaces) prm.out_nfaces[k] = n_faces;
@@ -287,7 +374,7 @@ double sqrt_threshold(double x) {
 
 extern "C" {
 
-size_t d3d_epa_workspace_bytes(int64_t n_pairs) { (void)n_pairs; return 256; }
+size_t d3d_epa_workspace_bytes(int64_t n_pairs) { return epa_ws_bytes(n_pairs); }
 
 int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
             const int32_t *npoints, int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
@@ -297,7 +384,8 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     if (n_pairs == 0) return 0;
     if (!c || !pairs || !Y || !out_mtv || !out_success || !workspace)
         return d3d_set_error("d3d_epa: null argument");
-    if (ws_bytes < 256) return d3d_set_error("d3d_epa: workspace too small");
+    if (n_pairs > 0x7fffffff) return d3d_set_error("d3d_epa: more than 2^31-1 pairs in one call");
+    if (ws_bytes < epa_ws_bytes(n_pairs)) return d3d_set_error("d3d_epa: workspace too small");
     if (max_faces < 4 || max_faces > 64 || max_loose_edges < 1 || max_loose_edges > 32)
         return d3d_set_error("d3d_epa: max_faces must be in [4, 64] and max_loose_edges in [1, 32]");
     EpaParams prm;
@@ -306,12 +394,33 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     prm.Y = Y; prm.npoints = npoints; prm.out_mtv = out_mtv; prm.out_success = out_success;
     prm.out_nfaces = out_nfaces; prm.out_iters = out_iters; prm.out_status = out_status;
     prm.out_faces = out_faces; prm.counter = reinterpret_cast<int *>(workspace);
-    D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, stream));
-    size_t per_warp = (size_t)12 * max_faces + (max_faces + 1) / 2 + 2;
+    D3D_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 2048, stream));
+    EpaOrder ord;
+    {
+        char *p = reinterpret_cast<char *>(workspace);
+        ord.hist = reinterpret_cast<int *>(p + 512);
+        ord.cursor = reinterpret_cast<int *>(p + 1280);
+        ord.keys = reinterpret_cast<uint8_t *>(p + 2048);
+        ord.perm = reinterpret_cast<int *>(p + 2048 + epa_au((size_t)n_pairs));
+    }
+    prm.perm = ord.perm;
+    {
+        int sms = d3d_sm_count();
+        int kb = (int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8);
+        k_epa_keys<<<kb, 256, 0, stream>>>(*c, pairs, npoints, n_pairs, ord);
+        k_epa_scan<<<1, 32, 0, stream>>>(ord);
+        k_epa_scatter<<<(int)d3d_min64((n_pairs + 2047) / 2048, (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, ord);
+    }
+    size_t per_warp = (size_t)12 * max_faces + (max_faces + 1) / 2 + 2 + 2 * D3D_COLLIDER_FIELDS;
     size_t smem = per_warp * EPA_WARPS * sizeof(double);
-    D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)d3d_min64((n_pairs + EPA_WARPS - 1) / EPA_WARPS, (int64_t)d3d_sm_count() * (EPA_BLOCKS_PER_SM + 2));
-    k_epa<<<blocks, EPA_WARPS * 32, smem, stream>>>(*c, pairs, n_pairs, prm);
+    if (max_faces == 64) {
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_epa<64><<<blocks, EPA_WARPS * 32, smem, stream>>>(*c, pairs, n_pairs, prm);
+    } else {
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_epa<0><<<blocks, EPA_WARPS * 32, smem, stream>>>(*c, pairs, n_pairs, prm);
+    }
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

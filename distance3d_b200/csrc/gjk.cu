@@ -234,17 +234,6 @@ D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32
     s.state = D3D_UNKNOWN;
 }
 
-// One shared copy of the ten-way support switch per kernel: both colliders of a pair
-// go through it (two calls), and because pairs are processed in (typeA, typeB) order
-// the switch is warp-uniform almost always.
-template <int G, int STRIDE, int TM>
-static __device__ __noinline__ v3 support_call(int type, int nv, const double *V, const real *base,
-                                               const int32_t *gpool, real dx, real dy, real dz, int lane) {
-    ColliderSmem<STRIDE> c;
-    c.type = type; c.nv = nv; c.V = V; c.base = base; c.gpool = gpool;
-    return support<G, TM>(c, V3(dx, dy, dz), lane);
-}
-
 // max(|Y_i|^2) over the slots selected by mask (_gjk_jolt.py:634-640)
 D3D_DEV real max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
     real m = (mask & 1) ? dot_blas(y0, y0) : -R(1.0);

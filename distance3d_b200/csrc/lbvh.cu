@@ -23,9 +23,15 @@
 //   k_brute         brute force; its pairs are appended with a warp-aggregated atomic
 //                   (ballot + one atomic per converged group)
 //
-// Node record = 64 bytes (one 128-bit-load quartet): lo[3], hi[3], left, right,
-// rope, parent.  Internal node i in [0, n-1), leaf j (sorted position) at n-1+j;
-// a leaf stores left = -(object index + 1).
+// Build record = 64 bytes: exact fp64 lo[3], hi[3], left, right, rope, parent.  Internal node
+// i in [0, n-1), leaf j (sorted position) at n-1+j; a leaf stores left = -(object index + 1).
+//
+// The queries read a second, compact copy of the tree.  Internal nodes: 32-byte records (two
+// 128-bit loads) with the box rounded OUTWARD to fp32 plus left / rope; the six comparisons of
+// a step are fp32 and the box is conservative, it can only add candidates.  Leaves: 64-byte
+// records with the exact fp64 box of the object, its index and the rope, so a leaf is decided
+// by the reference's closed-interval fp64 predicate in the same single fetch.  96 MB for 1 M
+// boxes instead of 128 MB: the whole tree stays in the 126 MB L2.
 #include "d3d_common.cuh"
 
 namespace {
@@ -36,6 +42,19 @@ struct __align__(16) BvhNode {
     int left, right, rope, parent;
 };
 static_assert(sizeof(BvhNode) == 64, "node record must be 64 bytes");
+
+struct __align__(16) TNode {  // traversal record of an internal node
+    float lo[3];
+    float hi[3];
+    int left, rope;
+};
+static_assert(sizeof(TNode) == 32, "traversal record must be 32 bytes");
+struct __align__(16) LeafRec {  // traversal record of a leaf (sorted position): the exact box
+    double box[6];              // lo.x hi.x lo.y hi.y lo.z hi.z (the (3,2) layout of the input)
+    int obj, rope;
+    int pad[2];
+};
+static_assert(sizeof(LeafRec) == 64, "leaf record must be 64 bytes");
 
 struct BvhHeader {  // first 256 bytes of the workspace
     int64_t n;
@@ -57,6 +76,8 @@ struct BvhLayout {
     int *flags;                   // [n-1]
     int *range_last;              // [2n-1] last sorted leaf covered by each node
     BvhNode *nodes;               // [2n-1]
+    TNode *tnodes;                // [n-1] compact internal nodes for the queries
+    LeafRec *leaves;              // [n] leaf records in sorted order
     int sort_blocks;
 };
 
@@ -66,7 +87,7 @@ inline size_t bvh_ws_bytes(int64_t n) {
     size_t nn = (size_t)(n > 0 ? n : 1);
     size_t sort_blocks = (nn + SORT_TILE - 1) / SORT_TILE;
     return 256 + au(1024 * 6 * 8) + 1024 + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nn * 4) +
-           au(2 * nn * 4) + au(2 * nn * sizeof(BvhNode));
+           au(2 * nn * 4) + au(2 * nn * sizeof(BvhNode)) + au(nn * sizeof(TNode)) + au(nn * sizeof(LeafRec));
 }
 
 inline BvhLayout bvh_carve(void *ws, int64_t n) {
@@ -82,7 +103,9 @@ inline BvhLayout bvh_carve(void *ws, int64_t n) {
     L.hist = reinterpret_cast<unsigned *>(p); p += au(256 * (size_t)L.sort_blocks * 4);
     L.flags = reinterpret_cast<int *>(p); p += au(nn * 4);
     L.range_last = reinterpret_cast<int *>(p); p += au(2 * nn * 4);
-    L.nodes = reinterpret_cast<BvhNode *>(p);
+    L.nodes = reinterpret_cast<BvhNode *>(p); p += au(2 * nn * sizeof(BvhNode));
+    L.tnodes = reinterpret_cast<TNode *>(p); p += au(nn * sizeof(TNode));
+    L.leaves = reinterpret_cast<LeafRec *>(p);
     return L;
 }
 
@@ -293,14 +316,27 @@ __device__ __forceinline__ int delta(const unsigned long long *keys, int n, int 
 
 // Leaf records (thread j < n) and the Karras hierarchy (thread i < n - 1) in one launch.  The
 // leaf part does not touch `parent`: that field is written by the internal node that adopts it.
+__device__ __forceinline__ void store_tbox(TNode *t, const double *lo, const double *hi) {
+    float4 a = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]),
+                           __double2float_ru(hi[0]));
+    float2 b = make_float2(__double2float_ru(hi[1]), __double2float_ru(hi[2]));
+    *reinterpret_cast<float4 *>(t) = a;
+    *reinterpret_cast<float2 *>(&t->hi[1]) = b;
+}
+
 __global__ void k_hierarchy(const double *__restrict__ aabb, const unsigned long long *__restrict__ keys,
-                            int n, BvhNode *nodes, int *range_first, int *range_last, int *flags) {
+                            int n, BvhNode *nodes, TNode *tnodes, LeafRec *leaves, int *range_first,
+                            int *range_last, int *flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     {
         int obj = (int)(unsigned)(keys[i] & 0xffffffffull);
         const double2 *b = reinterpret_cast<const double2 *>(aabb + 6 * (int64_t)obj);
         double2 x = __ldg(b), y = __ldg(b + 1), z = __ldg(b + 2);
+        double2 *lb = reinterpret_cast<double2 *>(leaves + i);
+        lb[0] = x; lb[1] = y; lb[2] = z;
+        leaves[i].obj = obj;
+        if (n == 1) leaves[0].rope = -1;
         BvhNode *nd = nodes + (n - 1 + i);
         nd->lo[0] = x.x; nd->lo[1] = y.x; nd->lo[2] = z.x;
         nd->hi[0] = x.y; nd->hi[1] = y.y; nd->hi[2] = z.y;
@@ -332,6 +368,7 @@ __global__ void k_hierarchy(const double *__restrict__ aabb, const unsigned long
     int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
     nodes[i].left = left;
     nodes[i].right = right;
+    tnodes[i].left = left;
     nodes[left].parent = i;
     nodes[right].parent = i;
     if (i == 0) nodes[0].parent = -1;
@@ -341,8 +378,8 @@ __global__ void k_hierarchy(const double *__restrict__ aabb, const unsigned long
 
 // rope(node covering [a, b]) = node that starts at b + 1: internal node b + 1 when its
 // range grows to the right, else leaf b + 1; -1 behind the last leaf.
-__global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes,
-                        const int *__restrict__ range_last) {
+__global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes, TNode *tnodes,
+                        LeafRec *leaves, const int *__restrict__ range_last) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * n - 1) return;
     int b = range_last[v];
@@ -355,6 +392,8 @@ __global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhN
         rope = d > 0 ? t : n - 1 + t;
     }
     nodes[v].rope = rope;
+    if (v < n - 1) tnodes[v].rope = rope;
+    else leaves[v - (n - 1)].rope = rope;
 }
 
 // Bottom-up refit: every leaf thread climbs, the second thread to arrive at a node merges the
@@ -363,7 +402,7 @@ __global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhN
 // and block-scope fences order the box stores (99.6 % of the nodes); only the nodes that span
 // blocks pay for device-scope fences and global atomics.
 __global__ void __launch_bounds__(256)
-k_refit(int n, BvhNode *nodes, int *flags, const int *__restrict__ range_first,
+k_refit(int n, BvhNode *nodes, TNode *tnodes, int *flags, const int *__restrict__ range_first,
         const int *__restrict__ range_last) {
     __shared__ int sflag[256];
     const int b0 = blockIdx.x * 256;
@@ -394,6 +433,7 @@ k_refit(int n, BvhNode *nodes, int *flags, const int *__restrict__ range_first,
             nodes[cur].lo[k] = lo[k];
             nodes[cur].hi[k] = hi[k];
         }
+        store_tbox(tnodes + cur, lo, hi);
         node = cur;
         cur = nodes[cur].parent;
     }
@@ -412,41 +452,89 @@ __device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, in
     if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(a, b);
 }
 
+// One traversal step on the compact tree.  q*: exact fp64 query box ((lo, hi) per axis),
+// f*: the same box rounded outward to fp32.
+struct QueryBox {
+    double2 x, y, z;
+    float lox, loy, loz, hix, hiy, hiz;
+    __device__ __forceinline__ void set(double2 qx, double2 qy, double2 qz) {
+        x = qx; y = qy; z = qz;
+        lox = __double2float_rd(qx.x); hix = __double2float_ru(qx.y);
+        loy = __double2float_rd(qy.x); hiy = __double2float_ru(qy.y);
+        loz = __double2float_rd(qz.x); hiz = __double2float_ru(qz.y);
+    }
+    __device__ __forceinline__ void set_empty() {  // never overlaps anything
+        x = y = z = make_double2(1e308, -1e308);
+        lox = loy = loz = 3.0e38f; hix = hiy = hiz = -3.0e38f;
+    }
+};
+struct Step {
+    bool ov;      // internal node: the fp32 boxes overlap (conservative); leaf: the exact boxes overlap
+    int left;     // >= 0: first child; < 0: leaf of object -left - 1
+    int rope;
+};
+struct Tree {
+    const TNode *__restrict__ tnodes;
+    const LeafRec *__restrict__ leaves;
+    int leaf0;  // node index of the first leaf (n - 1)
+};
+// Whether `node` is a leaf is known from its index, so a leaf costs ONE fetch: its 64-byte
+// record holds the exact box (aabb_tree.py:520-527, closed intervals), the object and the rope.
+__device__ __forceinline__ Step visit(const Tree &T, int node, const QueryBox &q) {
+    Step s;
+    if (node >= T.leaf0) {
+        const double2 *lb = reinterpret_cast<const double2 *>(T.leaves + (node - T.leaf0));
+        double2 x = __ldg(lb), y = __ldg(lb + 1), z = __ldg(lb + 2);
+        int2 link = __ldg(reinterpret_cast<const int2 *>(lb + 3));
+        s.ov = x.x <= q.x.y && x.y >= q.x.x && y.x <= q.y.y && y.y >= q.y.x && z.x <= q.z.y && z.y >= q.z.x;
+        s.left = -link.x - 1;
+        s.rope = link.y;
+    } else {
+        const float4 *p = reinterpret_cast<const float4 *>(T.tnodes + node);
+        float4 a = __ldg(p), b = __ldg(p + 1);  // lo.x lo.y lo.z hi.x | hi.y hi.z left rope
+        s.ov = a.x <= q.hix && a.w >= q.lox && a.y <= q.hiy && b.x >= q.loy && a.z <= q.hiz && b.y >= q.loz;
+        s.left = __float_as_int(b.z);
+        s.rope = __float_as_int(b.w);
+    }
+    return s;
+}
+
+static inline Tree tree_of(const BvhLayout &L, int64_t n) {
+    Tree T;
+    T.tnodes = L.tnodes; T.leaves = L.leaves; T.leaf0 = (int)n - 1;
+    return T;
+}
+
 // Traversal of one query box.  FILL = false: count the overlapping leaves;
 // FILL = true: write (object, query) pairs to out[offset ..).  Two passes instead of an
-// atomic append: the single-pass version spent 80 % of its time waiting for the
-// same-address atomic (profiles/r01_ncu_overlap_v1.txt); the two-pass form has no atomics,
-// an exact count before anything is written, and a deterministic output order
-// (queries in Morton order, leaves in depth-first order).
+// atomic append: no atomics, an exact count before anything is written, and a deterministic
+// output order (queries in the given order, leaves in depth-first order).
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
-          const int32_t *__restrict__ order, int64_t n_query, unsigned *__restrict__ counts,
-          const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
-          unsigned long long *visits) {
+k_overlap(Tree T, const BvhHeader *hdr,
+          const double *__restrict__ query, const int32_t *__restrict__ order, int64_t n_query,
+          unsigned *__restrict__ counts, const unsigned long long *__restrict__ offsets,
+          int32_t *out_pairs, int64_t cap, unsigned long long *visits) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_query) return;
     int qi = order ? order[t] : (int)t;
     const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
-    double2 qx = __ldg(qb), qy = __ldg(qb + 1), qz = __ldg(qb + 2);
+    QueryBox q;
+    q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
     int node = hdr->n > 0 ? hdr->root : -1;
     unsigned n_hits = 0, n_visited = 0;
     unsigned long long pos = FILL ? offsets[t] : 0ull;
     while (node >= 0) {
-        const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
-        double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);  // lo.x lo.y | lo.z hi.x | hi.y hi.z
-        int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));   // left right rope parent
-        // aabb_tree.py:520-527 (closed intervals)
-        bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
-        if (ov && link.x < 0) {
+        Step s = visit(T, node, q);
+        if (s.ov && s.left < 0) {
             if (FILL) {
-                if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-link.x - 1, qi);
+                if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-s.left - 1, qi);
                 ++pos;
             } else {
                 ++n_hits;
             }
         }
-        node = (ov && link.x >= 0) ? link.x : link.z;
+        node = (s.ov && s.left >= 0) ? s.left : s.rope;
         ++n_visited;
     }
     if (!FILL) counts[t] = n_hits;
@@ -469,38 +557,36 @@ k_overlap(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double 
 // L2 traffic drops by an order of magnitude on dense scenes.  Same results as k_overlap.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
-                 const int32_t *__restrict__ order, int64_t n_query, unsigned *__restrict__ counts,
-                 const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
-                 unsigned long long *visits) {
+k_overlap_packet(Tree T, const BvhHeader *hdr,
+                 const double *__restrict__ query, const int32_t *__restrict__ order, int64_t n_query,
+                 unsigned *__restrict__ counts, const unsigned long long *__restrict__ offsets,
+                 int32_t *out_pairs, int64_t cap, unsigned long long *visits) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool valid = t < n_query;
     int qi = valid ? (order ? order[t] : (int)t) : 0;
-    double2 qx = make_double2(1e308, -1e308), qy = qx, qz = qx;  // empty box: never overlaps
+    QueryBox q;
+    q.set_empty();
     if (valid) {
         const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
-        qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
+        q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
     }
     int node = hdr->n > 0 ? hdr->root : -1;  // warp-uniform
     unsigned n_hits = 0, n_visited = 0;
     unsigned long long pos = (FILL && valid) ? offsets[t] : 0ull;
     while (node >= 0) {
-        const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
-        double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-        int4 link = __ldg(reinterpret_cast<const int4 *>(p + 3));
-        bool ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
-        if (link.x < 0) {  // leaf (uniform branch)
-            if (ov) {
+        Step s = visit(T, node, q);
+        if (s.left < 0) {  // leaf (uniform branch)
+            if (s.ov) {
                 if (FILL) {
-                    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-link.x - 1, qi);
+                    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-s.left - 1, qi);
                     ++pos;
                 } else {
                     ++n_hits;
                 }
             }
-            node = link.z;
+            node = s.rope;
         } else {
-            node = __any_sync(0xffffffffu, ov) ? link.x : link.z;
+            node = __any_sync(0xffffffffu, s.ov) ? s.left : s.rope;
         }
         ++n_visited;
     }
@@ -520,6 +606,14 @@ k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
 // PW = 32 the full-warp packet; in between, the union of the nodes a group must see shrinks
 // faster than the number of groups per warp grows (dense capsule set: 8-wide groups need
 // ~2x fewer warp steps than 32-wide ones), while the PW lanes of a group still fetch one node.
+//
+// SELF = true: the queries are the tree's own leaves first_leaf .. first_leaf + n_query - 1
+// (sorted positions) and every unordered pair is wanted ONCE, without (i, i).  The depth-first
+// order of the tree is the sorted leaf order, so query s only needs the part of the walk that
+// lies to the right of leaf s: its group starts AT the leaf record of the group's first query
+// and follows the ropes from there (a rope always leads to the subtree that begins behind the
+// current one).  Half the nodes, half the output; pairs are written as (min, max) of the two
+// object indices.
 #ifndef APPEND_STAGE
 #define APPEND_STAGE 512  // pairs per warp; dense / sparse ms at 128, 256, 512, 1024: 14.6 14.3 14.2 20.2 / 0.50 0.50 0.47 0.66
 #endif
@@ -527,11 +621,12 @@ k_overlap_packet(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
 #define D3D_BVH_PACKET_WIDTH 8  // width used for packet = 1; 1 M capsules, ms dense / sparse at
 // widths 1, 2, 4, 8, 16, 32: 34.8 23.0 16.7 14.0 15.5 14.9 / 0.61 0.54 0.48 0.47 0.58 0.65
 #endif
-template <int PW>
+template <int PW, bool SELF>
 __global__ void __launch_bounds__(128)
-k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const double *__restrict__ query,
-                 const int32_t *__restrict__ order, int64_t n_query, int32_t *out_pairs, int64_t cap,
-                 unsigned long long *cursor, unsigned long long *visits) {
+k_overlap_append(Tree T, const BvhHeader *hdr,
+                 const double *__restrict__ query, const int32_t *__restrict__ order, int64_t first_leaf,
+                 int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *cursor,
+                 unsigned long long *visits) {
     __shared__ int2 stage_all[4][APPEND_STAGE];
     int2 *stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -539,37 +634,48 @@ k_overlap_append(const BvhNode *__restrict__ nodes, const BvhHeader *hdr, const 
     const unsigned group_mask = (PW == 32) ? FULL : (((1u << PW) - 1u) << (lane & ~(PW - 1)));
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool valid = t < n_query;
-    int qi = valid ? (order ? order[t] : (int)t) : 0;
-    double2 qx = make_double2(1e308, -1e308), qy = qx, qz = qx;  // empty box: never overlaps
+    int qi = 0;
+    int my_leaf = 0x7fffffff;  // SELF: node index of this query's own leaf record
+    QueryBox q;
+    q.set_empty();
     if (valid) {
-        const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
-        qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
+        const double2 *qb;
+        if (SELF) {
+            my_leaf = T.leaf0 + (int)(first_leaf + t);
+            qi = __ldg(&T.leaves[first_leaf + t].obj);
+            qb = reinterpret_cast<const double2 *>(T.leaves + (first_leaf + t));
+        } else {
+            qi = order ? order[t] : (int)t;
+            qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
+        }
+        q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
     }
     // group-uniform; a group with no valid query at all never starts
     bool group_valid = PW == 1 ? valid : (__ballot_sync(FULL, valid) & group_mask) != 0;
-    int node = (hdr->n > 0 && group_valid) ? hdr->root : -1;
+    int node = -1;
+    if (hdr->n > 0 && group_valid) {
+        if (SELF) node = T.leaf0 + (int)(first_leaf + (t & ~(int64_t)(PW - 1)));  // the group's first leaf (always valid)
+        else node = hdr->root;
+    }
     int staged = 0;  // warp-uniform
     unsigned n_visited = 0;
     while (__any_sync(FULL, node >= 0)) {
         bool ov = false, hit = false;
-        int4 link = make_int4(0, 0, -1, 0);
+        int left = 0, rope = -1;
         if (node >= 0) {
-            const double2 *p = reinterpret_cast<const double2 *>(nodes + node);
-            double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-            link = __ldg(reinterpret_cast<const int4 *>(p + 3));  // left right rope parent
-            // aabb_tree.py:520-527 (closed intervals)
-            ov = a.x <= qx.y && b.y >= qx.x && a.y <= qy.y && c.x >= qy.x && b.x <= qz.y && c.y >= qz.x;
+            Step s = visit(T, node, q);
+            ov = s.ov; left = s.left; rope = s.rope;
             ++n_visited;
         }
         bool any = PW == 1 ? ov : (__ballot_sync(FULL, ov) & group_mask) != 0;
-        int leaf = -link.x - 1;
+        int leaf = -left - 1;
         if (node >= 0) {
-            hit = ov && link.x < 0;
-            node = (any && link.x >= 0) ? link.x : link.z;
+            hit = ov && left < 0 && (!SELF || node > my_leaf);
+            node = (any && left >= 0) ? left : rope;
         }
         unsigned m = __ballot_sync(FULL, hit);
         if (m) {
-            if (hit) stage[staged + __popc(m & lt)] = make_int2(leaf, qi);
+            if (hit) stage[staged + __popc(m & lt)] = SELF ? make_int2(min(leaf, qi), max(leaf, qi)) : make_int2(leaf, qi);
             staged += __popc(m);
         }
         if (staged > APPEND_STAGE - 32) {
@@ -768,11 +874,12 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
     // 4 passes: sorted keys are back in keys[0]
     // the second key buffer is free after the sort: it holds the first leaf of every internal node
     int *range_first = reinterpret_cast<int *>(L.keys[1]);
-    k_hierarchy<<<nb, 256, 0, stream>>>(aabb, L.keys[0], (int)n, L.nodes, range_first, L.range_last, L.flags);
+    k_hierarchy<<<nb, 256, 0, stream>>>(aabb, L.keys[0], (int)n, L.nodes, L.tnodes, L.leaves, range_first,
+                                        L.range_last, L.flags);
     if (n > 1) {
-        k_ropes<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, stream>>>(L.keys[0], (int)n, L.nodes,
-                                                                       L.range_last);
-        k_refit<<<nb, 256, 0, stream>>>((int)n, L.nodes, L.flags, range_first, L.range_last);
+        k_ropes<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, stream>>>(L.keys[0], (int)n, L.nodes, L.tnodes,
+                                                                       L.leaves, L.range_last);
+        k_refit<<<nb, 256, 0, stream>>>((int)n, L.nodes, L.tnodes, L.flags, range_first, L.range_last);
     }
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -796,10 +903,10 @@ int d3d_bvh_overlap_count(const void *workspace, int64_t n, const double *query,
     QueryLayout Q = query_carve(query_ws, n_query);
     if (packet)
         k_overlap_packet<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            L.nodes, L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
+            tree_of(L, n), L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
     else
         k_overlap<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            L.nodes, L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
+            tree_of(L, n), L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
     k_scan_tiles<<<Q.n_tiles, 1024, 0, stream>>>(Q.counts, n_query, Q.offsets, Q.tile_sums);
     k_scan_top<<<1, 1024, 0, stream>>>(Q.tile_sums, Q.n_tiles, out_count);
     k_scan_add<<<(unsigned)((n_query + 255) / 256), 256, 0, stream>>>(Q.offsets, n_query, Q.tile_sums);
@@ -818,10 +925,40 @@ int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, 
     QueryLayout Q = query_carve(const_cast<void *>(query_ws), n_query);
     if (packet)
         k_overlap_packet<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            L.nodes, L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
+            tree_of(L, n), L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
     else
         k_overlap<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            L.nodes, L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
+            tree_of(L, n), L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_append(const BvhLayout &L, int64_t n, bool self, const double *query, const int32_t *order,
+                         int64_t first_leaf, int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                         unsigned long long *out_count, unsigned long long *out_visits, cudaStream_t stream) {
+    unsigned blocks = (unsigned)((n_query + 127) / 128);
+#define D3D_APPEND(PW)                                                                                  \
+    do {                                                                                                \
+        if (self)                                                                                       \
+            k_overlap_append<PW, true><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
+                                                                   first_leaf, n_query, out_pairs, cap, \
+                                                                   out_count, out_visits);             \
+        else                                                                                            \
+            k_overlap_append<PW, false><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
+                                                                    first_leaf, n_query, out_pairs, cap, \
+                                                                    out_count, out_visits);            \
+    } while (0)
+    switch (packet) {  // 0 / 1 = per thread / default packet; 2, 4, 8, 16, 32 = explicit width
+    case 0: D3D_APPEND(1); break;
+    case 1: D3D_APPEND(D3D_BVH_PACKET_WIDTH); break;
+    case 2: D3D_APPEND(2); break;
+    case 4: D3D_APPEND(4); break;
+    case 8: D3D_APPEND(8); break;
+    case 16: D3D_APPEND(16); break;
+    case 32: D3D_APPEND(32); break;
+    default: return d3d_set_error("d3d_bvh_overlap: packet must be 0, 1, 2, 4, 8, 16 or 32");
+    }
+#undef D3D_APPEND
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -840,23 +977,24 @@ int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const
     if (n_query == 0 || n == 0) return 0;
     if (!query || (cap > 0 && !out_pairs)) return d3d_set_error("d3d_bvh_overlap: null query / output");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    unsigned blocks = (unsigned)((n_query + 127) / 128);
-#define D3D_APPEND(PW)                                                                              \
-    k_overlap_append<PW><<<blocks, 128, 0, stream>>>(L.nodes, L.hdr, query, order, n_query, out_pairs, \
-                                                     cap, out_count, out_visits)
-    switch (packet) {  // 0 / 1 = per thread / default packet; 2, 4, 8, 16, 32 = explicit width
-    case 0: D3D_APPEND(1); break;
-    case 1: D3D_APPEND(D3D_BVH_PACKET_WIDTH); break;
-    case 2: D3D_APPEND(2); break;
-    case 4: D3D_APPEND(4); break;
-    case 8: D3D_APPEND(8); break;
-    case 16: D3D_APPEND(16); break;
-    case 32: D3D_APPEND(32); break;
-    default: return d3d_set_error("d3d_bvh_overlap: packet must be 0, 1, 2, 4, 8, 16 or 32");
-    }
-#undef D3D_APPEND
-    D3D_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    return launch_append(L, n, false, query, order, 0, n_query, packet, out_pairs, cap, out_count, out_visits, stream);
+}
+
+/* the tree against its own leaves first_leaf .. first_leaf + n_query - 1 (sorted positions):
+ * every unordered pair once, as (smaller, larger) object index, no (i, i) */
+int d3d_bvh_overlap_self(const void *workspace, int64_t n, int64_t first_leaf, int64_t n_query, int packet,
+                         int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                         unsigned long long *out_visits, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap_self: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
+    if (n_query == 0 || n == 0) return 0;
+    if (first_leaf < 0 || first_leaf + n_query > n) return d3d_set_error("d3d_bvh_overlap_self: leaf range out of bounds");
+    if (cap > 0 && !out_pairs) return d3d_set_error("d3d_bvh_overlap_self: null output");
+    BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+    return launch_append(L, n, true, nullptr, nullptr, first_leaf, n_query, packet, out_pairs, cap, out_count,
+                         out_visits, stream);
 }
 
 /* count + fill in one call: reproducible pair order (queries in the given order, leaves in

@@ -53,7 +53,7 @@ def epa_batch(colliders, pairs, simplices, max_iter=64, max_loose_edges=32, max_
     if n_points is not None:
         n_points = n_points.to(device=dc.device, dtype=torch.int32).contiguous()
     L = _lib.lib()
-    ws = workspace(256, dc.device, "epa")
+    ws = workspace(L.d3d_epa_workspace_bytes(c_i64(n)), dc.device, "epa")
     _lib._check(L.d3d_epa(
         ctypes.byref(dc.struct), ptr(pairs), c_i64(n), ptr(Y), ptr(n_points), c_int(max_iter),
         c_int(max_loose_edges), c_int(max_faces), c_dbl(epsilon), ptr(res.mtv), ptr(res.success),

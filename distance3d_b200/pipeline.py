@@ -17,38 +17,39 @@ class PipelineResult:
     """Candidates and contacts of one :func:`collide` call (device tensors)."""
 
     def __init__(self, n_overlaps, candidates, gjk, hits, epa):
-        self.n_overlaps = n_overlaps    # ordered AABB overlaps found by the traversal (incl. i == j)
-        self.candidates = candidates    # int32[C,2], i < j
+        self.n_overlaps = n_overlaps    # unordered AABB overlaps found by this rank's traversal (= C)
+        self.candidates = candidates    # int32[C,2], i < j, each unordered pair once
         self.gjk = gjk                  # GjkResult over the candidates
         self.hits = hits                # int64[H] indices into candidates with distance 0
-        self.epa = epa                  # EpaResult over the hits with a 4-point simplex (or None)
-        self.epa_index = None           # int64[E] indices into candidates that went through EPA
+        self.epa = epa                  # EpaResult over the hits (status 8 where the simplex had < 4 points)
+        self.epa_index = None           # int64[H] indices into candidates of the EPA rows
 
 
-def collide(colliders, penetration=True, distance_threshold=None, shard=True):
+def collide(colliders, penetration=True, distance_threshold=None, shard=True, candidate_capacity=None):
     """Broad phase + narrow phase for all colliders of a packed set.
 
     Returns a :class:`PipelineResult`.  `distance_threshold` is only used to report
-    `near` pairs by the caller; all candidates get an exact GJK distance.
+    `near` pairs by the caller; all candidates get an exact GJK distance.  With several
+    ranks (shard=True) every rank builds the same tree and walks its own contiguous range of
+    leaves; a candidate pair belongs to the rank that owns its earlier leaf, so the ranks'
+    candidate lists are disjoint and their union is the single-GPU list.
     """
     torch = _lib.torch_cuda()
     dc = _lib.as_device_colliders(colliders)
     aabb = _lib.aabb_device(dc)
     bvh = aabb_tree.Lbvh(aabb)
-    order = bvh.leaf_order()
-    if shard:
-        begin, end = parallel.shard_range(dc.n)
-        order = order[begin:end].contiguous()
-    pairs, count = bvh.overlap(aabb, order=order)
-    # every unordered pair once (the traversal reports both orientations and (i, i))
-    # (with several ranks the one that owns the larger index as query keeps the pair)
-    keep = pairs[:, 0] < pairs[:, 1]
-    candidates = pairs[keep].contiguous()
+    begin, end = parallel.shard_range(dc.n) if shard else (0, dc.n)
+    # every unordered pair once, straight from the traversal (no (i, i), no mirrored copy)
+    candidates, count = bvh.overlap_unique(begin, end - begin, capacity=candidate_capacity)
     g = _gjk.gjk_distance_batch(dc, candidates)
+    bad = int((g.status >= _gjk.STATUS_SANITY_FAILED).sum().item())
+    if bad:
+        raise RuntimeError("%d candidate pairs ended GJK without a verdict" % bad)
     hits = torch.nonzero(g.dist == 0.0).flatten()
     res = PipelineResult(count, candidates, g, hits, None)
     if penetration and hits.numel():
-        full = hits[g.n_points[hits] == 4]
-        res.epa_index = full
-        res.epa = _epa.epa_batch(dc, candidates[full], g.simplex[full])
+        # EPA is defined where GJK ended with a full simplex (SURVEY App. A #4); the others
+        # come back with status 8
+        res.epa_index = hits
+        res.epa = _epa.epa_batch(dc, candidates[hits], g.simplex[hits], n_points=g.n_points[hits])
     return res

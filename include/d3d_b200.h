@@ -181,6 +181,17 @@ int d3d_bvh_overlap_ordered(const void *workspace, int64_t n, const double *quer
                             unsigned long long *out_count, unsigned long long *out_visits,
                             void *query_ws, size_t query_ws_size, void *stream);
 
+/* aabb_tree.py:121-159 overlaps_aabb_tree(self) / broad_phase.py:229-252 aabb_overlapping_with_self
+ * without the redundancy: the tree against its own leaves first_leaf .. first_leaf + n_query - 1
+ * (positions in Morton order, see d3d_bvh_leaf_order; the whole tree: 0, n), ONE traversal.  Every
+ * unordered overlapping pair is appended once as (smaller, larger) object index; (i, i) is not
+ * reported.  A leaf only walks the part of the tree behind itself, so nodes visited and bytes
+ * written are half of d3d_bvh_overlap over the same boxes.  Disjoint leaf ranges (one per
+ * GPU) give disjoint pair lists whose union is the full set. */
+int d3d_bvh_overlap_self(const void *workspace, int64_t n, int64_t first_leaf, int64_t n_query, int packet,
+                         int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
+                         unsigned long long *out_visits, void *stream);
+
 /* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
 int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);
 

@@ -126,3 +126,56 @@ def test_aabbtree_api_matches_reference_semantics():
     assert 7 in overlaps and 500 not in set(overlaps) - {500} or True
     np.testing.assert_array_equal(tree.get_root_aabb()[:, 0], tree.aabbs[:, :, 0].min(axis=0))
     assert aabb_tree.aabb_overlap(A[0], A[0]) and not aabb_tree.aabb_overlap(A[0], A[0] + 100.0)
+
+
+@pytest.mark.parametrize("n,scale,names", [(1, 1.0, ("box",)), (2, 0.1, ("box",)), (33, 0.5, ("capsule",)),
+                                           (5000, 2.0, ("capsule", "box", "sphere")),
+                                           (60000, 8.0, ("capsule", "box", "sphere"))])
+def test_self_query_every_unordered_pair_once(n, scale, names):
+    """d3d_bvh_overlap_self: each leaf walks only the part of the tree behind itself; the list
+    holds every unordered pair of the brute-force set exactly once, as (smaller, larger)."""
+    rs = np.random.RandomState(100 + n)
+    cs = d3random.random_collider_set(rs, n, names=names, center_scale=scale)
+    A = _lib.aabb(cs)
+    bvh = aabb_tree.Lbvh(A)
+    ref = O.all_aabbs_overlap(A, A)
+    ref_u = as_set(ref[ref[:, 0] < ref[:, 1]])
+    for packet in (0, 1, 32):
+        pairs, count = bvh.overlap_unique(packet=packet, capacity=4)      # forces the exact-size re-run
+        p = pairs.cpu().numpy()
+        assert count == len(ref_u) == len(p) and as_set(p) == ref_u
+        assert np.all(p[:, 0] < p[:, 1]) if len(p) else True
+    # leaf ranges (one per rank): disjoint lists, union = the full set
+    cuts = [0, n // 3, n // 3, (2 * n) // 3 + 1, n]
+    parts = [bvh.overlap_unique(a, b - a)[0].cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
+    allp = np.concatenate(parts)
+    assert len(allp) == len(ref_u) and as_set(allp) == ref_u
+    # duplicates and touching boxes
+    if n >= 33:
+        B = np.concatenate([A, A[:17]])
+        B[5, :, 1] = B[6, :, 0]                                          # box 5 ends where box 6 starts
+        refB = O.all_aabbs_overlap(B, B)
+        pb, cb = aabb_tree.Lbvh(B).overlap_unique()
+        assert as_set(pb.cpu().numpy()) == as_set(refB[refB[:, 0] < refB[:, 1]])
+
+
+def test_float_node_boxes_keep_the_exact_fp64_predicate():
+    """The traversal compares fp32 boxes rounded outward and decides leaves on the exact fp64
+    boxes: pairs that differ from touching by one ulp are classified like the reference does."""
+    rs = np.random.RandomState(8)
+    n = 4000
+    lo = rs.uniform(-50, 50, size=(n, 3)) * 1e3      # large coordinates: fp32 spacing ~ 4e-3
+    ext = rs.uniform(0.001, 0.01, size=(n, 3))
+    A = np.stack([lo, lo + ext], axis=2)
+    for k in range(0, n - 1, 2):                       # neighbour touches exactly / misses by one ulp
+        A[k + 1, :, 0] = A[k, :, 1]
+        A[k + 1, :, 1] = A[k + 1, :, 0] + ext[k + 1]
+        if k % 4 == 0:
+            A[k + 1, 0, 0] = np.nextafter(A[k, 0, 1], np.inf)
+    ref = O.all_aabbs_overlap(A, A)
+    bvh = aabb_tree.Lbvh(A)
+    pairs, count = bvh.overlap_self()
+    assert count == len(ref) and as_set(pairs.cpu().numpy()) == as_set(ref)
+    pu, cu = bvh.overlap_unique()
+    assert as_set(pu.cpu().numpy()) == as_set(ref[ref[:, 0] < ref[:, 1]])
+    assert n - 1 > cu >= n // 4

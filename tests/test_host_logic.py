@@ -167,8 +167,14 @@ def test_c_abi_argument_checks_without_a_gpu():
     pairs = (ctypes.c_int32 * 2)(0, 0)
     rc = lib.d3d_epa(ctypes.byref(cs), pairs, i64(1), dummy, None, 64, 32, 65, dbl(1e-8), dummy,
                      ctypes.cast(dummy, vp), None, None, None, None, ctypes.cast(dummy, vp),
-                     ctypes.c_size_t(512), None)
+                     ctypes.c_size_t(1 << 20), None)
     assert rc == -1 and b"max_faces" in lib.d3d_last_error_string()
+    lib.d3d_epa_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.d3d_epa_workspace_bytes(i64(1 << 20)) >= 5 << 20   # processing order: 5 B per pair
+    rc = lib.d3d_epa(ctypes.byref(cs), pairs, i64(1), dummy, None, 64, 32, 64, dbl(1e-8), dummy,
+                     ctypes.cast(dummy, vp), None, None, None, None, ctypes.cast(dummy, vp),
+                     ctypes.c_size_t(64), None)
+    assert rc == -1 and b"workspace too small" in lib.d3d_last_error_string()
     assert lib.d3d_bvh_build(None, i64(-1), ctypes.cast(dummy, vp), ctypes.c_size_t(512), None) == -1
     assert b"out of range" in lib.d3d_last_error_string()
     assert lib.d3d_bvh_build(dummy, i64(1000), ctypes.cast(dummy, vp), ctypes.c_size_t(512), None) == -1
