@@ -11,6 +11,17 @@ cylinder, box} with the default scales of the reference's generators
 GPU (weak scaling: pairs are independent, every rank owns its shard, no
 data-path collective).  A step = one d3d_gjk_distance pass over the rank's shard.
 
+After the headline the same run measures BASELINE configs[1..4] at their stated sizes on all
+N ranks, with the collectives the multi-GPU design needs inside the timed regions
+(`broad_phase`, `epa`, `self_collision`, `pipeline` blocks of the JSON line):
+
+  C2  1 M capsules: every rank builds the same LBVH (replica) and walks its 1/N of the leaves
+      (strong scaling); the ranks' pair lists are all-gathered (exact-size slices)
+  C3  4 Mi intersecting hull pairs (64-256 vertices) per GPU through EPA; mtv all-gathered
+  C4  10 M joint configurations per GPU: FK + AABB + white-list filter + GJK; masks all-gathered
+  C5  2 M mixed shapes per GPU (16 M on 8 GPUs): replicated LBVH over ALL shapes, this rank's
+      leaves as queries, GJK on the candidates, EPA on the hits, contacts all-gathered
+
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement").
 """
 import argparse
@@ -29,7 +40,11 @@ sys.path.insert(0, REPO)
 
 FLOP_PER_ITER = 350.0  # algorithmic flop per GJK iteration (primitives)
 BYTES_PER_PAIR = 496.0  # 336 B in + 160 B out
-NCU_DRAM_BYTES_PER_PAIR = (497.15e6 + 228.49e6) / 1048576  # measured, see roofline.traffic
+NCU_PROFILE = os.path.join("profiles", "r02_ncu_k_gjk_thread_v8.txt")  # roofline.traffic is read from it
+# reference's own numba path (gjk.gjk on 3000 primitive pairs, seed 84, JIT warm, best of 3), timed in
+# the BUILD container (1 core of an 8-vCPU Xeon), not on the GPU box: its sources cannot travel
+NUMBA_REFERENCE = {"value": 3.03e3, "unit": "pairs/s", "cores": 1, "kind": "reference (numba)",
+                   "where": "build container, not the GPU box", "sample": "3000 pairs, seed 84"}
 
 
 def parse_args():
@@ -45,9 +60,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the broad-phase extra metrics")
     ap.add_argument("--capsules", type=int, default=1000000, help="C2: capsules in the broad phase")
-    ap.add_argument("--workload", default="gjk", choices=["gjk", "epa", "selfcollision", "pipeline"],
-                    help="gjk = headline (C1 + C2 extras); epa = C3; selfcollision = C4; pipeline = C5")
-    ap.add_argument("--items", type=int, default=0, help="size of the secondary workloads (0 = default)")
+    ap.add_argument("--only", default="", choices=["", "broad", "epa", "selfcollision", "pipeline"],
+                    help="run one secondary block only and print it (development)")
+    ap.add_argument("--epa-pairs", type=int, default=4 * 1024 * 1024, help="C3: EPA pairs per GPU")
+    ap.add_argument("--configurations", type=int, default=10000000, help="C4: joint configurations per GPU")
+    ap.add_argument("--shapes", type=int, default=2000000, help="C5: shapes per GPU")
+    ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of the secondary blocks")
     return ap.parse_args()
 
 
@@ -146,102 +164,6 @@ def make_capsules(n, center_scale=2.0, seed=32):
     return pack.ColliderSet(np.full(n, pack.CAPSULE, dtype=np.int32), pose, param, z, z, np.zeros((0, 3)))
 
 
-def bench_broad_phase(args, torch, _lib, hbm_peak, steps=5, cpu=True):
-    """C2: AABBs of n capsules, LBVH build, all-overlap self query (dense and sparse sets)."""
-    from distance3d_b200 import aabb_tree
-    n = args.capsules
-    out = {"capsules": n}
-    for name, scale in (("dense", 2.0), ("constant_density", 2.0 * (n / 2000.0) ** (1.0 / 3.0))):
-        cs = make_capsules(n, scale)
-        dc = cs.device()
-        aabb = _lib.aabb_device(dc)
-        bvh = aabb_tree.Lbvh(aabb)
-        modes = {}
-        for packet in (False, True):   # per-thread vs warp-packet traversal: keep the faster
-            tm = []
-            for it in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                pairs, count = bvh.overlap_self(count_visits=True, packet=packet)
-                e1.record()
-                torch.cuda.synchronize()
-                tm.append(e0.elapsed_time(e1))
-            modes[packet] = (min(tm), bvh.visits())
-            del pairs
-        buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=aabb.device)
-        single = {}
-        for packet in (False, True):   # single pass: independent traversals vs 8-wide packets
-            tm = []
-            for it in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=packet)
-                e1.record()
-                torch.cuda.synchronize()
-                tm.append(e0.elapsed_time(e1))
-            bvh.overlap_self(count_visits=True, packet=packet, ordered=False, out=buf)
-            single[packet] = (min(tm), bvh.visits())
-        packet = single[True][0] < single[False][0]
-        visits = single[packet][1]
-        tb, tq = [], []
-        for it in range(steps + 2):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record()
-            bvh.rebuild()
-            e[1].record()
-            _, cnt_dev = bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=packet)  # no host sync
-            e[2].record()
-            torch.cuda.synchronize()
-            assert int(cnt_dev.item()) == count, "single-pass and two-pass overlap counts differ"
-            if it >= 2:
-                tb.append(e[0].elapsed_time(e[1])); tq.append(e[1].elapsed_time(e[2]))
-        tb_ms, tq_ms = float(np.mean(tb)), float(np.mean(tq))
-        q_bytes = n * 48.0 + count * 8.0 + visits * 64.0
-        # compulsory DRAM traffic: every node record at most once (re-visits hit L1 / L2)
-        q_bytes_min = n * 48.0 + count * 8.0 + min(visits, 2 * n - 1) * 64.0
-        b_bytes = n * 176.0
-        out[name] = {
-            "center_scale": scale, "overlap_pairs": int(count), "node_visits": int(visits),
-            "traversal": "8-wide packets" if packet else "per thread",
-            "single_pass_ms_per_thread_mode": single[False][0], "single_pass_ms_packet_mode": single[True][0],
-            "query": "d3d_bvh_overlap: one traversal, warp-staged append (unordered pairs)",
-            "ordered_two_pass_ms_per_thread_mode": modes[False][0],
-            "ordered_two_pass_ms_packet_mode": modes[True][0],
-            "build_ms": tb_ms, "query_ms": tq_ms,
-            "build_aabbs_per_s": n / (tb_ms * 1e-3), "overlap_pairs_per_s": count / (tq_ms * 1e-3),
-            "queries_per_s": n / (tq_ms * 1e-3),
-            "roofline_query": {"bound": "hbm", "achieved": q_bytes / (tq_ms * 1e-3) / 1e9,
-                               "peak": hbm_peak, "unit": "GB/s",
-                               "frac": q_bytes / (tq_ms * 1e-3) / 1e9 / hbm_peak,
-                               "bytes": "Q*48 + pairs*8 + node_visits*64 (SURVEY 8d); node re-visits "
-                                        "are served by L1/L2, so this model can exceed the HBM peak",
-                               "frac_compulsory": q_bytes_min / (tq_ms * 1e-3) / 1e9 / hbm_peak,
-                               "bytes_compulsory": "Q*48 + pairs*8 + min(node_visits, 2n-1)*64"},
-            "roofline_build": {"bound": "hbm", "achieved": b_bytes / (tb_ms * 1e-3) / 1e9,
-                               "peak": hbm_peak, "unit": "GB/s",
-                               "frac": b_bytes / (tb_ms * 1e-3) / 1e9 / hbm_peak,
-                               "bytes": "176 B per primitive (SURVEY 8d)"},
-        }
-        del buf, bvh
-        torch.cuda.empty_cache()
-        if cpu and name == "constant_density":
-            # reference algorithm (incremental tree + per-box stack query) on a bounded sample
-            from oracle import cpu_oracle
-            m = min(n, 50000)
-            A = cpu_oracle.aabb(make_capsules(m, 2.0 * (m / 2000.0) ** (1.0 / 3.0)))
-            t0 = time.perf_counter()
-            tree = cpu_oracle.Tree()
-            tree.insert_aabbs(A)
-            t1 = time.perf_counter()
-            ref_pairs = tree.query(A)
-            t2 = time.perf_counter()
-            out["cpu_baseline"] = {
-                "kind": "port", "cores": 1, "sample": "%d capsules at constant density" % m,
-                "build_aabbs_per_s": m / (t1 - t0), "queries_per_s": m / (t2 - t1),
-                "overlap_pairs_per_s": len(ref_pairs) / (t2 - t1)}
-    return out
-
-
 def timed_steps(torch, dist, world, dev, fn, steps, warmup):
     """max-over-ranks CUDA-event time per step of fn()."""
     for _ in range(max(warmup, 3)):
@@ -263,139 +185,351 @@ def timed_steps(torch, dist, world, dev, fn, steps, warmup):
     return float(t.item())
 
 
-def secondary_workload(args, torch, dist, rank, world, dev):
-    """C3 / C4 / C5 of BASELINE.json (own JSON line, same schema; not the headline)."""
-    from distance3d_b200 import _lib, gjk, epa, random as d3random, pipeline
-    rs = np.random.RandomState(args.seed + 1000 * rank)
-    line = {"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic"}
-    if args.workload == "epa":
-        # C3: intersecting convex hulls with 64-256 vertices, library of shapes, unique poses
-        n_pairs = args.items or 500000
-        cs = d3random.random_collider_set(rs, 2 * n_pairs, names=("mesh",), center_scale=0.7,
-                                          hull_vertices=(64, 256), hull_library=4096)
-        pairs = np.arange(2 * n_pairs, dtype=np.int32).reshape(n_pairs, 2)
-        dc = cs.device(dev)
-        g = gjk.gjk_distance_batch(dc, pairs)
-        sel = torch.nonzero((g.dist == 0.0) & (g.n_points == 4)).flatten()
-        pairs_d = torch.from_numpy(pairs).to(dev)[sel].contiguous()
-        Y = g.simplex[sel].contiguous()
-        n = int(sel.numel())
+def all_sum(torch, dist, world, dev, x):
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t)
+    return float(t.item())
+
+
+def replicas_identical(torch, dist, world, t):
+    """All ranks generated the same device-resident set (replicated BVH needs it)."""
+    if world == 1:
+        return True
+    c = t.double().sum().reshape(1)
+    lo, hi = c.clone(), c.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool((lo == hi).item())
+
+
+def pair_keys(torch, pairs, n):
+    lo = torch.minimum(pairs[:, 0], pairs[:, 1]).long()
+    hi = torch.maximum(pairs[:, 0], pairs[:, 1]).long()
+    return lo * n + hi
+
+
+NVLINK_PEAK_GBS = 770.0  # measured peer copy per direction on this pool (B200_PROFILING.md)
+
+
+def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
+    """C2: AABBs of n capsules; every rank builds the same LBVH and walks its share of the
+    leaves (strong scaling); every unordered overlapping pair once; lists all-gathered."""
+    from distance3d_b200 import _lib, aabb_tree, parallel, random as d3random
+    n = args.capsules
+    steps = args.extra_steps
+    out = {"capsules": n, "scaling": "strong",
+           "design": "replicated LBVH (built redundantly on every GPU), leaves sharded 1/N per GPU, "
+                     "d3d_bvh_overlap_self: every unordered pair once; all-gather of exact-size slices"}
+    for name, scale in (("dense", 2.0), ("constant_density", 2.0 * (n / 2000.0) ** (1.0 / 3.0))):
+        dc = d3random.random_capsules_device(32, n, center_scale=scale, device=dev)
+        aabb = _lib.aabb_device(dc)
+        same = replicas_identical(torch, dist, world, aabb)
+        bvh = aabb_tree.Lbvh(aabb)
+        begin, end = parallel.shard_range(n, rank, world)
+        pairs, count = bvh.overlap_unique(begin, end - begin, count_visits=True)
+        visits = bvh.visits()
+        buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=dev)
+        total = int(all_sum(torch, dist, world, dev, count))
+        total_visits = int(all_sum(torch, dist, world, dev, visits))
+        gathered = torch.empty((max(total, 1), 2), dtype=torch.int32, device=dev)
+        build_ms = timed_steps(torch, dist, world, dev, lambda: bvh.rebuild(), steps, 3)
+        query_ms = timed_steps(torch, dist, world, dev,
+                               lambda: bvh.overlap_unique_async(buf, begin, end - begin), steps, 3)
         res = {}
-        ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=epa.epa_batch(dc, pairs_d, Y)),
-                         args.steps, args.warmup)
-        r = res["r"].cpu()
-        ms_gjk = timed_steps(torch, dist, world, dev, lambda: gjk.gjk_distance_batch(dc, pairs), 3, 1)
-        line.update({"metric": "epa_pairs_per_s", "value": world * n / (ms * 1e-3), "unit": "pairs/s",
-                     "ms_per_step": ms,
-                     "config": {"workload": "C3: EPA on intersecting convex hulls, 64-256 vertices, "
-                                            "4-point GJK simplex", "pairs_per_gpu": n,
-                                "hull_pairs_generated": n_pairs},
-                     "mean_epa_iterations": float(r["iters"].mean()),
-                     "max_faces_assert_rate": float((r["status"] == 7).mean()),
-                     "converged_rate": float(r["success"].mean()),
-                     "gjk_hull_pairs_per_s": world * n_pairs / (ms_gjk * 1e-3)})
-        if rank == 0 and not args.no_cpu_baseline:
-            from oracle import cpu_oracle
-            m = min(n, 20000)
-            threads = cpu_oracle.max_threads()
-            cpu_oracle.prepare(cs)
+
+        def gather():
+            res["g"] = parallel.all_gather_varlen(buf[:count], out=gathered)
+
+        def whole():
+            bvh.rebuild()
+            bvh.overlap_unique_async(buf, begin, end - begin)
+            gather()
+        gather_ms = timed_steps(torch, dist, world, dev, gather, steps, 3) if world > 1 else 0.0
+        whole_ms = timed_steps(torch, dist, world, dev, whole, steps, 3)
+        recv_bytes = (total - count) * 8.0
+        # the ordered form the reference returns (both orientations + (i, i)) for continuity with round 1
+        full_buf = torch.empty((2 * total + n, 2), dtype=torch.int32, device=dev) if world == 1 else None
+        ordered_ms = None
+        if world == 1:
+            ordered_ms = timed_steps(torch, dist, world, dev, lambda: bvh.overlap_async(
+                bvh.aabbs, full_buf, order=bvh.leaf_order(), packet=True), 3, 2)
+            del full_buf
+        q_bytes = (end - begin) * 64.0 + count * 8.0 + visits * 32.0
+        q_bytes_min = (end - begin) * 64.0 + count * 8.0 + min(visits * 32.0, n * 96.0)
+        entry = {
+            "center_scale": scale, "unique_overlap_pairs": total,
+            "ordered_form_pairs": 2 * total + n, "replicas_identical": same,
+            "node_visits": total_visits, "traversal": "self query, 8-wide packets",
+            "build_ms": build_ms, "query_ms": query_ms, "gather_ms": gather_ms,
+            "build_query_gather_ms": whole_ms,
+            "build_aabbs_per_s": n / (build_ms * 1e-3),
+            "overlap_pairs_per_s": total / (query_ms * 1e-3),
+            "ordered_form_pairs_per_s": (2 * total + n) / (query_ms * 1e-3),
+            "overlap_pairs_per_s_with_gather": total / ((query_ms + gather_ms) * 1e-3),
+            "queries_per_s": n / (query_ms * 1e-3),
+            "gather": {"bytes_received_per_gpu": recv_bytes,
+                       "nvlink_gbs_per_gpu": recv_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+                       "nvlink_peak_gbs": NVLINK_PEAK_GBS,
+                       "frac": recv_bytes / (gather_ms * 1e-3) / 1e9 / NVLINK_PEAK_GBS if gather_ms else None},
+            "roofline_query": {"bound": "hbm", "achieved": q_bytes / (query_ms * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s",
+                               "frac": q_bytes / (query_ms * 1e-3) / 1e9 / hbm_peak,
+                               "bytes": "rank 0: Q*64 + pairs*8 + node_visits*32 (compact records); "
+                                        "re-visits are served by L1 / L2",
+                               "frac_compulsory": q_bytes_min / (query_ms * 1e-3) / 1e9 / hbm_peak,
+                               "bytes_compulsory": "Q*64 + pairs*8 + min(node_visits*32, n*96)"},
+            "roofline_build": {"bound": "hbm", "achieved": n * 176.0 / (build_ms * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s",
+                               "frac": n * 176.0 / (build_ms * 1e-3) / 1e9 / hbm_peak,
+                               "bytes": "176 B per primitive (SURVEY 8d)"},
+        }
+        if ordered_ms is not None:
+            entry["ordered_form_query_ms"] = ordered_ms   # d3d_bvh_overlap of all boxes (round-1 metric)
+        if world > 1:   # the gathered list is the union of the ranks' disjoint lists
+            keys = pair_keys(torch, res["g"][0], n)
+            entry["gathered_pairs_unique"] = bool(torch.unique(keys).numel() == total)
+            del keys
+        else:
+            # set parity at full size against an independent kernel: brute force over all n^2 boxes
             t0 = time.perf_counter()
-            ref = cpu_oracle.epa(cs, pairs_d[:m].cpu().numpy(), Y[:m].cpu().numpy(), n_threads=threads)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "sample": "first %d EPA pairs" % m}
-            ok = ref["status"] != 7
-            line["parity_on_cpu_sample"] = {
-                "pairs": m, "bit_exact_mtv": bool(np.array_equal(r["mtv"][:m][ok], ref["mtv"][ok])),
-                "status_equal": bool(np.array_equal(r["status"][:m], ref["status"]))}
-    elif args.workload == "selfcollision":
-        # C4: robot arm (6 revolute joints, 8 cylinders), q ~ U(-pi, pi)^6
-        from distance3d_b200 import broad_phase, self_collision
-        from distance3d_b200.urdf import UrdfTransformManager
-        data = os.path.join(REPO, "tests", "data")
-        tm = UrdfTransformManager()
-        with open(os.path.join(data, "robot_arm.urdf")) as f:
-            tm.load_urdf(f.read(), mesh_path=data)
-        bvh = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
-        bvh.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
-        model = self_collision.RobotModel(tm, bvh)
-        n = args.items or 2000000
-        q = torch.from_numpy(rs.uniform(-np.pi, np.pi, size=(n, 6))).to(dev)
-        res = {}
-        ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=model.detect_batch(q)),
-                         args.steps, args.warmup)
-        mask, n_cand = res["r"]
-        line.update({"metric": "self_collision_configurations_per_s", "value": world * n / (ms * 1e-3),
-                     "unit": "configurations/s", "ms_per_step": ms,
-                     "config": {"workload": "C4: URDF arm (6 joints, 8 cylinders, 17 candidate pairs), "
-                                            "FK + AABB + white-list filter + GJK intersection",
-                                "configurations_per_gpu": n},
-                     "colliding_fraction": float((mask.sum(dim=1) > 0).double().mean().item()),
-                     "narrow_phase_candidates_per_configuration": n_cand / n})
-        if rank == 0 and not args.no_cpu_baseline:
-            from oracle import cpu_oracle
-            m = min(n, 200000)
-            threads = cpu_oracle.max_threads()
-            kin = tm.compile_kinematics(model.frames, "origin")
-            qs = q[:m].cpu().numpy()
-            t0 = time.perf_counter()
-            ref_mask, _ = cpu_oracle.self_collision_masks(model.template, kin, model.pattern, qs, threads)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": m / dt, "unit": "configurations/s", "cores": threads,
-                                    "kind": "port", "sample": "first %d configurations" % m}
-            line["parity_on_cpu_sample"] = {
-                "configurations": m,
-                "mask_agreement": float((mask[:m].cpu().numpy() == ref_mask).mean())}
-    else:
-        # C5: mixed shapes, LBVH broad phase + GJK + EPA
-        n = args.items or 2000000
-        scale = 0.33 * n ** (1.0 / 3.0)   # ~ 10-30 AABB overlaps per shape
-        cs = d3random.random_collider_set(rs, n, names=d3random.PRIMITIVES + ("mesh",),
-                                          center_scale=scale, hull_vertices=(10, 10))
-        dc = cs.device(dev)
-        res = {}
-        ms = timed_steps(torch, dist, world, dev,
-                         lambda: res.update(r=pipeline.collide(dc, shard=False)), args.steps, args.warmup)
-        r = res["r"]
-        line.update({"metric": "pipeline_shapes_per_s", "value": world * n / (ms * 1e-3), "unit": "shapes/s",
-                     "ms_per_step": ms,
-                     "config": {"workload": "C5: mixed random shapes (5 primitives + 10-vertex hulls), LBVH build + "
-                                            "all-overlap + GJK distance on candidates + EPA on hits",
-                                "shapes_per_gpu": n, "center_scale": scale},
-                     "aabb_overlaps_per_shape": r.n_overlaps / n,
-                     "candidate_pairs": int(r.candidates.shape[0]),
-                     "candidate_pairs_per_s": world * int(r.candidates.shape[0]) / (ms * 1e-3),
-                     "contacts": int(r.hits.numel()),
-                     "epa_pairs": 0 if r.epa is None else int(r.epa_index.numel())})
-        if rank == 0 and not args.no_cpu_baseline:
-            # reference algorithms on a bounded sample: incremental tree + stack queries, GJK, EPA
-            from oracle import cpu_oracle
-            m = min(n, 50000)
-            threads = cpu_oracle.max_threads()
-            sub = d3random.random_collider_set(np.random.RandomState(args.seed), m,
-                                               names=d3random.PRIMITIVES + ("mesh",),
-                                               center_scale=0.33 * m ** (1.0 / 3.0), hull_vertices=(10, 10))
-            t0 = time.perf_counter()
-            A = cpu_oracle.aabb(sub)
-            tree = cpu_oracle.Tree()
-            tree.insert_aabbs(A)
-            pr = tree.query(A)
-            cand = pr[pr[:, 0] < pr[:, 1]]
-            g = cpu_oracle.gjk_distance(sub, cand, n_threads=threads)
-            sel = (g["dist"] == 0.0) & (g["n_points"] == 4)
-            cpu_oracle.epa(sub, cand[sel], g["Y"][sel], n_threads=threads)
-            dt = time.perf_counter() - t0
-            gpu = pipeline.collide(sub, shard=False)
-            line["cpu_baseline"] = {"value": m / dt, "unit": "shapes/s", "cores": threads, "kind": "port",
-                                    "sample": "%d shapes at the same density (tree build / query single-threaded, "
-                                              "GJK / EPA on all threads)" % m}
-            line["parity_on_cpu_sample"] = {
-                "shapes": m, "candidates_equal": bool(len(cand) == gpu.candidates.shape[0]),
-                "contacts_equal": bool(int((g["dist"] == 0.0).sum()) == gpu.hits.numel())}
-    if rank == 0:
-        print(json.dumps(line))
+            bp, bc = aabb_tree.brute_force_pairs(aabb, aabb, capacity=2 * total + n + 16)
+            kb = torch.sort(pair_keys(torch, bp[bp[:, 0] < bp[:, 1]], n))[0]
+            kl = torch.sort(pair_keys(torch, buf[:count], n))[0]
+            entry["parity_vs_brute_force"] = {"boxes": n, "brute_pairs": int(bc),
+                                              "sets_equal": bool(bc == 2 * total + n and torch.equal(kb, kl)),
+                                              "seconds": time.perf_counter() - t0}
+            del bp, kb, kl
+        out[name] = entry
+        del buf, gathered, bvh, pairs, res
+        torch.cuda.empty_cache()
+    if rank == 0 and not args.no_cpu_baseline:
+        # reference algorithm (incremental tree + per-box stack query) on a bounded sample
+        from oracle import cpu_oracle
+        m = min(n, 50000)
+        A = cpu_oracle.aabb(make_capsules(m, 2.0 * (m / 2000.0) ** (1.0 / 3.0)))
+        t0 = time.perf_counter()
+        tree = cpu_oracle.Tree()
+        tree.insert_aabbs(A)
+        t1 = time.perf_counter()
+        ref_pairs = tree.query(A)
+        t2 = time.perf_counter()
+        out["cpu_baseline"] = {
+            "kind": "port", "cores": 1, "sample": "%d capsules at constant density" % m,
+            "build_aabbs_per_s": m / (t1 - t0), "queries_per_s": m / (t2 - t1),
+            "overlap_pairs_per_s": len(ref_pairs) / (t2 - t1)}
+    return out
+
+
+def block_epa(args, torch, dist, rank, world, dev):
+    """C3: EPA on intersecting convex-hull pairs with 64-256 vertices each, args.epa_pairs per GPU."""
+    from distance3d_b200 import gjk, epa, random as d3random
+    want = args.epa_pairs
+    n_gen = int(want * 1.06) + 1024          # ~97 % of the generated pairs intersect with a full simplex
+    dc = d3random.random_collider_set_device(args.seed + 7 + 1000 * rank, 2 * n_gen, names=("mesh",),
+                                             center_scale=0.5, hull_vertices=(64, 256), hull_library=4096,
+                                             device=dev)
+    pairs = torch.arange(2 * n_gen, dtype=torch.int32, device=dev).reshape(n_gen, 2)
+    g = gjk.gjk_distance_batch(dc, pairs, want_points=False)
+    ms_gjk = timed_steps(torch, dist, world, dev, lambda: gjk.gjk_distance_batch(dc, pairs, out=g), 2, 1)
+    sel = torch.nonzero((g.dist == 0.0) & (g.n_points == 4)).flatten()[:want]
+    n = int(sel.numel())
+    pairs_d = pairs[sel].contiguous()
+    Y = g.simplex[sel].contiguous()
+    del g
+    res = {}
+    gathered = torch.empty((world * n, 3), dtype=torch.float64, device=dev) if world > 1 else None
+    same_n = all_sum(torch, dist, world, dev, n) == world * n
+
+    def step():
+        res["r"] = epa.epa_batch(dc, pairs_d, Y)
+        if world > 1 and same_n:
+            dist.all_gather_into_tensor(gathered, res["r"].mtv)
+    ms = timed_steps(torch, dist, world, dev, step, args.extra_steps, 3)
+    total = all_sum(torch, dist, world, dev, n)
+    r = res["r"]
+    out = {"metric": "epa_pairs_per_s", "value": total / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+           "scaling": "weak",
+           "config": {"workload": "C3: EPA on intersecting convex hulls, 64-256 vertices, 4-point GJK simplex, "
+                                  "two fresh hulls per pair (4096 shapes, unique poses), center_scale 0.5",
+                      "pairs_per_gpu": n, "hull_pairs_generated": n_gen,
+                      "vertex_pool_gb": float(dc.verts.numel() * 8 / 1e9),
+                      "collective": "all_gather_into_tensor of mtv inside the step" if world > 1 else "none"},
+           "mean_epa_iterations": float(r.iters.double().mean().item()),
+           "max_faces_assert_rate": float((r.status == 7).double().mean().item()),
+           "converged_rate": float(r.success.double().mean().item()),
+           "gjk_hull_pairs_per_s": world * n_gen / (ms_gjk * 1e-3)}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_oracle
+        m = min(n, 20000)
+        threads = cpu_oracle.max_threads()
+        sub_pairs = pairs_d[:m]
+        idx = sub_pairs.reshape(-1)
+        cs = d3random.device_set_to_host(dc, idx)
+        host_pairs = np.arange(2 * m, dtype=np.int32).reshape(m, 2)
+        t0 = time.perf_counter()
+        ref = cpu_oracle.epa(cs, host_pairs, Y[:m].cpu().numpy(), n_threads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "sample": "first %d EPA pairs of rank 0" % m}
+        ok = ref["status"] != 7
+        out["parity_on_cpu_sample"] = {
+            "pairs": m, "bit_exact_mtv": bool(np.array_equal(r.mtv[:m].cpu().numpy()[ok], ref["mtv"][ok])),
+            "status_equal": bool(np.array_equal(r.status[:m].cpu().numpy(), ref["status"]))}
+    del dc, Y, pairs_d, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def block_self_collision(args, torch, dist, rank, world, dev):
+    """C4: robot arm (6 revolute joints, 8 cylinders), q ~ U(-pi, pi)^6, args.configurations per GPU."""
+    from distance3d_b200 import broad_phase, self_collision
+    from distance3d_b200.urdf import UrdfTransformManager
+    data = os.path.join(REPO, "tests", "data")
+    tm = UrdfTransformManager()
+    with open(os.path.join(data, "robot_arm.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=data)
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
+    bvh.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
+    model = self_collision.RobotModel(tm, bvh)
+    n = args.configurations
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed + 11 + 1000 * rank)
+    q = (torch.rand((n, 6), generator=gen, device=dev, dtype=torch.float64) * 2.0 - 1.0) * np.pi
+    res = {}
+    gathered = torch.empty((world * n, model.n_frames), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        res["r"] = model.detect_batch(q)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res["r"][0])
+    ms = timed_steps(torch, dist, world, dev, step, args.extra_steps, 3)
+    mask, n_cand = res["r"]
+    out = {"metric": "self_collision_configurations_per_s", "value": world * n / (ms * 1e-3),
+           "unit": "configurations/s", "ms_per_step": ms, "scaling": "weak",
+           "config": {"workload": "C4: URDF arm (6 joints, 8 cylinders, 17 candidate pairs), "
+                                  "FK + AABB + white-list filter + GJK intersection",
+                      "configurations_per_gpu": n,
+                      "collective": "all_gather_into_tensor of the 8-bit masks inside the step" if world > 1 else "none"},
+           "colliding_fraction": float((mask.sum(dim=1) > 0).double().mean().item()),
+           "narrow_phase_candidates_per_configuration": n_cand / n}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_oracle
+        m = min(n, 200000)
+        threads = cpu_oracle.max_threads()
+        kin = tm.compile_kinematics(model.frames, "origin")
+        qs = q[:m].cpu().numpy()
+        t0 = time.perf_counter()
+        ref_mask, _ = cpu_oracle.self_collision_masks(model.template, kin, model.pattern, qs, threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "configurations/s", "cores": threads,
+                               "kind": "port", "sample": "first %d configurations" % m}
+        out["parity_on_cpu_sample"] = {
+            "configurations": m,
+            "masks_equal": bool(np.array_equal(mask[:m].cpu().numpy(), ref_mask))}
+    del q, res, gathered
+    torch.cuda.empty_cache()
+    return out
+
+
+def block_pipeline(args, torch, dist, rank, world, dev):
+    """C5: args.shapes mixed shapes per GPU; LBVH over ALL shapes on every GPU (replica), this
+    rank's leaves as queries, GJK on the candidates, EPA on the hits, contacts all-gathered."""
+    from distance3d_b200 import pipeline, parallel, random as d3random
+    n = args.shapes * world
+    names = d3random.PRIMITIVES + ("mesh",)
+    scale = 0.33 * n ** (1.0 / 3.0)   # ~ 10-30 AABB overlaps per shape
+    dc = d3random.random_collider_set_device(args.seed + 13, n, names=names, center_scale=scale,
+                                             hull_vertices=(10, 10), device=dev)
+    same = replicas_identical(torch, dist, world, dc.pose)
+    res = {}
+    cap = int(12 * args.shapes)
+    stage = {}
+
+    def step():
+        r = pipeline.collide(dc, shard=True, candidate_capacity=cap, timings=stage)
+        contacts = r.candidates[r.hits]
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        res["contacts"], res["counts"] = parallel.all_gather_varlen(contacts)
+        if r.epa is not None and world > 1:
+            res["mtv"], _ = parallel.all_gather_varlen(r.epa.mtv)
+        ev2 = torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        stage["gather"] = (ev, ev2)
+        res["r"] = r
+    ms = timed_steps(torch, dist, world, dev, step, args.extra_steps, 3)
+    torch.cuda.synchronize()
+    r = res["r"]
+    cand_total = all_sum(torch, dist, world, dev, r.candidates.shape[0])
+    hits_total = all_sum(torch, dist, world, dev, r.hits.numel())
+    stages_ms = {k: float(a.elapsed_time(b)) for k, (a, b) in stage.items()}
+    out = {"metric": "pipeline_shapes_per_s", "value": n / (ms * 1e-3), "unit": "shapes/s", "ms_per_step": ms,
+           "scaling": "weak (queries per GPU fixed, the replicated tree grows with N)",
+           "config": {"workload": "C5: mixed random shapes (5 primitives + 10-vertex hulls), LBVH build + self "
+                                  "overlap query + GJK distance on candidates + EPA on hits + contact all-gather",
+                      "shapes_total": n, "query_shapes_per_gpu": args.shapes, "center_scale": scale,
+                      "replicas_identical": same},
+           "aabb_overlaps_per_shape": 2.0 * cand_total / n,
+           "candidate_pairs": int(cand_total),
+           "candidate_pairs_per_s": cand_total / (ms * 1e-3),
+           "contacts": int(hits_total),
+           "gathered_contacts": int(res["contacts"].shape[0]),
+           "stage_ms_rank0": stages_ms,
+           "epa_share_of_step": stages_ms.get("epa", 0.0) / ms}
+    if rank == 0 and not args.no_cpu_baseline:
+        # reference algorithms on a bounded sample: incremental tree + stack queries, GJK, EPA
+        from oracle import cpu_oracle
+        m = min(n, 50000)
+        threads = cpu_oracle.max_threads()
+        sub_d = d3random.random_collider_set_device(args.seed + 17, m, names=names,
+                                                    center_scale=0.33 * m ** (1.0 / 3.0),
+                                                    hull_vertices=(10, 10), device=dev)
+        sub = d3random.device_set_to_host(sub_d)
+        t0 = time.perf_counter()
+        A = cpu_oracle.aabb(sub)
+        tree = cpu_oracle.Tree()
+        tree.insert_aabbs(A)
+        pr = tree.query(A)
+        cand = pr[pr[:, 0] < pr[:, 1]]
+        g = cpu_oracle.gjk_distance(sub, cand, n_threads=threads)
+        selc = (g["dist"] == 0.0) & (g["n_points"] == 4)
+        e = cpu_oracle.epa(sub, cand[selc], g["Y"][selc], n_threads=threads)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            gpu = None   # collide() would shard; the sample parity is checked in the N = 1 run
+        else:
+            gpu = pipeline.collide(sub_d, shard=False)
+        out["cpu_baseline"] = {"value": m / dt, "unit": "shapes/s", "cores": threads, "kind": "port",
+                               "sample": "%d shapes at the same density (tree build / query single-threaded, "
+                                         "GJK / EPA on all threads)" % m}
+        if gpu is not None:
+            gc = gpu.candidates.cpu().numpy()
+            ko = np.argsort(gc[:, 0].astype(np.int64) * m + gc[:, 1])
+            kr = np.argsort(cand[:, 0].astype(np.int64) * m + cand[:, 1])
+            sets_equal = len(gc) == len(cand) and bool(np.array_equal(gc[ko], cand[kr]))
+            gd = gpu.gjk.dist.cpu().numpy()
+            out["parity_on_cpu_sample"] = {
+                "shapes": m, "candidate_sets_equal": sets_equal,
+                "distances_bit_exact": bool(sets_equal and np.array_equal(gd[ko], g["dist"][kr])),
+                "contact_sets_equal": bool(sets_equal and np.array_equal(gd[ko] == 0.0, g["dist"][kr] == 0.0))}
+    del dc, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def six_type_mix(args, torch, dist, world, dev):
+    """SURVEY 8d "report both": C1 with 10-vertex convex hulls as the sixth type."""
+    from distance3d_b200 import gjk, random as d3random
+    n = 1 << 20
+    dc = d3random.random_collider_set_device(args.seed + 19, 2 * n, names=d3random.PRIMITIVES + ("mesh",),
+                                             hull_vertices=(10, 10), device=dev)
+    pairs = torch.arange(2 * n, dtype=torch.int32, device=dev).reshape(n, 2)
+    out = gjk.gjk_distance_batch(dc, pairs)
+    ms = timed_steps(torch, dist, world, dev, lambda: gjk.gjk_distance_batch(dc, pairs, out=out), 5, 3)
+    return {"value": world * n / (ms * 1e-3), "unit": "pairs/s", "pairs_per_gpu": n,
+            "types": "sphere, ellipsoid, capsule, cylinder, box, 10-vertex convex hull (randn_convex default)",
+            "mean_gjk_iterations": float(out.iters.double().mean().item())}
 
 
 def cpu_baseline(cs, pairs, sample):
@@ -451,6 +585,30 @@ def workload_config(args, pairs_per_gpu):
                          % (pairs_per_gpu * BYTES_PER_PAIR / 1e6)}
 
 
+def ncu_traffic_per_pair():
+    """DRAM bytes per pair of the dominant GJK kernel from the committed ncu summary
+    (profiles/...: `dram__bytes_read.sum`, `dram__bytes_write.sum`, and the `pairs:` line the
+    capture script writes).  Returns (bytes per pair | None, source)."""
+    path = os.path.join(REPO, NCU_PROFILE)
+    try:
+        rd = wr = pairs = None
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        with open(path) as f:
+            for ln in f:
+                parts = ln.split()
+                if ln.startswith("pairs:"):
+                    pairs = float(parts[1])
+                elif parts and parts[0] == "dram__bytes_read.sum" and len(parts) >= 3:
+                    rd = float(parts[2].replace(",", "")) * scale.get(parts[1], 1.0)
+                elif parts and parts[0] == "dram__bytes_write.sum" and len(parts) >= 3:
+                    wr = float(parts[2].replace(",", "")) * scale.get(parts[1], 1.0)
+        if rd is None or wr is None or not pairs:
+            return None, NCU_PROFILE + " (incomplete)"
+        return (rd + wr) / pairs, NCU_PROFILE
+    except OSError:
+        return None, NCU_PROFILE + " (missing)"
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -470,8 +628,21 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    if args.workload != "gjk":
-        secondary_workload(args, torch, dist, rank, world, dev)
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if args.only:
+        block = {"broad": lambda: block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak),
+                 "epa": lambda: block_epa(args, torch, dist, rank, world, dev),
+                 "selfcollision": lambda: block_self_collision(args, torch, dist, rank, world, dev),
+                 "pipeline": lambda: block_pipeline(args, torch, dist, rank, world, dev)}[args.only]()
+        if rank == 0:
+            block["n_gpus"] = world
+            print(json.dumps(block))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -569,17 +740,22 @@ def main():
     e2e_ok = bool(np.array_equal(e2e_res["dist"].numpy(), res["dist"]))
     del pipe
 
+    # ---- BASELINE configs[1..4] at their stated sizes, on all ranks ----------
+    extras = {}
+    if not args.no_extra:
+        del dc, out, pairs_d, host
+        torch.cuda.empty_cache()
+        extras["six_type_mix"] = six_type_mix(args, torch, dist, world, dev)
+        extras["broad_phase"] = block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak)
+        extras["epa"] = block_epa(args, torch, dist, rank, world, dev)
+        extras["self_collision"] = block_self_collision(args, torch, dist, rank, world, dev)
+        extras["pipeline"] = block_pipeline(args, torch, dist, rank, world, dev)
+
     if rank == 0:
         fp64_peak = measure_fp64_peak(torch, _lib)
         per_gpu = value / world
         achieved = per_gpu * mean_iters * FLOP_PER_ITER / 1e12
-        peaks = {}
-        try:
-            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic_per_pair, traffic_src = ncu_traffic_per_pair()
         line = {
             "metric": "gjk_distance_pairs_per_s", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -590,11 +766,11 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of k_gjk_thread<0> from the ncu --set
-                # full capture of a 1 Mi-pair launch (profiles/r01_ncu_k_gjk_thread_v6_primitive_instance.txt:
-                # 497.1 MB + 228.5 MB incl. the parked simplices), scaled to this launch; algorithmic
-                # bytes are 496 B per pair
-                "traffic": n * NCU_DRAM_BYTES_PER_PAIR, "traffic_unit": "bytes per launch",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, read from the
+                # committed ncu --set full summary (per pair of the captured launch, scaled to this
+                # launch); algorithmic bytes are 496 B per pair
+                "traffic": None if traffic_per_pair is None else n * traffic_per_pair,
+                "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "kernel": "k_gjk_thread<0, primitive instance>",
                 "note": "algorithmic flop = pairs x mean_iters x 350 (SURVEY 8d); peak = FP64 FMA "
                         "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -612,11 +788,8 @@ def main():
             "fp32_mode": fp32_mode,
             "clocks": clocks,
         }
-        if not args.no_extra:
-            del dc, out, pairs_d, host
-            torch.cuda.empty_cache()
-            line["broad_phase"] = bench_broad_phase(args, torch, _lib, hbm_peak,
-                                                    cpu=not args.no_cpu_baseline)
+        line.update(extras)
+        line["numba_reference"] = NUMBA_REFERENCE
         if not args.no_cpu_baseline:
             cpu_value, threads, sample_n, ref = cpu_baseline(cs, pairs, args.cpu_sample)
             line["cpu_baseline"] = {

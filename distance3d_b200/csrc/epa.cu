@@ -138,7 +138,7 @@ struct WarpMem {
 D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v2 - v0)); }
 
 #ifndef EPA_BLOCKS_PER_SM
-#define EPA_BLOCKS_PER_SM 8  // 64 registers, 32 warps per SM; measured Mpairs/s at 5/6/7/8: 20.1/20.5/21.4/21.9
+#define EPA_BLOCKS_PER_SM 6  // 80 registers, 24 warps per SM; r02 sweep (scripts/r02_run2.sh) C3 / C5 ms at 4,5,6,8: 7.3 7.7 7.2 7.8 / 493 491 481 494
 #endif
 template <int MF>
 __global__ void __launch_bounds__(EPA_WARPS * 32, EPA_BLOCKS_PER_SM)

@@ -4,7 +4,8 @@ The hot path has no exchange step: pairs, queries and joint configurations are
 independent, so every rank works on a contiguous shard with a replicated collider
 set / BVH.  The only collective is the variable-length
 all-gather of result lists (contact lists, overlap pairs) when the caller wants them
-in one place: an all-gather of the int64 counts followed by a padded all-gather.
+in one place: an all-gather of the int64 counts, an exclusive scan, and one group of
+exact-size point-to-point transfers into the slices of a single output buffer.
 """
 import numpy as np
 
@@ -34,27 +35,45 @@ def shard_counts(n, world_size):
             for r in range(world_size)]
 
 
-def all_gather_varlen(t, group=None):
-    """Concatenate tensors whose first dimension differs between ranks.
+def all_gather_varlen(t, group=None, out=None):
+    """Concatenate tensors whose first dimension differs between ranks; every rank gets all.
 
-    Works on CPU tensors (gloo) and CUDA tensors (NCCL).  Returns the
-    concatenation in rank order and the list of per-rank counts.
+    Counts first (one small all-gather), then an exclusive scan gives every rank its slice of
+    ONE output buffer and the slices travel as a single group of point-to-point transfers of
+    exactly their size (NCCL: ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd over NVLink;
+    gloo on CPU for the tests) - no padding to the largest rank, no staging copies.  Works on
+    CPU and CUDA tensors.  Returns the concatenation in rank order and the per-rank counts;
+    `out` (optional) is a buffer with room for the total that is re-used between calls.
     """
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t, [int(t.shape[0])]
-    ws = dist.get_world_size(group)
+    ws, rank = dist.get_world_size(group), dist.get_rank(group)
+    t = t.contiguous()
     count = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    counts = [torch.zeros_like(count) for _ in range(ws)]
-    dist.all_gather(counts, count, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    padded = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    padded[:t.shape[0]] = t
-    parts = [torch.empty_like(padded) for _ in range(ws)]
-    dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0), counts
+    counts_t = torch.empty(ws, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(counts_t, count, group=group)
+    counts = [int(c) for c in counts_t.cpu().tolist()]
+    offsets = np.concatenate(([0], np.cumsum(counts)))
+    total = int(offsets[-1])
+    if out is None or out.shape[0] < total or out.dtype != t.dtype or tuple(out.shape[1:]) != tuple(t.shape[1:]):
+        out = torch.empty((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    full = out[:total]
+    ops = []
+    for peer in range(ws):
+        if peer == rank:
+            continue
+        if counts[rank]:
+            ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, peer) if group else peer, group))
+        if counts[peer]:
+            ops.append(dist.P2POp(dist.irecv, full[offsets[peer]:offsets[peer + 1]],
+                                  dist.get_global_rank(group, peer) if group else peer, group))
+    full[offsets[rank]:offsets[rank + 1]].copy_(t)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return full, counts
 
 
 def gjk_distance_sharded(colliders, pairs, gather=False, **kwargs):
@@ -79,6 +98,18 @@ def overlap_sharded(bvh, query, gather=True):
     if count:
         pairs = pairs.clone()
         pairs[:, 1] += begin
+    if not gather:
+        return pairs, count
+    full, counts = all_gather_varlen(pairs)
+    return full, int(sum(counts))
+
+
+def overlap_unique_sharded(bvh, gather=True, out=None):
+    """Self query with a replicated BVH: this rank walks its contiguous range of leaves
+    (`Lbvh.overlap_unique`), so the ranks' lists of unordered pairs are disjoint; with
+    gather=True every rank receives the whole list."""
+    begin, end = shard_range(bvh.n)
+    pairs, count = bvh.overlap_unique(begin, end - begin, out=out)
     if not gather:
         return pairs, count
     full, counts = all_gather_varlen(pairs)

@@ -25,7 +25,8 @@ class PipelineResult:
         self.epa_index = None           # int64[H] indices into candidates of the EPA rows
 
 
-def collide(colliders, penetration=True, distance_threshold=None, shard=True, candidate_capacity=None):
+def collide(colliders, penetration=True, distance_threshold=None, shard=True, candidate_capacity=None,
+            timings=None):
     """Broad phase + narrow phase for all colliders of a packed set.
 
     Returns a :class:`PipelineResult`.  `distance_threshold` is only used to report
@@ -33,15 +34,31 @@ def collide(colliders, penetration=True, distance_threshold=None, shard=True, ca
     ranks (shard=True) every rank builds the same tree and walks its own contiguous range of
     leaves; a candidate pair belongs to the rank that owns its earlier leaf, so the ranks'
     candidate lists are disjoint and their union is the single-GPU list.
+    `timings` (optional dict) receives a (start, end) CUDA event pair per stage.
     """
     torch = _lib.torch_cuda()
+
+    def mark(name, start=None):
+        if timings is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            timings[name] = (start, ev)
+        return ev
+
     dc = _lib.as_device_colliders(colliders)
+    t0 = mark(None)
     aabb = _lib.aabb_device(dc)
+    t1 = mark("aabb", t0)
     bvh = aabb_tree.Lbvh(aabb)
+    t2 = mark("bvh_build", t1)
     begin, end = parallel.shard_range(dc.n) if shard else (0, dc.n)
     # every unordered pair once, straight from the traversal (no (i, i), no mirrored copy)
     candidates, count = bvh.overlap_unique(begin, end - begin, capacity=candidate_capacity)
+    t3 = mark("overlap", t2)
     g = _gjk.gjk_distance_batch(dc, candidates)
+    t4 = mark("gjk", t3)
     bad = int((g.status >= _gjk.STATUS_SANITY_FAILED).sum().item())
     if bad:
         raise RuntimeError("%d candidate pairs ended GJK without a verdict" % bad)
@@ -51,5 +68,7 @@ def collide(colliders, penetration=True, distance_threshold=None, shard=True, ca
         # EPA is defined where GJK ended with a full simplex; the others
         # come back with status 8
         res.epa_index = hits
+        t5 = mark(None)
         res.epa = _epa.epa_batch(dc, candidates[hits], g.simplex[hits], n_points=g.n_points[hits])
+        mark("epa", t5)
     return res

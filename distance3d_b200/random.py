@@ -246,6 +246,139 @@ def random_meshgraph_set(rs, n_meshes, n_mesh_colliders, n_other, hull_vertices=
                                                             center_scale=center_scale)])
 
 
+# ---------------------------------------------------------------------------
+# Device-side generation (torch): the same distributions as above, drawn in HBM.  Used for
+# the large benchmark sets (16 M shapes would take minutes on the host); the streams differ
+# from the numpy ones, the distributions do not.  A given (seed, device type) yields the same
+# set on every GPU, which is how all ranks of a job hold identical replicas.
+def random_transforms_device(gen, n, device):
+    import torch
+    S = torch.randn((n, 6), generator=gen, device=device, dtype=torch.float64)
+    w = S[:, :3]
+    theta = torch.linalg.norm(w, dim=1)
+    safe = torch.where(theta > 0.0, theta, torch.ones_like(theta))
+    a = w / safe[:, None]
+    v = S[:, 3:] / safe[:, None]
+    K = torch.zeros((n, 3, 3), device=device, dtype=torch.float64)
+    K[:, 0, 1] = -a[:, 2]; K[:, 0, 2] = a[:, 1]
+    K[:, 1, 0] = a[:, 2]; K[:, 1, 2] = -a[:, 0]
+    K[:, 2, 0] = -a[:, 1]; K[:, 2, 1] = a[:, 0]
+    K2 = K @ K
+    s = torch.sin(theta)[:, None, None]
+    c = torch.cos(theta)[:, None, None]
+    th = theta[:, None, None]
+    eye = torch.eye(3, device=device, dtype=torch.float64)[None]
+    R = eye + s * K + (1.0 - c) * K2
+    V = eye * th + (1.0 - c) * K + (th - s) * K2
+    T = torch.zeros((n, 4, 4), device=device, dtype=torch.float64)
+    T[:, :3, :3] = R
+    T[:, :3, 3] = torch.einsum("nij,nj->ni", V, v)
+    T[:, 3, 3] = 1.0
+    return T
+
+
+def random_collider_set_device(seed, n, names=PRIMITIVES, center_scale=1.0, size_scale=1.0,
+                               hull_vertices=(10, 10), hull_library=None, hull_min_radius=1.0,
+                               device=None, chunk=1 << 21):
+    """Device-resident counterpart of :func:`random_collider_set`: returns
+    :class:`~distance3d_b200.pack.DeviceColliders` (nothing touches the host).  With
+    `hull_library` the hulls are re-posed copies of that many shapes; the world-frame vertex
+    pool is still unique per hull (the reference's ConvexHullVertices is a world-frame list)."""
+    import torch
+    device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    f64 = dict(device=device, dtype=torch.float64)
+    code = {"sphere": _pack.SPHERE, "ellipsoid": _pack.ELLIPSOID, "capsule": _pack.CAPSULE,
+            "cylinder": _pack.CYLINDER, "box": _pack.BOX, "mesh": _pack.HULL, "cone": _pack.CONE}
+    codes = torch.tensor([code[nm] for nm in names], dtype=torch.int32, device=device)
+    type_ = codes[torch.randint(len(names), (n,), generator=gen, device=device)]
+    pose = torch.empty((n, 4, 4), **f64)
+    for s0 in range(0, n, chunk):
+        pose[s0:s0 + chunk] = random_transforms_device(gen, min(chunk, n - s0), device)
+    pose[:, :3, 3] *= center_scale
+    param = (1.0 - torch.rand((n, 3), generator=gen, **f64)) * size_scale
+    is_sphere = type_ == _pack.SPHERE
+    pose[is_sphere, :3, :3] = torch.eye(3, **f64)
+    two = (type_ == _pack.SPHERE) | (type_ == _pack.CAPSULE) | (type_ == _pack.CYLINDER) | (type_ == _pack.CONE)
+    param[two, 2] = 0.0
+    param[is_sphere, 1] = 0.0
+    vert_len = torch.zeros(n, dtype=torch.int64, device=device)
+    vert_len[type_ == _pack.BOX] = 8
+    hull_idx = torch.nonzero(type_ == _pack.HULL).flatten()
+    nh = int(hull_idx.numel())
+    L = nh if hull_library is None else min(int(hull_library), nh)
+    if nh:
+        lib_len = torch.randint(hull_vertices[0], hull_vertices[1] + 1, (max(L, 1),), generator=gen, device=device)
+        lib_of = torch.arange(nh, device=device) % max(L, 1)
+        vert_len[hull_idx] = lib_len[lib_of]
+    vert_off = torch.cumsum(vert_len, 0) - vert_len
+    total = int(vert_len.sum().item())
+    if total >= 2 ** 31:
+        raise ValueError("vertex pool exceeds int32 offsets; shard the set")
+    verts = torch.zeros((max(total, 1), 3), **f64)
+    if nh:
+        # library shapes: points on an ellipsoid (randn_convex), local frame
+        lib_off = torch.cumsum(lib_len, 0) - lib_len
+        lib_total = int(lib_len.sum().item())
+        phis = torch.rand(lib_total, generator=gen, **f64) * np.pi
+        thetas = torch.rand(lib_total, generator=gen, **f64) * (2 * np.pi)
+        radii = hull_min_radius + (1.0 - torch.rand((max(L, 1), 3), generator=gen, **f64)) * size_scale
+        owner_lib = torch.repeat_interleave(torch.arange(max(L, 1), device=device), lib_len)
+        sp = torch.sin(phis)
+        lib_local = torch.stack((sp * torch.cos(thetas), sp * torch.sin(thetas), torch.cos(phis)), dim=1) * radii[owner_lib]
+        per = max(1, chunk // max(1, hull_vertices[1]))
+        for h0 in range(0, nh, per):     # world-frame copies, a slab of hulls at a time
+            hs = hull_idx[h0:h0 + per]
+            lens = vert_len[hs]
+            owner = torch.repeat_interleave(torch.arange(hs.numel(), device=device), lens)
+            first = torch.cumsum(lens, 0) - lens
+            within = torch.arange(int(lens.sum().item()), device=device) - first[owner]
+            src = lib_off[lib_of[h0:h0 + per]][owner] + within
+            Rm = pose[hs][owner]
+            world = torch.einsum("nij,nj->ni", Rm[:, :3, :3], lib_local[src]) + Rm[:, :3, 3]
+            verts[vert_off[hs][owner] + within] = world
+        pose[hull_idx] = torch.eye(4, **f64)
+        param[hull_idx] = 0.0
+    return _pack.DeviceColliders.from_tensors(type_, pose, param, vert_off.to(torch.int32),
+                                              vert_len.to(torch.int32), verts)
+
+
+def random_capsules_device(seed, n, center_scale=2.0, radius_scale=0.1, height_scale=0.5, device=None):
+    """BASELINE configs[1] (vis_capsules_benchmark.py:22-30 scaled up) generated in HBM."""
+    import torch
+    device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    pose = random_transforms_device(gen, n, device)
+    pose[:, :3, 3] *= center_scale
+    param = torch.zeros((n, 3), device=device, dtype=torch.float64)
+    param[:, 0] = (1.0 - torch.rand(n, generator=gen, device=device, dtype=torch.float64)) * radius_scale
+    param[:, 1] = (1.0 - torch.rand(n, generator=gen, device=device, dtype=torch.float64)) * height_scale
+    type_ = torch.full((n,), _pack.CAPSULE, dtype=torch.int32, device=device)
+    return _pack.DeviceColliders.from_tensors(type_, pose, param)
+
+
+def device_set_to_host(dc, idx=None):
+    """Host :class:`ColliderSet` with the colliders `idx` of a device set (all by default): the
+    CPU oracle consumes exactly the numbers the kernels saw."""
+    import torch
+    if idx is None:
+        idx = torch.arange(dc.n, device=dc.device)
+    idx = torch.as_tensor(idx, device=dc.device).long()
+    lens = dc.vert_len[idx].long()
+    offs = dc.vert_off[idx].long()
+    owner = torch.repeat_interleave(torch.arange(idx.numel(), device=dc.device), lens)
+    first = torch.cumsum(lens, 0) - lens
+    within = torch.arange(int(lens.sum().item()), device=dc.device) - first[owner]
+    verts = dc.verts[offs[owner] + within] if within.numel() else dc.verts[:0]
+    cs = _pack.ColliderSet(dc.type[idx].cpu().numpy(), dc.pose[idx].cpu().numpy(), dc.param[idx].cpu().numpy(),
+                           first.cpu().numpy(), lens.cpu().numpy(), verts.cpu().numpy(),
+                           None if dc.margin is None else dc.margin[idx].cpu().numpy())
+    cs.boxes_prepared = True   # box vertices were generated on the device (d3d_prepare)
+    return cs
+
+
 def random_pairs(rs, n_colliders, n_pairs):
     """Random (i, j) index pairs, i != j."""
     a = rs.randint(n_colliders, size=n_pairs)
