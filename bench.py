@@ -219,15 +219,15 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
     n = args.capsules
     steps = args.extra_steps
     out = {"capsules": n, "scaling": "strong",
-           "design": "replicated LBVH (built redundantly on every GPU), leaves sharded 1/N per GPU, "
+           "design": "replicated LBVH (built redundantly on every GPU), 128-leaf blocks dealt round-robin to the GPUs, "
                      "d3d_bvh_overlap_self: every unordered pair once; all-gather of exact-size slices"}
     for name, scale in (("dense", 2.0), ("constant_density", 2.0 * (n / 2000.0) ** (1.0 / 3.0))):
         dc = d3random.random_capsules_device(32, n, center_scale=scale, device=dev)
         aabb = _lib.aabb_device(dc)
         same = replicas_identical(torch, dist, world, aabb)
         bvh = aabb_tree.Lbvh(aabb)
-        begin, end = parallel.shard_range(n, rank, world)
-        pairs, count = bvh.overlap_unique(begin, end - begin, count_visits=True)
+        n_mine = len(range(rank, (n + 127) // 128, world)) * 128   # leaves of this rank's blocks
+        pairs, count = bvh.overlap_unique(rank, world, count_visits=True)
         visits = bvh.visits()
         buf = torch.empty((max(count, 1), 2), dtype=torch.int32, device=dev)
         total = int(all_sum(torch, dist, world, dev, count))
@@ -235,7 +235,7 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
         gathered = torch.empty((max(total, 1), 2), dtype=torch.int32, device=dev)
         build_ms = timed_steps(torch, dist, world, dev, lambda: bvh.rebuild(), steps, 3)
         query_ms = timed_steps(torch, dist, world, dev,
-                               lambda: bvh.overlap_unique_async(buf, begin, end - begin), steps, 3)
+                               lambda: bvh.overlap_unique_async(buf, rank, world), steps, 3)
         res = {}
 
         def gather():
@@ -243,7 +243,7 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
 
         def whole():
             bvh.rebuild()
-            bvh.overlap_unique_async(buf, begin, end - begin)
+            bvh.overlap_unique_async(buf, rank, world)
             gather()
         gather_ms = timed_steps(torch, dist, world, dev, gather, steps, 3) if world > 1 else 0.0
         whole_ms = timed_steps(torch, dist, world, dev, whole, steps, 3)
@@ -255,8 +255,8 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
             ordered_ms = timed_steps(torch, dist, world, dev, lambda: bvh.overlap_async(
                 bvh.aabbs, full_buf, order=bvh.leaf_order(), packet=True), 3, 2)
             del full_buf
-        q_bytes = (end - begin) * 64.0 + count * 8.0 + visits * 32.0
-        q_bytes_min = (end - begin) * 64.0 + count * 8.0 + min(visits * 32.0, n * 96.0)
+        q_bytes = n_mine * 64.0 + count * 8.0 + visits * 32.0
+        q_bytes_min = n_mine * 64.0 + count * 8.0 + min(visits * 32.0, n * 96.0)
         entry = {
             "center_scale": scale, "unique_overlap_pairs": total,
             "ordered_form_pairs": 2 * total + n, "replicas_identical": same,
@@ -705,39 +705,66 @@ def main():
     del out32
 
     # ---- end to end through the public API with HOST buffers ---------------
-    # distance3d_b200.stream.GjkDistanceStream: per step the batch's collider arrays and pairs
-    # travel from pinned host memory to the device, d3d_prepare + d3d_gjk_distance run, and
-    # dist / closest points / status travel back; two slots keep PCIe and the SMs busy at once.
+    # distance3d_b200.stream.GjkDistanceStream: per step the batch's collider records and pairs
+    # travel from pinned host memory to the device (compact wire format: a sphere is 4 doubles,
+    # not a 4x4 pose), d3d_unpack_colliders + d3d_prepare + d3d_gjk_distance run, and dist /
+    # closest points / status travel back; three slots keep PCIe and the SMs busy at once.
     from distance3d_b200 import stream as d3stream
-    host = d3stream.pin_batch(cs, pairs)
-    pipe = d3stream.GjkDistanceStream(len(cs), n, cs.n_vertices, slots=2, device=dev)
-    e2e_steps = max(4, min(args.steps, 8))
+    host = d3stream.pin_batch(cs, pairs, wire=True)
+    pipe = d3stream.GjkDistanceStream(len(cs), n, cs.n_vertices, slots=3, device=dev)
+    e2e_steps = max(6, min(args.steps, 9))
 
-    def e2e_run(k_steps):
-        prev = None
+    def e2e_run(k_steps, repack=False):
+        pending = []
         last = None
         for _ in range(k_steps):
-            ticket = pipe.submit(host)
-            if prev is not None:
-                last = pipe.result(prev)
-            prev = ticket
-        return pipe.result(prev)
+            if repack:   # the caller's structure-of-arrays set is packed and staged again every step
+                d3stream.pin_batch(cs, pairs, wire=True, out=host)
+            pending.append(pipe.submit(host))
+            if len(pending) == len(pipe.slots):
+                last = pipe.result(pending.pop(0))
+        while pending:
+            last = pipe.result(pending.pop(0))
+        return last
 
-    e2e_res = e2e_run(2)
-    barrier()
-    cur = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(cur)
-    e2e_res = e2e_run(e2e_steps)
-    pipe.drain_into(cur)
-    e1.record(cur)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n / (float(t.item()) * 1e-3)
+    def e2e_timed(k_steps, repack=False):
+        barrier()
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(cur)
+        r = e2e_run(k_steps, repack)
+        pipe.drain_into(cur)
+        e1.record(cur)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        # with host-side packing in the loop the device clock does not see the host time: take the
+        # larger of the two clocks
+        ms = max(e0.elapsed_time(e1), wall if repack else 0.0) / k_steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t.item())
+
+    e2e_res = e2e_run(3)
+    e2e_res, e2e_ms = e2e_timed(e2e_steps)
+    e2e_value = world * n / (e2e_ms * 1e-3)
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_ok = bool(np.array_equal(e2e_res["dist"].numpy(), res["dist"]))
+    _, e2e_pack_ms = e2e_timed(2, repack=True)
+    # PCIe reference: one large pinned host -> device copy on this GPU
+    probe_h = torch.empty(1 << 28, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(4):
+        probe_d.copy_(probe_h, non_blocking=True)
+    pe1.record()
+    barrier()
+    pcie_gbs = 4 * (1 << 28) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    del probe_h, probe_d
     del pipe
 
     # ---- BASELINE configs[1..4] at their stated sizes, on all ranks ----------
@@ -780,8 +807,15 @@ def main():
                 "hbm_frac": per_gpu * BYTES_PER_PAIR / 1e9 / hbm_peak,
             },
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "api": "stream.GjkDistanceStream (2 slots)",
-                    "result_equals_device_run": e2e_ok},
+                    "d2h_bytes_per_step": int(d2h),
+                    "api": "stream.GjkDistanceStream (3 slots, compact wire records)",
+                    "result_equals_device_run": e2e_ok,
+                    "h2d_bytes_per_pair": h2d / n, "h2d_bytes_per_pair_reference_layout": 336,
+                    "h2d_gbs_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
+                    "pcie_h2d_peak_gbs_measured": pcie_gbs,
+                    "value_including_host_packing": world * n / (e2e_pack_ms * 1e-3),
+                    "host_packing": "ColliderSet.wire() + copy into the pinned buffers every step "
+                                    "(numpy, one thread per rank)"},
             # k_pair_keys, k_bin_scan, k_bin_scatter, k_gjk_thread x2 (primitive / generic instance),
             # k_gjk_finish, k_gjk_warp
             "gpu_launches": 7 * args.steps,

@@ -129,32 +129,31 @@ class Lbvh:
             None, c_size(0), _lib.stream_ptr()))
         return out, self._count
 
-    def overlap_unique_async(self, out, first_leaf=0, n_leaves=None, packet=True, count_visits=False):
-        """The tree against its own leaves ``first_leaf .. first_leaf + n_leaves`` (positions in
-        Morton order; default: all): every unordered overlapping pair ONCE as (smaller, larger)
-        object index, no (i, i); one traversal in which a leaf only walks the part of the tree
-        behind itself (half the nodes and half the output of `overlap_self`).  Appends into
-        `out` int32[cap, 2] without synchronising the host; returns ``(out, count)`` with the
-        exact count as a device int64 tensor (pairs beyond cap are dropped).  Disjoint leaf
-        ranges - one per rank - produce disjoint lists whose union is the full set."""
-        if n_leaves is None:
-            n_leaves = self.n - first_leaf
+    def overlap_unique_async(self, out, part=0, n_parts=1, packet=True, count_visits=False):
+        """The tree against its own leaves: every unordered overlapping pair ONCE as (smaller,
+        larger) object index, no (i, i); one traversal in which a leaf only walks the part of
+        the tree behind itself (half the nodes and half the output of `overlap_self`).
+        `part` of `n_parts` (one per rank, all holding the same tree): the leaves are dealt in
+        blocks of 128 of the Morton order, round-robin; the parts' lists are disjoint and their
+        union is the full set.  Appends into `out` int32[cap, 2] without synchronising the
+        host; returns ``(out, count)`` with the exact count as a device int64 tensor (pairs
+        beyond cap are dropped)."""
         _lib._check(_lib.lib().d3d_bvh_overlap_self(
-            ptr(self.workspace), c_i64(self.n), c_i64(first_leaf), c_i64(n_leaves),
+            ptr(self.workspace), c_i64(self.n), ctypes.c_int(part), ctypes.c_int(n_parts),
             ctypes.c_int(int(packet)), ptr(out), c_i64(out.shape[0]), ptr(self._count),
             ptr(self._visits) if count_visits else None, _lib.stream_ptr()))
         return out, self._count
 
-    def overlap_unique(self, first_leaf=0, n_leaves=None, capacity=None, out=None, packet=True,
+    def overlap_unique(self, part=0, n_parts=1, capacity=None, out=None, packet=True,
                        count_visits=False):
         """Synchronous form of :meth:`overlap_unique_async`: ``(pairs int32[count, 2], count)``;
         the traversal is repeated with the exact size when the buffer was too small."""
         torch = _lib.torch_cuda()
-        nq = self.n - first_leaf if n_leaves is None else n_leaves
         if out is None:
-            out = torch.empty((max(int(capacity or 8 * nq), 1), 2), dtype=torch.int32, device=self.device)
+            out = torch.empty((max(int(capacity or 8 * (self.n // n_parts + 1)), 1), 2),
+                              dtype=torch.int32, device=self.device)
         for _ in range(2):
-            self.overlap_unique_async(out, first_leaf, n_leaves, packet, count_visits)
+            self.overlap_unique_async(out, part, n_parts, packet, count_visits)
             count = int(self._count.item())
             if count <= out.shape[0]:
                 break

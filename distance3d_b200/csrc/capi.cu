@@ -41,6 +41,72 @@ __global__ void k_prepare(d3d_colliders c, double *verts_out) {
     st3(verts_out + 3 * ((int64_t)c.vert_off[i] + v), box_vertex(col, v));
 }
 
+// Compact wire records -> the structure-of-arrays collider set (include/d3d_b200.h
+// d3d_unpack_colliders).  One thread per collider; the record is at wire[wire_off[i]].
+__device__ __forceinline__ int wire_doubles(int type) {
+    switch (type) {
+    case D3D_SPHERE: return 4;     // centre, radius
+    case D3D_CAPSULE: return 14;   // pose rows 0-2, radius, height
+    case D3D_CYLINDER: return 14;  // pose rows 0-2, radius, length
+    case D3D_ELLIPSOID: return 15; // pose rows 0-2, radii
+    case D3D_BOX: return 16;       // pose rows 0-2, size, (vert_off, vert_len)
+    case D3D_HULL: return 1;       // (vert_off, vert_len)
+    case D3D_MESH: return 13;      // pose rows 0-2, (vert_off, vert_len)
+    case D3D_DISK: return 7;       // centre, normal, radius
+    case D3D_ELLIPSE: return 11;   // centre, axis 0, axis 1, radii
+    case D3D_CONE: return 14;      // pose rows 0-2, radius, height
+    }
+    return 0;
+}
+
+__global__ void k_unpack(const uint8_t *__restrict__ wtype, const int32_t *__restrict__ woff,
+                         const double *__restrict__ wire, int64_t n, int32_t *type, double *pose,
+                         double *param, int32_t *vert_off, int32_t *vert_len) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = wtype[i];
+    const double *r = wire + woff[i];
+    double T[12] = {1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0};
+    double p[3] = {0.0, 0.0, 0.0};
+    int2 vr = make_int2(0, 0);
+    const bool full_pose = t == D3D_CAPSULE || t == D3D_CYLINDER || t == D3D_ELLIPSOID || t == D3D_BOX ||
+                           t == D3D_MESH || t == D3D_CONE;
+    int k = 0;
+    if (full_pose) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) T[j] = r[j];
+        k = 12;
+    }
+    switch (t) {
+    case D3D_SPHERE: T[3] = r[0]; T[7] = r[1]; T[11] = r[2]; p[0] = r[3]; break;
+    case D3D_CAPSULE: case D3D_CYLINDER: case D3D_CONE: p[0] = r[k]; p[1] = r[k + 1]; break;
+    case D3D_ELLIPSOID: p[0] = r[k]; p[1] = r[k + 1]; p[2] = r[k + 2]; break;
+    case D3D_BOX:
+        p[0] = r[k]; p[1] = r[k + 1]; p[2] = r[k + 2];
+        vr = *reinterpret_cast<const int2 *>(r + k + 3);
+        break;
+    case D3D_HULL: vr = *reinterpret_cast<const int2 *>(r); break;
+    case D3D_MESH: vr = *reinterpret_cast<const int2 *>(r + k); break;
+    case D3D_DISK:  // pack.py: centre = pose[:3,3], normal = pose[:3,2] of an identity matrix
+        T[3] = r[0]; T[7] = r[1]; T[11] = r[2]; T[2] = r[3]; T[6] = r[4]; T[10] = r[5]; p[0] = r[6];
+        break;
+    case D3D_ELLIPSE:  // centre, axes = pose[:3,0], pose[:3,1] of an identity matrix
+        T[3] = r[0]; T[7] = r[1]; T[11] = r[2];
+        T[0] = r[3]; T[4] = r[4]; T[8] = r[5]; T[1] = r[6]; T[5] = r[7]; T[9] = r[8];
+        p[0] = r[9]; p[1] = r[10];
+        break;
+    }
+    type[i] = t;
+    double2 *o = reinterpret_cast<double2 *>(pose + 16 * i);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[j] = make_double2(T[2 * j], T[2 * j + 1]);
+    o[6] = make_double2(0.0, 0.0);
+    o[7] = make_double2(0.0, 1.0);
+    param[3 * i] = p[0]; param[3 * i + 1] = p[1]; param[3 * i + 2] = p[2];
+    vert_off[i] = vr.x;
+    vert_len[i] = vr.y;
+}
+
 __global__ void k_support(d3d_colliders c, const int32_t *idx, const double *dirs, int64_t n,
                           double *out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -202,6 +268,18 @@ int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream) {
     if (c->n == 0) return 0;
     int64_t threads = c->n * 8;
     k_prepare<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*c, verts_out);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_unpack_colliders(const uint8_t *wire_type, const int32_t *wire_off, const double *wire,
+                         int64_t n, int32_t *type, double *pose, double *param, int32_t *vert_off,
+                         int32_t *vert_len, void *stream) {
+    if (n == 0) return 0;
+    if (!wire_type || !wire_off || !wire || !type || !pose || !param || !vert_off || !vert_len)
+        return d3d_set_error("d3d_unpack_colliders: null argument");
+    k_unpack<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(wire_type, wire_off, wire, n, type,
+                                                                           pose, param, vert_off, vert_len);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

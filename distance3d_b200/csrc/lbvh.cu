@@ -607,8 +607,11 @@ k_overlap_packet(Tree T, const BvhHeader *hdr,
 // faster than the number of groups per warp grows (dense capsule set: 8-wide groups need
 // ~2x fewer warp steps than 32-wide ones), while the PW lanes of a group still fetch one node.
 //
-// SELF = true: the queries are the tree's own leaves first_leaf .. first_leaf + n_query - 1
-// (sorted positions) and every unordered pair is wanted ONCE, without (i, i).  The depth-first
+// SELF = true: the queries are the tree's own leaves (sorted positions) and every unordered pair
+// is wanted ONCE, without (i, i).  The leaves are dealt to `n_parts` parts (one per GPU) in
+// blocks of 128 = one CTA, round-robin: CTA b of part p walks leaves (b * n_parts + p) * 128 ...
+// (a contiguous split would give the part with the early leaves most of the pairs, because a
+// pair belongs to its earlier leaf).  The depth-first
 // order of the tree is the sorted leaf order, so query s only needs the part of the walk that
 // lies to the right of leaf s: its group starts AT the leaf record of the group's first query
 // and follows the ropes from there (a rope always leads to the subtree that begins behind the
@@ -624,7 +627,7 @@ k_overlap_packet(Tree T, const BvhHeader *hdr,
 template <int PW, bool SELF>
 __global__ void __launch_bounds__(128)
 k_overlap_append(Tree T, const BvhHeader *hdr,
-                 const double *__restrict__ query, const int32_t *__restrict__ order, int64_t first_leaf,
+                 const double *__restrict__ query, const int32_t *__restrict__ order, int part, int n_parts,
                  int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *cursor,
                  unsigned long long *visits) {
     __shared__ int2 stage_all[4][APPEND_STAGE];
@@ -632,7 +635,8 @@ k_overlap_append(Tree T, const BvhHeader *hdr,
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
     const unsigned group_mask = (PW == 32) ? FULL : (((1u << PW) - 1u) << (lane & ~(PW - 1)));
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // SELF: t = sorted position of this thread's leaf, n_query = number of leaves of the tree
+    int64_t t = (SELF ? (int64_t)blockIdx.x * n_parts + part : (int64_t)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
     bool valid = t < n_query;
     int qi = 0;
     int my_leaf = 0x7fffffff;  // SELF: node index of this query's own leaf record
@@ -641,9 +645,9 @@ k_overlap_append(Tree T, const BvhHeader *hdr,
     if (valid) {
         const double2 *qb;
         if (SELF) {
-            my_leaf = T.leaf0 + (int)(first_leaf + t);
-            qi = __ldg(&T.leaves[first_leaf + t].obj);
-            qb = reinterpret_cast<const double2 *>(T.leaves + (first_leaf + t));
+            my_leaf = T.leaf0 + (int)t;
+            qi = __ldg(&T.leaves[t].obj);
+            qb = reinterpret_cast<const double2 *>(T.leaves + t);
         } else {
             qi = order ? order[t] : (int)t;
             qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
@@ -654,7 +658,7 @@ k_overlap_append(Tree T, const BvhHeader *hdr,
     bool group_valid = PW == 1 ? valid : (__ballot_sync(FULL, valid) & group_mask) != 0;
     int node = -1;
     if (hdr->n > 0 && group_valid) {
-        if (SELF) node = T.leaf0 + (int)(first_leaf + (t & ~(int64_t)(PW - 1)));  // the group's first leaf (always valid)
+        if (SELF) node = T.leaf0 + (int)(t & ~(int64_t)(PW - 1));  // the group's first leaf (always valid)
         else node = hdr->root;
     }
     int staged = 0;  // warp-uniform
@@ -934,18 +938,20 @@ int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, 
 }
 
 static int launch_append(const BvhLayout &L, int64_t n, bool self, const double *query, const int32_t *order,
-                         int64_t first_leaf, int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
+                         int part, int n_parts, int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
                          unsigned long long *out_count, unsigned long long *out_visits, cudaStream_t stream) {
-    unsigned blocks = (unsigned)((n_query + 127) / 128);
+    int64_t all_blocks = (n_query + 127) / 128;
+    unsigned blocks = (unsigned)(self ? (all_blocks - part + n_parts - 1) / n_parts : all_blocks);
+    if (blocks == 0) return 0;
 #define D3D_APPEND(PW)                                                                                  \
     do {                                                                                                \
         if (self)                                                                                       \
             k_overlap_append<PW, true><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
-                                                                   first_leaf, n_query, out_pairs, cap, \
+                                                                   part, n_parts, n_query, out_pairs, cap, \
                                                                    out_count, out_visits);             \
         else                                                                                            \
             k_overlap_append<PW, false><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
-                                                                    first_leaf, n_query, out_pairs, cap, \
+                                                                    part, n_parts, n_query, out_pairs, cap, \
                                                                     out_count, out_visits);            \
     } while (0)
     switch (packet) {  // 0 / 1 = per thread / default packet; 2, 4, 8, 16, 32 = explicit width
@@ -977,23 +983,24 @@ int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const
     if (n_query == 0 || n == 0) return 0;
     if (!query || (cap > 0 && !out_pairs)) return d3d_set_error("d3d_bvh_overlap: null query / output");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    return launch_append(L, n, false, query, order, 0, n_query, packet, out_pairs, cap, out_count, out_visits, stream);
+    return launch_append(L, n, false, query, order, 0, 1, n_query, packet, out_pairs, cap, out_count, out_visits, stream);
 }
 
-/* the tree against its own leaves first_leaf .. first_leaf + n_query - 1 (sorted positions):
- * every unordered pair once, as (smaller, larger) object index, no (i, i) */
-int d3d_bvh_overlap_self(const void *workspace, int64_t n, int64_t first_leaf, int64_t n_query, int packet,
+/* the tree against its own leaves: every unordered pair once, as (smaller, larger) object index,
+ * no (i, i).  Part `part` of `n_parts` (one per GPU; 0 of 1 = everything) takes the 128-leaf
+ * blocks part, part + n_parts, ... of the sorted order. */
+int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts, int packet,
                          int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
                          unsigned long long *out_visits, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap_self: null argument");
     D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
     if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
-    if (n_query == 0 || n == 0) return 0;
-    if (first_leaf < 0 || first_leaf + n_query > n) return d3d_set_error("d3d_bvh_overlap_self: leaf range out of bounds");
+    if (n == 0) return 0;
+    if (n_parts < 1 || part < 0 || part >= n_parts) return d3d_set_error("d3d_bvh_overlap_self: part out of range");
     if (cap > 0 && !out_pairs) return d3d_set_error("d3d_bvh_overlap_self: null output");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    return launch_append(L, n, true, nullptr, nullptr, first_leaf, n_query, packet, out_pairs, cap, out_count,
+    return launch_append(L, n, true, nullptr, nullptr, part, n_parts, n, packet, out_pairs, cap, out_count,
                          out_visits, stream);
 }
 

@@ -25,6 +25,7 @@ import ctypes
 import numpy as np
 
 SPHERE, CAPSULE, BOX, ELLIPSOID, CYLINDER, HULL, MESH, DISK, ELLIPSE, CONE = range(10)
+D3D_NUM_TYPES = 10
 TYPE_NAMES = ["sphere", "capsule", "box", "ellipsoid", "cylinder", "hull", "mesh",
               "disk", "ellipse", "cone"]
 
@@ -139,6 +140,49 @@ class ColliderSet:
                            graph_off=None if self.graph_off is None else self.graph_off[idx],
                            graph=self.graph,
                            mesh_start=None if self.mesh_start is None else self.mesh_start[idx])
+
+    def wire(self):
+        """Compact wire records (include/d3d_b200.h d3d_unpack_colliders): ``(wire_type uint8[n],
+        wire_off int32[n], wire f64[total])``.  Built with array operations per type."""
+        n = len(self)
+        size_of = np.zeros(D3D_NUM_TYPES, dtype=np.int64)
+        size_of[[SPHERE, CAPSULE, BOX, ELLIPSOID, CYLINDER, HULL, MESH, DISK, ELLIPSE, CONE]] = \
+            [4, 14, 16, 15, 14, 1, 13, 7, 11, 14]
+        sizes = size_of[self.type]
+        off = np.zeros(n, dtype=np.int64)
+        if n:
+            off[1:] = np.cumsum(sizes[:-1])
+        total = int(sizes.sum())
+        if total >= 2 ** 31:
+            raise ValueError("wire buffer exceeds int32 offsets; split the batch")
+        wire = np.empty(max(total, 1))
+        rows = self.pose[:, :3, :].reshape(n, 12)
+        ranges = np.stack((self.vert_off, self.vert_len), axis=1).astype(np.int32).view(np.float64).reshape(n)
+
+        def put(idx, col, values):
+            wire[off[idx][:, None] + col + np.arange(values.shape[1])[None, :]] = values
+
+        for t in np.unique(self.type):
+            idx = np.nonzero(self.type == t)[0]
+            if t == SPHERE:
+                put(idx, 0, self.pose[idx, :3, 3])
+                put(idx, 3, self.param[idx, :1])
+            elif t in (CAPSULE, CYLINDER, CONE):
+                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx, :2])
+            elif t == ELLIPSOID:
+                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx])
+            elif t == BOX:
+                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx]); put(idx, 15, ranges[idx, None])
+            elif t == HULL:
+                put(idx, 0, ranges[idx, None])
+            elif t == MESH:
+                put(idx, 0, rows[idx]); put(idx, 12, ranges[idx, None])
+            elif t == DISK:
+                put(idx, 0, self.pose[idx, :3, 3]); put(idx, 3, self.pose[idx, :3, 2]); put(idx, 6, self.param[idx, :1])
+            elif t == ELLIPSE:
+                put(idx, 0, self.pose[idx, :3, 3]); put(idx, 3, self.pose[idx, :3, 0])
+                put(idx, 6, self.pose[idx, :3, 1]); put(idx, 9, self.param[idx, :2])
+        return self.type.astype(np.uint8), off.astype(np.int32), wire[:max(total, 1)]
 
     def commit_mesh_state(self, device=None):
         """Scalar API: copy the vertex every MeshGraph ended on back into the objects

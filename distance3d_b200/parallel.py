@@ -105,11 +105,11 @@ def overlap_sharded(bvh, query, gather=True):
 
 
 def overlap_unique_sharded(bvh, gather=True, out=None):
-    """Self query with a replicated BVH: this rank walks its contiguous range of leaves
-    (`Lbvh.overlap_unique`), so the ranks' lists of unordered pairs are disjoint; with
-    gather=True every rank receives the whole list."""
-    begin, end = shard_range(bvh.n)
-    pairs, count = bvh.overlap_unique(begin, end - begin, out=out)
+    """Self query with a replicated BVH: this rank walks its share of the leaves
+    (`Lbvh.overlap_unique`: 128-leaf blocks dealt round-robin), so the ranks' lists of
+    unordered pairs are disjoint; with gather=True every rank receives the whole list."""
+    rank, ws = world()
+    pairs, count = bvh.overlap_unique(rank, ws, out=out)
     if not gather:
         return pairs, count
     full, counts = all_gather_varlen(pairs)

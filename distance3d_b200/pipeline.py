@@ -31,9 +31,10 @@ def collide(colliders, penetration=True, distance_threshold=None, shard=True, ca
 
     Returns a :class:`PipelineResult`.  `distance_threshold` is only used to report
     `near` pairs by the caller; all candidates get an exact GJK distance.  With several
-    ranks (shard=True) every rank builds the same tree and walks its own contiguous range of
-    leaves; a candidate pair belongs to the rank that owns its earlier leaf, so the ranks'
-    candidate lists are disjoint and their union is the single-GPU list.
+    ranks (shard=True) every rank builds the same tree and walks its own share of the leaves
+    (128-leaf blocks of the Morton order dealt round-robin); a candidate pair belongs to the
+    rank that owns its earlier leaf, so the ranks' candidate lists are disjoint and their union
+    is the single-GPU list.
     `timings` (optional dict) receives a (start, end) CUDA event pair per stage.
     """
     torch = _lib.torch_cuda()
@@ -53,9 +54,9 @@ def collide(colliders, penetration=True, distance_threshold=None, shard=True, ca
     t1 = mark("aabb", t0)
     bvh = aabb_tree.Lbvh(aabb)
     t2 = mark("bvh_build", t1)
-    begin, end = parallel.shard_range(dc.n) if shard else (0, dc.n)
+    part, n_parts = parallel.world() if shard else (0, 1)
     # every unordered pair once, straight from the traversal (no (i, i), no mirrored copy)
-    candidates, count = bvh.overlap_unique(begin, end - begin, capacity=candidate_capacity)
+    candidates, count = bvh.overlap_unique(part, n_parts, capacity=candidate_capacity)
     t3 = mark("overlap", t2)
     g = _gjk.gjk_distance_batch(dc, candidates)
     t4 = mark("gjk", t3)

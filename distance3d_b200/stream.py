@@ -1,9 +1,13 @@
-"""Double-buffered host -> device -> host pipeline for batches of GJK queries.
+"""Multi-buffered host -> device -> host pipeline for batches of GJK queries.
 
-The narrow phase needs 336 bytes of input per pair when every pair brings its own
-colliders, so a caller that holds its data in HOST memory is PCIe bound.  (The vertex pool
-travels only when the batch has hull / mesh vertices in it: the 8 vertices of a box are
-derived data that `d3d_prepare` writes on the device.)  This class
+The narrow phase needs 336 bytes of input per pair in the reference's own layout (a 4x4
+pose per collider) when every pair brings its own colliders, so a caller that holds its data
+in HOST memory is PCIe bound.  `pin_batch(..., wire=True)` (the default) therefore ships the
+compact wire records of `ColliderSet.wire()` - a sphere is 4 doubles, a capsule 14, 99 bytes
+per collider on the primitive mix instead of 164 - and `d3d_unpack_colliders` expands them
+into the structure of arrays in HBM.  (The vertex pool travels only when the batch has hull /
+mesh vertices in it: the 8 vertices of a box are derived data that `d3d_prepare` writes on
+the device.)  This class
 keeps `slots` sets of device buffers and CUDA streams: while the kernels of batch k
 run, the inputs of batch k+1 are already on their way over PCIe and the results of
 batch k-1 are copied back (H2D and D2H use different copy engines).  All work of one
@@ -23,12 +27,30 @@ _ARRAYS = ("type", "pose", "param", "vert_off", "vert_len", "verts")
 # every 128 bytes) moves 19 % fewer bytes but measured 6 % slower end to end on B200 / PCIe 5.
 
 
-def pin_batch(cs, pairs):
-    """Pinned host tensors of a ColliderSet and its pair list (one-off staging copy)."""
+def pin_batch(cs, pairs, wire=True, out=None):
+    """Pinned host tensors of a ColliderSet and its pair list (staging copy).
+
+    wire=True: compact wire records (type-specific, see `ColliderSet.wire`); wire=False: the
+    structure-of-arrays layout as it is (4x4 poses).  `out`: a dict returned by an earlier call
+    with the same sizes, whose pinned buffers are overwritten instead of allocated."""
     torch = _lib.torch_cuda()
     from .pack import HULL, MESH
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(cs, k))).pin_memory() for k in _ARRAYS}
-    host["pairs"] = torch.from_numpy(np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)).pin_memory()
+    if cs.margin is not None or cs.graph_off is not None:
+        raise NotImplementedError("GjkDistanceStream batches carry no Margin / MeshGraph fields; "
+                                  "use gjk_distance_batch")
+    if wire:
+        wt, wo, w = cs.wire()
+        arrays = {"wire_type": wt, "wire_off": wo, "wire": w, "verts": cs.verts}
+    else:
+        arrays = {k: getattr(cs, k) for k in _ARRAYS}
+    arrays["pairs"] = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    if out is not None:
+        for k, a in arrays.items():
+            out[k].numpy()[...] = a.reshape(out[k].shape)
+        return out
+    host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for k, a in arrays.items()}
+    host["wire_format"] = bool(wire)
+    host["n_colliders"] = len(cs)
     # box slots of the pool are filled on the device; without hulls / meshes nothing is uploaded
     host["has_vertex_data"] = bool(np.any((cs.type == HULL) | (cs.type == MESH)))
     return host
@@ -43,7 +65,10 @@ class _Slot:
         self.dev = {"type": torch.empty(n, **i32), "pose": torch.empty((n, 4, 4), **f64),
                     "param": torch.empty((n, 3), **f64), "vert_off": torch.empty(n, **i32),
                     "vert_len": torch.empty(n, **i32), "verts": torch.empty((m, 3), **f64),
-                    "pairs": torch.empty((p, 2), **i32)}
+                    "pairs": torch.empty((p, 2), **i32),
+                    # wire records: at most 16 doubles per collider
+                    "wire_type": torch.empty(n, dtype=torch.uint8, device=dev),
+                    "wire_off": torch.empty(n, **i32), "wire": torch.empty(16 * n, **f64)}
         self.out = {"dist": torch.empty(p, **f64), "closest_a": torch.empty((p, 3), **f64),
                     "closest_b": torch.empty((p, 3), **f64), "status": torch.empty(p, **i32)}
         self.host_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in self.out.items()}
@@ -82,7 +107,8 @@ class GjkDistanceStream:
         slot = self.slots[idx]
         if slot.busy:
             raise RuntimeError("slot still holds an uncollected result; call result() first")
-        n = host["type"].shape[0]
+        wire = host.get("wire_format", False)
+        n = host["n_colliders"] if wire else host["type"].shape[0]
         p = host["pairs"].shape[0]
         m = host["verts"].shape[0]
         if (n > slot.dev["type"].shape[0] or p > slot.dev["pairs"].shape[0]
@@ -96,10 +122,18 @@ class GjkDistanceStream:
             for k in _ARRAYS + ("pairs",):
                 size = {"verts": m, "pairs": p}.get(k, n)
                 views[k] = slot.dev[k][:size]
+            sent = ("wire_type", "wire_off", "wire", "verts", "pairs") if wire else _ARRAYS + ("pairs",)
+            for k in sent:
                 if k == "verts" and not host.get("has_vertex_data", True):
                     continue
-                views[k].copy_(host[k].reshape(views[k].shape), non_blocking=True)
+                dst = views[k] if k in views else slot.dev[k][:host[k].shape[0]]
+                dst.copy_(host[k].reshape(dst.shape), non_blocking=True)
                 h2d += host[k].numel() * host[k].element_size()
+            if wire:   # expand the records into the structure of arrays (HBM to HBM)
+                _lib._check(L.d3d_unpack_colliders(
+                    ptr(slot.dev["wire_type"]), ptr(slot.dev["wire_off"]), ptr(slot.dev["wire"]), c_i64(n),
+                    ptr(views["type"]), ptr(views["pose"]), ptr(views["param"]), ptr(views["vert_off"]),
+                    ptr(views["vert_len"]), ctypes.c_void_p(slot.stream.cuda_stream)))
             dc = DeviceColliders.__new__(DeviceColliders)
             dc._init(views["type"], views["pose"], views["param"], views["vert_off"],
                      views["vert_len"], views["verts"], None)     # d3d_prepare on this stream

@@ -44,6 +44,21 @@ int d3d_debug_vdiv(const double *v, const double *s, int64_t n, double *out, voi
  * `c` into verts_out[vert_off .. vert_off+8). */
 int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream);
 
+/* Compact wire format for collider sets that arrive over PCIe (stream.GjkDistanceStream): the
+ * reference's objects carry a 4x4 pose per collider (colliders.py:243-646, 128 B) although a
+ * sphere is four numbers.  One record of doubles per collider at wire[wire_off[i]], layout by
+ * wire_type[i] (= the type tag):
+ *   sphere 4: centre, radius                      capsule / cylinder / cone 14: pose rows 0-2, r, h
+ *   ellipsoid 15: pose rows 0-2, radii            box 16: pose rows 0-2, size, {vert_off, vert_len}
+ *   hull 1: {vert_off, vert_len}                  mesh 13: pose rows 0-2, {vert_off, vert_len}
+ *   disk 7: centre, normal, radius                ellipse 11: centre, axis 0, axis 1, radii
+ * ({a, b} = two int32 in one 8-byte slot).  99 B per collider on the five-primitive mix instead of
+ * 164 B.  Expands the records into the d3d_colliders arrays (type, pose, param, vert_off,
+ * vert_len; margin / MeshGraph fields are passed to d3d_colliders as they are). */
+int d3d_unpack_colliders(const uint8_t *wire_type, const int32_t *wire_off, const double *wire,
+                         int64_t n, int32_t *type, double *pose, double *param, int32_t *vert_off,
+                         int32_t *vert_len, void *stream);
+
 /* colliders.py:131,221,272,326,374,426,479,533,590,629 <collider>.support_function(d):
  * out[k,:] = support of collider idx[k] in direction dirs[k,:]. */
 int d3d_support(const d3d_colliders *c, const int32_t *idx, const double *dirs, int64_t n,
@@ -182,13 +197,15 @@ int d3d_bvh_overlap_ordered(const void *workspace, int64_t n, const double *quer
                             void *query_ws, size_t query_ws_size, void *stream);
 
 /* aabb_tree.py:121-159 overlaps_aabb_tree(self) / broad_phase.py:229-252 aabb_overlapping_with_self
- * without the redundancy: the tree against its own leaves first_leaf .. first_leaf + n_query - 1
- * (positions in Morton order, see d3d_bvh_leaf_order; the whole tree: 0, n), ONE traversal.  Every
- * unordered overlapping pair is appended once as (smaller, larger) object index; (i, i) is not
- * reported.  A leaf only walks the part of the tree behind itself, so nodes visited and bytes
- * written are half of d3d_bvh_overlap over the same boxes.  Disjoint leaf ranges (one per
- * GPU) give disjoint pair lists whose union is the full set. */
-int d3d_bvh_overlap_self(const void *workspace, int64_t n, int64_t first_leaf, int64_t n_query, int packet,
+ * without the redundancy: the tree against its own leaves, ONE traversal.  Every unordered
+ * overlapping pair is appended once as (smaller, larger) object index; (i, i) is not reported.
+ * A leaf only walks the part of the tree behind itself in Morton order, so nodes visited and
+ * bytes written are half of d3d_bvh_overlap over the same boxes.  part / n_parts split the work
+ * between GPUs that hold replicas of the tree: the leaves are dealt in blocks of 128 of the
+ * Morton order, round-robin (block b goes to part b % n_parts), which balances pairs and
+ * traversal cost; the parts' lists are disjoint and their union is the full set.  One GPU:
+ * part = 0, n_parts = 1. */
+int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts, int packet,
                          int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
                          unsigned long long *out_visits, void *stream);
 

@@ -145,11 +145,14 @@ def test_self_query_every_unordered_pair_once(n, scale, names):
         p = pairs.cpu().numpy()
         assert count == len(ref_u) == len(p) and as_set(p) == ref_u
         assert np.all(p[:, 0] < p[:, 1]) if len(p) else True
-    # leaf ranges (one per rank): disjoint lists, union = the full set
-    cuts = [0, n // 3, n // 3, (2 * n) // 3 + 1, n]
-    parts = [bvh.overlap_unique(a, b - a)[0].cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
-    allp = np.concatenate(parts)
-    assert len(allp) == len(ref_u) and as_set(allp) == ref_u
+    # parts (one per rank): disjoint lists, union = the full set
+    for n_parts in (2, 3, 8):
+        parts = [bvh.overlap_unique(p, n_parts)[0].cpu().numpy() for p in range(n_parts)]
+        allp = np.concatenate(parts)
+        assert len(allp) == len(ref_u) and as_set(allp) == ref_u
+        if n >= 60000:   # round-robin blocks balance the parts
+            sizes = [len(p) for p in parts]
+            assert max(sizes) < 1.25 * min(sizes)
     # duplicates and touching boxes
     if n >= 33:
         B = np.concatenate([A, A[:17]])

@@ -242,18 +242,26 @@ def test_meshgraph_random_batches_thread_and_warp_kernels():
     compare_distance(nog, pairs[:4000], exact_types=EXACT)
 
 
-def test_streamed_host_pipeline_equals_batch_call():
+@pytest.mark.parametrize("wire,slots", [(True, 3), (False, 2)])
+def test_streamed_host_pipeline_equals_batch_call(wire, slots):
+    """Host buffers in, host buffers out; wire=True ships the compact type-specific records
+    (d3d_unpack_colliders expands them on the device), wire=False the 4x4-pose layout."""
     from distance3d_b200 import stream as d3stream
     rs = np.random.RandomState(15)
-    pipe = d3stream.GjkDistanceStream(6000, 3000, 20000, slots=2)
+    pipe = d3stream.GjkDistanceStream(6000, 3000, 60000, slots=slots)
     with pytest.raises(ValueError):
         d3stream.GjkDistanceStream(10, 10, 10).submit(d3stream.pin_batch(
             d3random.random_collider_set(rs, 50), d3random.random_pairs(rs, 50, 5)))
     batches = []
     for b in range(5):
-        cs = d3random.random_collider_set(rs, 2000 + 500 * b, names=d3random.PRIMITIVES + ("mesh",))
+        cs = d3random.random_collider_set(rs, 2000 + 500 * b, names=d3random.PRIMITIVES + ("mesh", "cone"),
+                                          hull_vertices=(4, 90))
         pairs = d3random.random_pairs(rs, len(cs), 1000 + 300 * b)
-        batches.append((cs, pairs, d3stream.pin_batch(cs, pairs)))
+        batches.append((cs, pairs, d3stream.pin_batch(cs, pairs, wire=wire)))
+    if wire:   # 99 B per collider on the primitive mix instead of 164 B
+        prim = d3random.random_collider_set(rs, 5000)
+        wt, wo, w = prim.wire()
+        assert (wt.nbytes + wo.nbytes + w.nbytes) / len(prim) < 0.68 * 164
     tickets = []
     results = []
     for k, (cs, pairs, host) in enumerate(batches):
@@ -265,7 +273,40 @@ def test_streamed_host_pipeline_equals_batch_call():
         ref = O.gjk_distance(cs, pairs)
         assert np.array_equal(got["dist"].numpy(), ref["dist"])
         assert np.array_equal(got["closest_a"].numpy(), ref["a"])
+        assert np.array_equal(got["closest_b"].numpy(), ref["b"])
         assert np.array_equal(got["status"].numpy(), ref["status"])
+
+
+def test_wire_records_of_every_collider_type_unpack_exactly():
+    """d3d_unpack_colliders reproduces the structure-of-arrays set bit for bit (all ten types)."""
+    import ctypes
+    import torch
+    from distance3d_b200 import _lib, colliders as C
+    rs = np.random.RandomState(3)
+    cs = d3random.random_collider_set(rs, 400, names=d3random.PRIMITIVES + ("mesh", "cone"), hull_vertices=(4, 30))
+    extra = P.pack_colliders([C.Disk(rs.randn(3), 0.7, np.array([0.0, 0.6, 0.8])),
+                              C.Ellipse(rs.randn(3), np.eye(3)[:2], np.array([0.4, 0.9])),
+                              C.MeshGraph(np.eye(4), rs.randn(12, 3), np.array([[0, 1, 2], [1, 2, 3]]))])
+    extra.graph_off = extra.graph = extra.mesh_start = None
+    cs = P.concat_sets([cs, extra])
+    wt, wo, w = cs.wire()
+    dev = torch.device("cuda")
+    n = len(cs)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    out = dict(type=torch.empty(n, dtype=torch.int32, device=dev), pose=torch.empty((n, 4, 4), dtype=torch.float64, device=dev),
+               param=torch.empty((n, 3), dtype=torch.float64, device=dev), vert_off=torch.empty(n, dtype=torch.int32, device=dev),
+               vert_len=torch.empty(n, dtype=torch.int32, device=dev))
+    a, b, c = t(wt), t(wo), t(w)
+    _lib._check(_lib.lib().d3d_unpack_colliders(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), ctypes.c_int64(n),
+                                                _lib.ptr(out["type"]), _lib.ptr(out["pose"]), _lib.ptr(out["param"]),
+                                                _lib.ptr(out["vert_off"]), _lib.ptr(out["vert_len"]), _lib.stream_ptr()))
+    assert np.array_equal(out["type"].cpu().numpy(), cs.type)
+    assert np.array_equal(out["pose"].cpu().numpy(), cs.pose)
+    used = cs.param.copy()
+    assert np.array_equal(out["param"].cpu().numpy(), used)
+    hv = np.isin(cs.type, (P.BOX, P.HULL, P.MESH))
+    assert np.array_equal(out["vert_off"].cpu().numpy()[hv], cs.vert_off[hv])
+    assert np.array_equal(out["vert_len"].cpu().numpy()[hv], cs.vert_len[hv])
 
 
 def test_fp32_mode_stated_tolerance():
