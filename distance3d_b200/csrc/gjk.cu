@@ -169,30 +169,61 @@ __global__ void __launch_bounds__(256) k_bin_scatter(int64_t n, GjkWorkspace w) 
 //   [44,56)  P  support points on A
 //   [56,68)  Q  support points on B
 #define GJK_FIELDS 68       // warp kernel: everything in shared memory
-#ifndef GJK_PQ_LOCAL
-#define GJK_PQ_LOCAL 0
+// GJK_PQ_GLOBAL = 1 (thread kernel, distance mode): P and Q are written once per iteration
+// and read only at the very end, so they do not live in shared memory at all: the new support
+// points go straight into the pair's parked record in the workspace (the record k_gjk_finish
+// reads anyway; it stays in L2 while the pair is in flight).  44 instead of 68 values per
+// thread.  0 = P / Q in shared memory.
+#ifndef GJK_PQ_GLOBAL
+#define GJK_PQ_GLOBAL 1
 #endif
-#define GJK_FIELDS_THREAD (GJK_PQ_LOCAL ? 44 : 68)
+#define GJK_FIELDS_THREAD (GJK_PQ_GLOBAL ? 44 : 68)
 #define GJK_OFF_B 16
 #define GJK_OFF_Y 32
 #define GJK_OFF_P 44
 #define GJK_OFF_Q 56
 
-// P and Q are touched once per iteration (store) and at the very end (closest points).
-// GJK_PQ_LOCAL = 1 keeps them in per-thread LOCAL memory to make room for a 4th resident
-// CTA per SM; measured on B200 this is slower (1.66e8 vs 1.80e8 pairs/s: the extra warps
-// add instruction-cache pressure, the kernel is fetch-latency bound), so the default
-// is shared memory and 3 CTAs per SM.
+// Simplex storage.  Points never move: slot i of the simplex (the reference's row i of Y / P / Q)
+// lives in PHYSICAL slot (perm >> 2 i) & 3, and update_simplex_y / update_simplex_ypq
+// (_gjk_jolt.py:643-664, "keep the rows selected by the mask, in order") only rewrites the
+// 8-bit permutation instead of copying up to nine vectors through shared memory.
 template <int STRIDE>
 struct Simplex {
     real *base;
-    real *pq;  // 24 doubles: P then Q (stride 1)
-    D3D_DEV real &at(int off, int s, int c) const {
-        if (GJK_PQ_LOCAL && STRIDE != 1 && off >= GJK_OFF_P) return pq[(off - GJK_OFF_P) + 3 * s + c];
-        return base[(off + 3 * s + c) * STRIDE];
+    real *pq;  // thread kernel with GJK_PQ_GLOBAL: P then Q of this pair in its parked record (stride 1)
+    int perm;
+    D3D_DEV int phys(int i) const { return (perm >> (2 * i)) & 3; }
+    D3D_DEV real &at_phys(int off, int ps, int c) const {
+        if (GJK_PQ_GLOBAL && STRIDE != 1 && off >= GJK_OFF_P) return pq[(off - GJK_OFF_P) + 3 * ps + c];
+        return base[(off + 3 * ps + c) * STRIDE];
     }
-    D3D_DEV v3 get(int off, int s) const { return V3(at(off, s, 0), at(off, s, 1), at(off, s, 2)); }
-    D3D_DEV void set(int off, int s, v3 v) const { at(off, s, 0) = v.x; at(off, s, 1) = v.y; at(off, s, 2) = v.z; }
+    D3D_DEV real &at(int off, int s, int c) const { return at_phys(off, phys(s), c); }
+    D3D_DEV v3 get(int off, int s) const {
+        const int ps = phys(s);
+        return V3(at_phys(off, ps, 0), at_phys(off, ps, 1), at_phys(off, ps, 2));
+    }
+    D3D_DEV void set(int off, int s, v3 v) const {
+        const int ps = phys(s);
+        at_phys(off, ps, 0) = v.x; at_phys(off, ps, 1) = v.y; at_phys(off, ps, 2) = v.z;
+    }
+    // physical slot for a new point behind the n live ones; the permutation entry n is set to it
+    D3D_DEV void claim(int n) {
+        int used = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (i < n) used |= 1 << phys(i);
+        const int free_slot = __ffs(~used) - 1;
+        perm = (perm & ~(3 << (2 * n))) | (free_slot << (2 * n));
+    }
+    // keep the slots selected by `mask` (bit i = slot i) in order; returns the new count
+    D3D_DEV int compact(int n, int mask) {
+        int np = 0, nn = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n && (mask & (1 << i))) { np |= phys(i) << (2 * nn); ++nn; }
+        perm = np;
+        return nn;
+    }
 };
 
 struct GjkParams {
@@ -220,8 +251,9 @@ struct PairState {
 };
 
 template <int STRIDE>
-D3D_DEV void init_pair(PairState<STRIDE> &s, const d3d_colliders &c, const int32_t *pairs, int k,
-                       real *base) {
+D3D_DEV void init_pair(PairState<STRIDE> &s, Simplex<STRIDE> &S, const d3d_colliders &c, const int32_t *pairs,
+                       int k, real *base) {
+    S.perm = 0;
     int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
     s.A = stage_collider<STRIDE>(c, pr.x, base);
     s.B = stage_collider<STRIDE>(c, pr.y, base + GJK_OFF_B * STRIDE);
@@ -250,7 +282,7 @@ D3D_DEV real max_y_len_sq(v3 y0, v3 y1, v3 y2, v3 y3, int mask) {
 // First half of _distance_loop (MODE 0, _gjk_jolt.py:228-242) / _intersection_loop (MODE 1,
 // :86-97).  Returns true when the simplex solve is needed.
 template <int MODE, int G, int STRIDE, int TM>
-D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
+D3D_DEV bool gjk_pre(PairState<STRIDE> &s, Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (s.iters >= D3D_GJK_ITER_CAP) { s.state = D3D_ITER_CAP; return false; }
     ++s.iters;
     v3 p = support_call<G, STRIDE, TM>(s.A.type, s.A.nv, s.A.V, s.A.base, prm.graph, s.sd.x, s.sd.y, s.sd.z, lane);
@@ -266,6 +298,7 @@ D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkPa
         if (dot < -D3D_EPS) { s.state = D3D_NO_INTERSECTION; return false; }
     }
     if (STRIDE == 1) __syncwarp();
+    S.claim(s.n_points);
     S.set(GJK_OFF_Y, s.n_points, w);
     if (MODE == 0) { S.set(GJK_OFF_P, s.n_points, p); S.set(GJK_OFF_Q, s.n_points, q); }
     if (STRIDE == 1) __syncwarp();
@@ -275,7 +308,7 @@ D3D_DEV bool gjk_pre(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkPa
 
 // Second half (_gjk_jolt.py:244-288 / :100-135) given the solver's answer.
 template <int MODE, int STRIDE>
-D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, bool ok,
+D3D_DEV void gjk_post(PairState<STRIDE> &s, Simplex<STRIDE> &S, const GjkParams &prm, bool ok,
                       v3 v_new, real v_len_sq_new, int simplex) {
     v3 y0 = S.get(GJK_OFF_Y, 0), y1 = S.get(GJK_OFF_Y, 1), y2 = S.get(GJK_OFF_Y, 2),
        y3 = S.get(GJK_OFF_Y, 3);
@@ -300,23 +333,8 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
         }
     }
     if (MODE == 0) {
-        // update_simplex_ypq (_gjk_jolt.py:654-664)
-        if (STRIDE == 1) __syncwarp();
-        int nn = 0;
-#pragma unroll 1
-        for (int i = 0; i < s.n_points; ++i)
-            if (simplex & (1 << i)) {
-                if (nn != i) {
-                    v3 ty = S.get(GJK_OFF_Y, i), tp = S.get(GJK_OFF_P, i), tq = S.get(GJK_OFF_Q, i);
-                    if (STRIDE == 1) __syncwarp();  // warp kernel: the record is shared by 32 lanes
-                    S.set(GJK_OFF_Y, nn, ty);
-                    S.set(GJK_OFF_P, nn, tp);
-                    S.set(GJK_OFF_Q, nn, tq);
-                    if (STRIDE == 1) __syncwarp();
-                }
-                ++nn;
-            }
-        s.n_points = nn;
+        // update_simplex_ypq (_gjk_jolt.py:654-664): the rows stay where they are, the map changes
+        s.n_points = S.compact(s.n_points, simplex);
         if (s.v_len_sq <= prm.tolerance_sq) { s.v_len_sq = R(0.0); s.state = D3D_INTERSECTION; return; }
         if (s.v_len_sq <= D3D_EPS * max_y_len_sq(y0, y1, y2, y3, simplex)) {
             s.v_len_sq = R(0.0);
@@ -333,26 +351,13 @@ D3D_DEV void gjk_post(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkP
     s.prev_v_len_sq = s.v_len_sq;
     if (MODE == 1) {
         // update_simplex_y (_gjk_jolt.py:643-651)
-        if (STRIDE == 1) __syncwarp();
-        int nn = 0;
-#pragma unroll 1
-        for (int i = 0; i < s.n_points; ++i)
-            if (simplex & (1 << i)) {
-                if (nn != i) {
-                    v3 ty = S.get(GJK_OFF_Y, i);
-                    if (STRIDE == 1) __syncwarp();
-                    S.set(GJK_OFF_Y, nn, ty);
-                    if (STRIDE == 1) __syncwarp();
-                }
-                ++nn;
-            }
-        s.n_points = nn;
+        s.n_points = S.compact(s.n_points, simplex);
     }
 }
 
 // Whole iteration with the per-lane solver (warp-per-pair kernel: all lanes are in step).
 template <int MODE, int G, int STRIDE>
-D3D_DEV void gjk_step(PairState<STRIDE> &s, const Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
+D3D_DEV void gjk_step(PairState<STRIDE> &s, Simplex<STRIDE> &S, const GjkParams &prm, int lane) {
     if (!gjk_pre<MODE, G, STRIDE, D3D_ALL_TYPES_MASK>(s, S, prm, lane)) return;
     v3 v_new;
     real v_len_sq_new;
@@ -381,9 +386,9 @@ struct TriResult {
 struct WarpScratch {
     TriResult *res;       // [32] results of the current round
     int *set;             // [32] feature sets of the current round (already in tetra numbering)
-    unsigned char *desc;  // [128] item -> (owner lane << 2 | face)
+    unsigned short *desc;  // [128] item -> (owner's slot permutation << 8 | owner lane << 2 | face)
 };
-#define GJK_SCRATCH_BYTES (32 * sizeof(TriResult) + 32 * sizeof(int) + 128)
+#define GJK_SCRATCH_BYTES (32 * sizeof(TriResult) + 32 * sizeof(int) + 256)
 
 template <int STRIDE>
 D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, int n_points,
@@ -420,7 +425,8 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
         // nothing to share: finish locally
     } else {
         int j = first;
-        for (int todo = faces; todo; todo &= todo - 1) W.desc[j++] = (unsigned char)((lane << 2) | (__ffs(todo) - 1));
+        for (int todo = faces; todo; todo &= todo - 1)
+            W.desc[j++] = (unsigned short)(((S.perm & 0xff) << 8) | (lane << 2) | (__ffs(todo) - 1));
         __syncwarp();
         real best_dist_sq = D3D_MAX_FLOAT;
 #pragma unroll 1
@@ -428,10 +434,11 @@ D3D_DEV bool closest_point_to_origin_warp(bool solve, const Simplex<STRIDE> &S, 
             int item = base + lane;
             if (item < total) {
                 int d = W.desc[item];
-                int o = d >> 2, f = d & 3;
+                int o = (d >> 2) & 31, f = d & 3;
                 Simplex<STRIDE> So;
                 So.base = S.base + (o - lane);
                 So.pq = nullptr;
+                So.perm = d >> 8;
                 // faces: abc, acd, adb, bdc (slot indices packed two bits each)
                 const int ia = (f == 3) ? 1 : 0;
                 const int ib = (f == 0) ? 1 : ((f == 1) ? 2 : 3);
@@ -542,9 +549,19 @@ D3D_DEV void gjk_finish(const PS &s, const SX &S, const GjkParams &prm, bool wri
 #ifdef D3D_F32
 #define GJK_BLOCKS_PER_SM 5  // fp32 state is half the size: 40 KB per CTA
 #else
-#define GJK_BLOCKS_PER_SM (GJK_PQ_LOCAL ? 4 : 3)
+#define GJK_BLOCKS_PER_SM 3
 #endif
 #endif
+// the primitive-only instance fits four CTAs per SM once P / Q are out of shared memory
+// (44 values per thread = 45 KB + scratch per CTA, 120 registers)
+#ifndef GJK_BLOCKS_PRIM
+#ifdef D3D_F32
+#define GJK_BLOCKS_PRIM GJK_BLOCKS_PER_SM
+#else
+#define GJK_BLOCKS_PRIM (GJK_PQ_GLOBAL ? 4 : 3)
+#endif
+#endif
+#define GJK_BLOCKS_FOR(TM) ((TM) == D3D_PRIMITIVE_MASK ? GJK_BLOCKS_PRIM : GJK_BLOCKS_PER_SM)
 #ifndef GJK_REFILL_MIN
 #define GJK_REFILL_MIN 8
 #endif
@@ -570,8 +587,10 @@ struct FinState {
 };
 struct SimplexFin {  // Y, P, Q of one parked pair (record of GJK_FIN_FIELDS values)
     const real *base;
+    int perm;  // Y is parked in simplex order; P / Q sit in their physical slots (GJK_PQ_GLOBAL)
     D3D_DEV v3 get(int off, int s) const {
-        const real *p = base + (off - GJK_OFF_Y + 3 * s);
+        const int ps = (GJK_PQ_GLOBAL && off >= GJK_OFF_P) ? ((perm >> (2 * s)) & 3) : s;
+        const real *p = base + (off - GJK_OFF_Y + 3 * ps);
         return V3(p[0], p[1], p[2]);
     }
 };
@@ -598,15 +617,18 @@ D3D_DEV void gjk_finish_or_park(const PairState<GJK_THREADS> &s, const Simplex<G
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             o[3 * i + j] = S.at(GJK_OFF_Y, i, j);
-            o[12 + 3 * i + j] = S.at(GJK_OFF_P, i, j);
-            o[24 + 3 * i + j] = S.at(GJK_OFF_Q, i, j);
+            if (!GJK_PQ_GLOBAL) {
+                o[12 + 3 * i + j] = S.at(GJK_OFF_P, i, j);
+                o[24 + 3 * i + j] = S.at(GJK_OFF_Q, i, j);
+            }
         }
     }
     o[36] = s.sd.x;
     o[37] = s.sd.y;
     o[38] = s.sd.z;
     o[39] = s.v_len_sq;
-    o[40] = fin_pack(s.n_points | (s.state << 4) | (s.iters << 8));
+    // n_points (3 bits) | state (4 bits) | slot permutation (8 bits) | iterations
+    o[40] = fin_pack(s.n_points | (s.state << 3) | ((GJK_PQ_GLOBAL ? (S.perm & 0xff) : 0xe4) << 7) | (s.iters << 15));
 }
 
 // Pairs of the warp kernel (wide hulls) are finished by that kernel: their key is the wide bin.
@@ -620,9 +642,10 @@ __global__ void __launch_bounds__(256) k_gjk_finish(GjkWorkspace w, GjkParams pr
         s.sd = V3(S.base[36], S.base[37], S.base[38]);
         s.v_len_sq = S.base[39];
         int packed = fin_unpack(S.base[40]);
-        s.n_points = packed & 15;
-        s.state = (packed >> 4) & 15;
-        s.iters = packed >> 8;
+        s.n_points = packed & 7;
+        s.state = (packed >> 3) & 15;
+        S.perm = (packed >> 7) & 0xff;
+        s.iters = packed >> 15;
         s.k = (int)k;
         gjk_finish<0>(s, S, prm, true);
     }
@@ -636,21 +659,21 @@ __global__ void __launch_bounds__(256) k_gjk_finish(GjkWorkspace w, GjkParams pr
 // (2.40e8 vs 2.53e8 vs 2.66e8 pairs/s for the split), the larger kernel image costs more
 // than the saved launch tail.
 template <int MODE, int TM>
-__global__ void __launch_bounds__(GJK_THREADS, GJK_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(GJK_THREADS, GJK_BLOCKS_FOR(TM))
 k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, GjkParams prm) {
     extern __shared__ real smem[];
     real *base = smem + threadIdx.x;
-    real pq_local[24];
     Simplex<GJK_THREADS> S;
     S.base = base;
-    S.pq = pq_local;
+    S.pq = nullptr;
+    S.perm = 0;
     WarpScratch W;
     {
         char *scratch = reinterpret_cast<char *>(smem + GJK_FIELDS_THREAD * GJK_THREADS) +
                         (threadIdx.x >> 5) * GJK_SCRATCH_BYTES;
         W.res = reinterpret_cast<TriResult *>(scratch);
         W.set = reinterpret_cast<int *>(scratch + 32 * sizeof(TriResult));
-        W.desc = reinterpret_cast<unsigned char *>(scratch + 32 * sizeof(TriResult) + 32 * sizeof(int));
+        W.desc = reinterpret_cast<unsigned short *>(scratch + 32 * sizeof(TriResult) + 32 * sizeof(int));
     }
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -711,7 +734,8 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
                 if (start + rank < total) mine = start + rank;
 #endif
                 if (!running && mine >= 0) {
-                    init_pair<GJK_THREADS>(s, c, pairs, __ldg(w.perm + mine), base);
+                    init_pair<GJK_THREADS>(s, S, c, pairs, __ldg(w.perm + mine), base);
+                    if (GJK_PQ_GLOBAL && MODE == 0) S.pq = w.fin + (int64_t)s.k * GJK_FIN_FIELDS + 12;
                     running = true;
                 }
             }
@@ -739,7 +763,7 @@ k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, G
     real *base = smem + (threadIdx.x >> 5) * GJK_FIELDS;
     Simplex<1> S;
     S.base = base;
-    S.pq = base + GJK_OFF_P;
+    S.pq = nullptr;
     const int first = w.counters[2], total = w.counters[3];
     for (;;) {
         int idx = 0;
@@ -747,7 +771,7 @@ k_gjk_warp(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w, G
         idx = __shfl_sync(0xffffffffu, idx, 0) + first;
         if (idx >= total) break;
         PairState<1> s;
-        init_pair<1>(s, c, pairs, __ldg(w.perm + idx), base);
+        init_pair<1>(s, S, c, pairs, __ldg(w.perm + idx), base);
         __syncwarp();
         while (s.state == D3D_UNKNOWN) {
             gjk_step<MODE, 32, 1>(s, S, prm, lane);
@@ -788,8 +812,9 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int blocks = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PER_SM);
+    int blocks_prim = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PRIM);
     // ranges are read on the device; an instance whose range is empty exits at once
-    k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks_prim, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     k_gjk_thread<MODE, D3D_ALL_TYPES_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     if (MODE == 0)
         k_gjk_finish<<<(int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8), 256, 0, stream>>>(w, prm);
