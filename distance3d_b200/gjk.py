@@ -184,6 +184,34 @@ def gjk_intersection_jolt(collider1, collider2, tolerance=1e-10):
     return bool(hit[0])
 
 
+def gjk_intersection_libccd_batch(colliders, pairs, max_iterations=100, want_iters=False, sort_by_type=True):
+    """libccd-style boolean GJK for every pair (gjk/_gjk_libccd.py:14-266), one thread per pair:
+    ``(hit uint8[P], iters int32[P] | None)``.  An independent algorithm for the same question as
+    `gjk_intersection_batch`; the two agree except on touching configurations."""
+    torch = _lib.torch_cuda()
+    dc = _lib.as_device_colliders(colliders)
+    pairs = _lib.as_device_pairs(pairs, dc.device)
+    n = pairs.shape[0]
+    hit = torch.empty(n, dtype=torch.uint8, device=dc.device)
+    iters = torch.empty(n, dtype=torch.int32, device=dc.device) if want_iters else None
+    perm = None
+    if sort_by_type and n > 64:
+        key = dc.type[pairs[:, 0].long()] * 16 + dc.type[pairs[:, 1].long()]
+        perm = torch.argsort(key).to(torch.int32)
+    _lib._check(_lib.lib().d3d_gjk_intersection_libccd(
+        ctypes.byref(dc.struct), ptr(pairs), ptr(perm), c_i64(n), ctypes.c_int(max_iterations),
+        ptr(hit), ptr(iters), _lib.stream_ptr()))
+    return hit, iters
+
+
+def gjk_intersection_libccd(collider1, collider2, max_iterations=100):
+    """Do two convex colliders intersect? libccd variant (reference: _gjk_libccd.py:14-53)."""
+    cs = pack_colliders([collider1, collider2], track_mesh_state=True)
+    hit, _ = gjk_intersection_libccd_batch(cs, _PAIR01, max_iterations)
+    cs.commit_mesh_state()
+    return bool(hit[0])
+
+
 gjk = gjk_distance_jolt
 gjk_distance = gjk_distance_jolt
 gjk_intersection = gjk_intersection_jolt

@@ -112,6 +112,15 @@ int d3d_gjk_intersection_f32(const d3d_colliders *c, const int32_t *pairs, int64
                              double tolerance, uint8_t *out_hit, int32_t *out_iters,
                              int32_t *out_status, void *workspace, size_t ws_bytes, void *stream);
 
+/* gjk/_gjk_libccd.py:14-91 gjk_intersection_libccd(collider1, collider2, max_iterations): the
+ * reference's second, libccd-style boolean GJK (:112-266 simplex cases), which its tests use as
+ * an independent cross-check of the Jolt variant (test/test_gjk.py:341-354).  out_hit[k] = 1 when
+ * the pair intersects; out_iters (optional) = support evaluations.  `perm` (optional,
+ * int32[n_pairs]): processing order, e.g. pairs grouped by collider types. */
+int d3d_gjk_intersection_libccd(const d3d_colliders *c, const int32_t *pairs, const int32_t *perm,
+                                int64_t n_pairs, int max_iterations, uint8_t *out_hit,
+                                int32_t *out_iters, void *stream);
+
 /* epa.py:9-78 epa(simplex, collider1, collider2, max_iter, max_loose_edges, max_faces, epsilon)
  * for pairs[k] with GJK simplex Y[k,4,3] (out_Y of d3d_gjk_distance).  The reference reads all
  * four rows of the simplex although GJK may have ended with fewer valid points (its result is
@@ -214,6 +223,39 @@ int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *str
 
 /* aabb_tree.py:183-191 AabbTree.get_root_aabb: out[3,2] */
 int d3d_bvh_root_aabb(const void *workspace, int64_t n, double *out, void *stream);
+
+/* ---- hydroelastic contact: the other consumer of the AABB broad phase -------- */
+
+/* hydroelastic_contact/_mesh_processing.py:4-20 tetrahedral_mesh_aabbs:
+ * points[n,4,3] -> out_aabb[n,3,2] (feeds d3d_bvh_build / d3d_bvh_overlap, which replace
+ * rigid_body.aabbtree_.overlaps_aabb_tree / all_aabbs_overlap in
+ * hydroelastic_contact/_interface.py:76-80). */
+int d3d_tetra_aabb(const double *points, int64_t n, double *out_aabb, void *stream);
+
+/* hydroelastic_contact/_barycentric_transform.py:4-9 barycentric_transforms:
+ * points[n,4,3] -> out_X[n,4,4], the inverse of [[p0 p1 p2 p3], [1 1 1 1]] in closed form (the
+ * reference calls numpy's pinv); row i = barycentric coordinate function of vertex i. */
+int d3d_tetra_barycentric(const double *points, int64_t n, double *out_X, void *stream);
+
+/* hydroelastic_contact/_tetrahedron_intersection.py:7-140 intersect_tetrahedron_pairs for the
+ * candidate pairs[k] = (tetrahedron of mesh 1, tetrahedron of mesh 2), both meshes expressed in
+ * one frame (points[n,4,3], vertex potentials eps[n,4]); X1 / X2 [n,4,4] are optional (NULL: the
+ * barycentric transforms are computed per pair on the fly).
+ *   out_hit[k]        1 = the tetrahedra intersect (contact polygon with >= 3 vertices)
+ *   out_plane[k,4]    contact plane in Hesse normal form (:165-216)
+ *   out_nverts[k], out_poly[k,max_vertices,3]  contact polygon, counter-clockwise (:377-423)
+ *   out_status[k]     0, 1 = "same tetrahedron" branch (:132-134, 143-162), 2 = polygon had more
+ *                     than max_vertices vertices (excess dropped); may be NULL
+ * 3 <= max_vertices <= 24.  Tolerance contract: planes and polygon regions within 1e-9 of the
+ * reference's (its pinv / atan2 are not reproduced bit for bit); where a face normal is parallel
+ * to the contact plane normal the reference reads an uninitialised half-plane row
+ * (:279-292 indexes by i, not hp_idx) - here the remaining half-planes are used. */
+int d3d_tetra_intersect_pairs(const int32_t *pairs, int64_t n_pairs, const double *points1,
+                              const double *eps1, const double *X1, const double *points2,
+                              const double *eps2, const double *X2, double youngs_modulus1,
+                              double youngs_modulus2, int max_vertices, uint8_t *out_hit,
+                              double *out_plane, int32_t *out_nverts, double *out_poly,
+                              int32_t *out_status, void *stream);
 
 /* ---- robot self-collision (BASELINE config 4) ------------------------------ */
 

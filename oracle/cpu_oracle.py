@@ -308,3 +308,50 @@ def self_collision_masks_ordered(template, kin, whitelist, q, n_threads=1):
                     break
         masks[b] = [contacts[f] for f in range(K)]
     return masks
+
+
+def tetra_aabbs(points):
+    """tetrahedral_mesh_aabbs (hydroelastic_contact/_mesh_processing.py:4-20)."""
+    points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 4, 3)
+    out = np.zeros((len(points), 3, 2))
+    lib().d3do_tetra_aabbs(_p(points), c_i64(len(points)), _p(out))
+    return out
+
+
+def barycentric_transforms(points):
+    points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 4, 3)
+    X = np.zeros((len(points), 4, 4))
+    for k in range(len(points)):
+        lib().d3do_barycentric_transform(_p(points[k]), _p(X[k]))
+    return X
+
+
+def tetra_pairs(pairs, points1, eps1, points2, eps2, X1=None, X2=None, youngs_modulus1=1.0,
+                youngs_modulus2=1.0, max_vertices=12, n_threads=1):
+    """intersect_tetrahedron_pairs (hydroelastic_contact/_tetrahedron_intersection.py:7-140)."""
+    pairs = _pairs(pairs)
+    n = len(pairs)
+    f = lambda a, shape: np.ascontiguousarray(a, dtype=np.float64).reshape(shape)  # noqa: E731
+    points1, points2 = f(points1, (-1, 4, 3)), f(points2, (-1, 4, 3))
+    eps1, eps2 = f(eps1, (-1, 4)), f(eps2, (-1, 4))
+    X1 = None if X1 is None else f(X1, (-1, 4, 4))
+    X2 = None if X2 is None else f(X2, (-1, 4, 4))
+    out = dict(hit=np.zeros(n, dtype=np.uint8), plane=np.zeros((n, 4)), n_vertices=np.zeros(n, dtype=np.int32),
+               polygon=np.zeros((n, max_vertices, 3)), status=np.zeros(n, dtype=np.int32))
+    lib().d3do_tetra_pairs(_p(pairs), c_i64(n), _p(points1), _p(eps1), None if X1 is None else _p(X1),
+                           _p(points2), _p(eps2), None if X2 is None else _p(X2),
+                           c_dbl(youngs_modulus1), c_dbl(youngs_modulus2), c_int(max_vertices),
+                           _p(out["hit"]), _p(out["plane"]), _p(out["n_vertices"]), _p(out["polygon"]),
+                           _p(out["status"]), c_int(n_threads))
+    return out
+
+
+def gjk_intersection_libccd(cs, pairs, max_iterations=100, n_threads=1):
+    """gjk_intersection_libccd (gjk/_gjk_libccd.py:14-91)."""
+    s = _ready(cs)
+    pairs = _pairs(pairs)
+    n = len(pairs)
+    out = dict(hit=np.zeros(n, dtype=np.uint8), iters=np.zeros(n, dtype=np.int32))
+    lib().d3do_gjk_intersection_libccd(ctypes.byref(s), _p(pairs), c_i64(n), c_int(max_iterations),
+                                       _p(out["hit"]), _p(out["iters"]), c_int(n_threads))
+    return out

@@ -193,8 +193,116 @@ def branched_fixture():
                         wl=np.array([[int(fj in wl[fi]) for fj in frames] for fi in frames], dtype=np.uint8))
 
 
+def _load_hydroelastic():
+    """The reference's hydroelastic modules without its package __init__ (which imports the
+    matplotlib / Open3D visualisation): only the numerical files are loaded."""
+    import importlib.util
+    import types
+    pkg_dir = os.path.join(refbridge.REFERENCE, "distance3d", "hydroelastic_contact")
+    pkg = types.ModuleType("distance3d.hydroelastic_contact")
+    pkg.__path__ = [pkg_dir]
+    sys.modules["distance3d.hydroelastic_contact"] = pkg
+    mods = {}
+    for name in ("_halfplanes", "_barycentric_transform", "_mesh_processing", "_tetra_mesh_creation",
+                 "_tetrahedron_intersection"):
+        spec = importlib.util.spec_from_file_location("distance3d.hydroelastic_contact." + name,
+                                                      os.path.join(pkg_dir, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods
+
+
+def tetra_fixture():
+    """Hydroelastic broad-phase consumer: two tetrahedral meshes made by the
+    reference's own mesh generators, broad phase with all_aabbs_overlap, narrow phase with
+    intersect_tetrahedron_pairs (hydroelastic_contact/_interface.py:52-101 without the forces)."""
+    H = _load_hydroelastic()
+    from distance3d.utils import transform_points
+    from pytransform3d import transformations as pt
+    mk = H["_tetra_mesh_creation"]
+    rs = np.random.RandomState(123)
+    cases = []
+    bodies = [("sphere", mk.make_tetrahedral_sphere(0.15, 2)), ("box", mk.make_tetrahedral_box(np.array([0.2, 0.25, 0.3]))),
+              ("cube", mk.make_tetrahedral_cube(0.2)), ("ellipsoid", mk.make_tetrahedral_ellipsoid(np.array([0.1, 0.15, 0.2]), 2)),
+              ("cylinder", mk.make_tetrahedral_cylinder(0.1, 0.3, 0.05))]
+    out = {}
+    n_case = 0
+    for a in range(len(bodies)):
+        for b in range(a, len(bodies)):
+            (na, (va, ta, pa)), (nb, (vb, tb, pb)) = bodies[a], bodies[b]
+            A2o = pt.random_transform(rs); A2o[:3, 3] *= 0.03
+            B2o = pt.random_transform(rs); B2o[:3, 3] *= 0.03
+            # rigid body 1 expressed in the frame of body 2 (_interface.py:74)
+            rel = np.dot(np.linalg.inv(B2o), A2o)
+            if a == b and n_case % 2 == 0:
+                rel = np.eye(4)       # bit-identical bodies: the "same tetrahedron" branch (:132-134)
+            tp1 = np.ascontiguousarray(transform_points(rel, va)[ta])
+            tp2 = np.ascontiguousarray(vb[tb])
+            e1 = np.ascontiguousarray(pa[ta]); e2 = np.ascontiguousarray(pb[tb])
+            aabbs1 = H["_mesh_processing"].tetrahedral_mesh_aabbs(tp1)
+            aabbs2 = H["_mesh_processing"].tetrahedral_mesh_aabbs(tp2)
+            b1, b2, bpairs = aabb_tree.all_aabbs_overlap(aabbs1, aabbs2)
+            X1 = H["_barycentric_transform"].barycentric_transforms(tp1[b1])
+            X2 = H["_barycentric_transform"].barycentric_transforms(tp2[b2])
+            X1d = {j: X1[i] for i, j in enumerate(b1)}
+            X2d = {j: X2[i] for i, j in enumerate(b2)}
+            ym1, ym2 = 1.0 + (n_case % 3), 1.0
+            inter, planes, polys, i1, i2 = H["_tetrahedron_intersection"].intersect_tetrahedron_pairs(
+                bpairs, tp1, tp2, e1, e2, X1d, X2d, ym1, ym2)
+            bp = np.array(bpairs, dtype=np.int32).reshape(-1, 2)
+            hit = np.zeros(len(bp), dtype=np.uint8)
+            plane = np.zeros((len(bp), 4)); nv = np.zeros(len(bp), dtype=np.int32); poly = np.zeros((len(bp), 12, 3))
+            lookup = {tuple(p): k for k, p in enumerate(bp.tolist())}
+            for q, (i, j) in enumerate(zip(i1, i2)):
+                k = lookup[(int(i), int(j))]
+                hit[k] = 1; plane[k] = planes[q]; nv[k] = len(polys[q]); poly[k, :len(polys[q])] = polys[q][:12]
+            key = "c%d_" % n_case
+            out.update({key + "tp1": tp1, key + "tp2": tp2, key + "e1": e1, key + "e2": e2,
+                        key + "aabb1": aabbs1, key + "aabb2": aabbs2, key + "pairs": bp, key + "hit": hit,
+                        key + "plane": plane, key + "nv": nv, key + "poly": poly,
+                        key + "ym": np.array([ym1, ym2])})
+            print("tetra case %d %s-%s: %d x %d tetrahedra, %d broad pairs, %d intersecting, max polygon %d" % (
+                n_case, na, nb, len(tp1), len(tp2), len(bp), int(hit.sum()), int(nv.max()) if len(nv) else 0))
+            n_case += 1
+    out["n_cases"] = np.array(n_case)
+    np.savez_compressed(os.path.join(OUT, "tetra.npz"), **out)
+
+
+def libccd_fixture():
+    """gjk_intersection_libccd (gjk/_gjk_libccd.py:14-266) on all collider types + Margin +
+    MeshGraph, far apart and close together; a fresh reference object per call."""
+    from distance3d import colliders as RC
+    from distance3d.gjk import gjk_intersection_libccd
+    out = {}
+    for tag, scale in (("far", 1.0), ("near", 0.3)):
+        rs = np.random.RandomState(77)
+        kw = {n: dict(center_scale=scale) for n in ALL if n not in ("disk", "ellipse")}
+        cols = refbridge.random_reference_colliders(rs, 300, ALL, **kw)
+        cols += refbridge.random_reference_colliders(rs, 60, ["mesh"], hull_as_vertices=False,
+                                                     mesh=dict(center_scale=scale, n_vertices=24))
+        for k in range(0, 300, 15):
+            cols[k] = RC.Margin(cols[k], 0.1 * rs.rand())
+        cs = refbridge.to_set(cols)
+        pairs = rs.randint(0, len(cols), size=(2500, 2)).astype(np.int32)
+        hit = np.array([gjk_intersection_libccd(fresh(cols[i]), fresh(cols[j])) for i, j in pairs], dtype=np.uint8)
+        jolt = np.array([gjk.gjk_intersection(fresh(cols[i]), fresh(cols[j])) for i, j in pairs], dtype=np.uint8)
+        print("libccd %s: %d pairs, %.3f intersecting, %d disagree with the Jolt variant" % (
+            tag, len(pairs), hit.mean(), int((hit != jolt).sum())))
+        out.update({tag + "_pairs": pairs, tag + "_hit": hit, tag + "_hit_jolt": jolt})
+        out.update(set_arrays(cs, prefix=tag + "_cs_"))
+    np.savez_compressed(os.path.join(OUT, "libccd.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-libccd" in sys.argv:
+        libccd_fixture()
+        return
+    if "--only-tetra" in sys.argv:
+        tetra_fixture()
+        return
     if "--only-meshgraph" in sys.argv:
         meshgraph_fixture()
         return
@@ -331,6 +439,9 @@ def main():
 
     meshgraph_fixture()
     branched_fixture()
+    tetra_fixture()
+    libccd_fixture()
+    libccd_fixture()
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -379,3 +379,34 @@ def test_scalar_support_and_geometry_api_vs_reference_outputs():
     tri = mesh.make_convex_mesh(verts)
     idx, pt = mesh.MeshSupportFunction(np.eye(4), verts, tri)(np.array([0.0, 0.0, 1.0]))
     assert idx == int(np.argmax(verts[:, 2])) and np.allclose(pt, verts[idx])
+
+
+def test_libccd_boolean_gjk_vs_reference_outputs_and_as_cross_check():
+    """gjk_intersection_libccd (gjk/_gjk_libccd.py:14-266) batched: identical booleans to the
+    reference's on the fixture (all collider types, Margin, MeshGraph), identical to the oracle
+    on a large random batch, and - the role it has in the reference's tests
+    (test_gjk.py:341-354) - an independent cross-check of the Jolt kernel."""
+    for tag in ("far", "near"):
+        cs, g = load_golden("libccd.npz", prefix=tag + "_cs_")
+        hit, iters = gjk.gjk_intersection_libccd_batch(cs, g[tag + "_pairs"], want_iters=True)
+        assert np.array_equal(hit.cpu().numpy(), g[tag + "_hit"])
+        ref = O.gjk_intersection_libccd(cs, g[tag + "_pairs"])
+        assert np.array_equal(iters.cpu().numpy(), ref["iters"])
+    rs = np.random.RandomState(33)
+    cs = d3random.random_collider_set(rs, 4000, names=d3random.PRIMITIVES + ("mesh", "cone"), center_scale=0.6,
+                                      hull_vertices=(4, 60))
+    pairs = d3random.random_pairs(rs, len(cs), 200000)
+    hit, _ = gjk.gjk_intersection_libccd_batch(cs, pairs)
+    hit = hit.cpu().numpy()
+    ref = O.gjk_intersection_libccd(cs, pairs, n_threads=O.max_threads())
+    assert np.array_equal(hit, ref["hit"])
+    jolt, _, _ = gjk.gjk_intersection_batch(cs, pairs)
+    dist = gjk.gjk_distance_batch(cs, pairs, want_points=False, want_simplex=False).dist.cpu().numpy()
+    clear = (dist > 1e-6) | (dist == 0.0)
+    disagree = hit != jolt.cpu().numpy()
+    assert disagree[clear].mean() < 2e-4, disagree[clear].mean()   # touching / grazing pairs only
+    assert 0.2 < hit.mean() < 0.8
+    from distance3d_b200 import colliders as C
+    s1, s2 = C.Sphere(np.zeros(3), 1.0), C.Sphere(np.array([0.0, 0.0, 1.5]), 1.0)
+    assert gjk.gjk_intersection_libccd(s1, s2) is True
+    assert gjk.gjk_intersection_libccd(s1, C.Sphere(np.array([0.0, 0.0, 2.5]), 1.0)) is False

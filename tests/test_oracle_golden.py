@@ -214,3 +214,37 @@ def test_meshgraph_hill_climbing_bit_exact():
             pt, start = O.support(cs, mi, g["seq_dirs"][mi, t], start=start, return_index=True)
             np.testing.assert_array_equal(pt, g["seq_pts"][mi, t])
             assert start == g["seq_idx"][mi, t]
+
+
+def test_tetrahedron_pairs_vs_reference_outputs():
+    """Hydroelastic broad-phase consumer: the oracle's intersect_tetrahedron_pairs
+    against the reference's on 15 pairs of tetrahedral meshes made by the reference's generators
+    (270 k candidate pairs from all_aabbs_overlap).  Booleans identical, planes and polygon
+    regions within 1e-9 (tests/util.py compare_tetra_results)."""
+    import os
+    from util import GOLDEN, compare_tetra_results
+    g = dict(np.load(os.path.join(GOLDEN, "tetra.npz")))
+    compared = 0
+    for c in range(int(g["n_cases"])):
+        k = "c%d_" % c
+        np.testing.assert_array_equal(O.tetra_aabbs(g[k + "tp1"]), g[k + "aabb1"])
+        np.testing.assert_array_equal(O.tetra_aabbs(g[k + "tp2"]), g[k + "aabb2"])
+        # the candidate list of the fixture is the brute-force overlap of the boxes
+        np.testing.assert_array_equal(O.all_aabbs_overlap(g[k + "aabb1"], g[k + "aabb2"]), g[k + "pairs"])
+        r = O.tetra_pairs(g[k + "pairs"], g[k + "tp1"], g[k + "e1"], g[k + "tp2"], g[k + "e2"],
+                          youngs_modulus1=g[k + "ym"][0], youngs_modulus2=g[k + "ym"][1],
+                          n_threads=O.max_threads())
+        compared += compare_tetra_results(r, g, k)
+    assert compared > 2500
+
+
+def test_gjk_intersection_libccd_vs_reference_outputs():
+    """The reference's second boolean GJK (gjk/_gjk_libccd.py:14-266), all collider types +
+    Margin + MeshGraph: identical booleans on 5000 pairs; and, as in the reference's own
+    test_gjk.py:341-354, agreement with the Jolt variant."""
+    for tag in ("far", "near"):
+        cs, g = load_golden("libccd.npz", prefix=tag + "_cs_")
+        got = O.gjk_intersection_libccd(cs, g[tag + "_pairs"])
+        np.testing.assert_array_equal(got["hit"], g[tag + "_hit"])
+        np.testing.assert_array_equal(O.gjk_intersection(cs, g[tag + "_pairs"])["hit"], g[tag + "_hit_jolt"])
+        assert 0.1 < g[tag + "_hit"].mean() < 0.8
