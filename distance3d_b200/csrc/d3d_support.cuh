@@ -61,7 +61,13 @@ struct ColliderSmem {
     }
     D3D_DEV int mesh_cur() const { return (int)f(12); }
     D3D_DEV void set_mesh_cur(int v, int lane) const {
-        if (STRIDE != 1 || lane == 0) const_cast<real *>(base)[12 * STRIDE] = (real)v;
+        if (STRIDE == 1) {  // warp-shared record: every lane has read the old value, lane 0 writes
+            __syncwarp();
+            if (lane == 0) const_cast<real *>(base)[12] = (real)v;
+            __syncwarp();
+        } else {
+            const_cast<real *>(base)[12 * STRIDE] = (real)v;
+        }
     }
     D3D_DEV real r00() const { return f(0); }
     D3D_DEV real r01() const { return f(1); }

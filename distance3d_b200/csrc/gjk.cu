@@ -251,12 +251,25 @@ struct PairState {
 };
 
 template <int STRIDE>
+D3D_DEV void stage_pair(PairState<STRIDE> &s, const d3d_colliders &c, int2 pr, real *base) {
+    s.A = stage_collider<STRIDE>(c, pr.x, base);
+    s.B = stage_collider<STRIDE>(c, pr.y, base + GJK_OFF_B * STRIDE);
+}
+// warp-shared record: the lanes share the stores (racecheck-clean)
+template <>
+D3D_DEV void stage_pair<1>(PairState<1> &s, const d3d_colliders &c, int2 pr, real *base) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    s.A = stage_collider_warp(c, pr.x, base, lane);
+    s.B = stage_collider_warp(c, pr.y, base + GJK_OFF_B, lane);
+}
+
+template <int STRIDE>
 D3D_DEV void init_pair(PairState<STRIDE> &s, Simplex<STRIDE> &S, const d3d_colliders &c, const int32_t *pairs,
                        int k, real *base) {
     S.perm = 0;
     int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
-    s.A = stage_collider<STRIDE>(c, pr.x, base);
-    s.B = stage_collider<STRIDE>(c, pr.y, base + GJK_OFF_B * STRIDE);
+    stage_pair(s, c, pr, base);
     s.sd = V3(R(1.0), R(0.0), R(0.0));
     s.v_len_sq = R(1.0);  // np.dot(sd, sd), _gjk_jolt.py:197
     s.prev_v_len_sq = D3D_MAX_FLOAT;

@@ -2,10 +2,9 @@
 
 The reference delegates to Open3D or trimesh; neither is a dependency here.  The two formats
 its data and examples use for collision geometry are read directly with numpy: STL (binary
-and ASCII) and Wavefront OBJ.  Only the vertex SET matters to the collision path (a
-`MeshGraph` is its vertices + a pose; the support map is an arg-max over them), so vertices
-that occur several times in the file - every STL facet repeats its corners - are merged,
-keeping the order of first occurrence.
+and ASCII) and Wavefront OBJ.  A `MeshGraph` climbs the triangle graph (mesh.py:12-139), which
+only works on a connected mesh, so vertices that occur several times in the file - every STL
+facet repeats its corners - are merged, keeping the order of first occurrence.
 """
 import os
 import struct

@@ -125,9 +125,11 @@ class RobotModel:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.frames = list(bvh.colliders_.keys())
         self.template = pack_colliders(list(bvh.colliders_.values()))
-        if np.any(self.template.vert_len > 0):
-            raise NotImplementedError("batched self-collision supports analytic colliders "
-                                      "(sphere, cylinder, capsule, ellipsoid, cone) only")
+        from .pack import BOX, HULL
+        if np.any(np.isin(self.template.type, (BOX, HULL))):
+            raise NotImplementedError("batched self-collision supports analytic colliders (sphere, "
+                                      "cylinder, capsule, ellipsoid, cone) and MeshGraph colliders; "
+                                      "boxes / world-frame hulls keep per-pose vertex lists")
         kin = tm.compile_kinematics(self.frames, "origin")
         self.joint_names = kin["joint_names"]
         self.n_frames = len(self.frames)
@@ -139,6 +141,14 @@ class RobotModel:
         self.wl_t = t(wl.view(np.int64))
         self.type_t = t(self.template.type)
         self.param_t = t(self.template.param)
+        # MeshGraph colliders: local-frame vertices and adjacency records are shared by all
+        # configurations, only the pose differs
+        self.mesh = None
+        if np.any(self.template.vert_len > 0):
+            tp = self.template
+            self.mesh = dict(vert_off=t(tp.vert_off), vert_len=t(tp.vert_len), verts=t(tp.verts),
+                             graph_off=None if tp.graph_off is None else t(tp.graph_off),
+                             graph=None if tp.graph is None else t(tp.graph))
         self.device = dev
 
     def forward_kinematics(self, q):
@@ -159,8 +169,14 @@ class RobotModel:
     def colliders_for(self, poses):
         """DeviceColliders of B * K colliders posed by `poses` [B,K,4,4]."""
         B = poses.shape[0]
-        return DeviceColliders.from_tensors(self.type_t.repeat(B), poses.reshape(-1, 4, 4),
-                                            self.param_t.repeat(B, 1))
+        if self.mesh is None:
+            return DeviceColliders.from_tensors(self.type_t.repeat(B), poses.reshape(-1, 4, 4),
+                                                self.param_t.repeat(B, 1))
+        m = self.mesh
+        return DeviceColliders.from_tensors(
+            self.type_t.repeat(B), poses.reshape(-1, 4, 4), self.param_t.repeat(B, 1),
+            m["vert_off"].repeat(B), m["vert_len"].repeat(B), m["verts"],
+            graph_off=None if m["graph_off"] is None else m["graph_off"].repeat(B), graph=m["graph"])
 
     def detect_batch(self, q, chunk=1 << 20):
         """Contact mask for every joint configuration: uint8 device tensor [B, K]

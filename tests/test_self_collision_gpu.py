@@ -176,3 +176,41 @@ def test_urdf_mesh_colliders_through_the_bvh(tmp_path):
         assert self_collision.detect_any(bvh) == hit
         seen.add(hit)
     assert seen == {True, False}
+
+
+def test_mesh_robot_reference_pins_0_2_4():
+    """distance3d/test/test_self_collision.py:44-76: sphere + three cone meshes (URDF <mesh>,
+    binary STL) at joint angles 0 / 1.5 / 2.7 -> 0 / 2 / 4 colliders in contact.  The fixtures
+    are re-authored (tests/data/simple_mechanism.urdf, cone.stl); the real reference run on
+    them gives the same 0 / 2 / 4 and the same frames (checked when the fixtures were made)."""
+    tm = UrdfTransformManager()
+    with open(os.path.join(DATA, "simple_mechanism.urdf")) as f:
+        tm.load_urdf(f.read(), mesh_path=DATA)
+    bvh = broad_phase.BoundingVolumeHierarchy(tm, "simple_mechanism")
+    bvh.fill_tree_with_colliders(tm, make_artists=False, fill_self_collision_whitelists=True)
+    frames = ["collision:cone%d/cone1" % k for k in (1, 2, 3, 4)]
+    assert list(bvh.colliders_.keys()) == frames
+    cone = bvh.colliders_[frames[1]]
+    assert isinstance(cone, colliders.MeshGraph) and cone.vertices.shape == (64, 3) and len(cone.triangles) == 124
+    expect = {0.0: [0, 0, 0, 0], 1.5: [1, 0, 0, 1], 2.7: [1, 1, 1, 1]}
+    for q, mask in expect.items():
+        for j in ("joint1", "joint2", "joint3"):
+            tm.set_joint(j, q)
+        bvh.update_collider_poses()
+        contacts = self_collision.detect(bvh)
+        assert [int(contacts[f]) for f in frames] == mask
+        assert self_collision.detect_any(bvh) == bool(sum(mask))
+    # the batched model handles MeshGraph colliders too (shared vertices / adjacency, one pose per configuration)
+    model = self_collision.RobotModel(tm, bvh)
+    q = np.array([[a, a, a] for a in expect])
+    mask, _ = model.detect_batch(q)
+    assert mask.cpu().numpy().tolist() == list(expect.values())
+    rs = np.random.RandomState(2)
+    qs = rs.uniform(-2.7, 2.7, size=(400, 3))
+    mb, _ = model.detect_batch(qs)
+    for b in range(0, 400, 57):
+        for j, v in zip(model.joint_names, qs[b]):
+            tm.set_joint(j, v)
+        bvh.update_collider_poses()
+        contacts = self_collision.detect(bvh)
+        assert [int(contacts[f]) for f in frames] == mb[b].cpu().numpy().tolist()
