@@ -814,8 +814,8 @@ def main():
                     "h2d_gbs_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
                     "pcie_h2d_peak_gbs_measured": pcie_gbs,
                     "value_including_host_packing": world * n / (e2e_pack_ms * 1e-3),
-                    "host_packing": "ColliderSet.wire() + copy into the pinned buffers every step "
-                                    "(numpy, one thread per rank)"},
+                    "host_packing": "d3d_pack_wire_host straight into the pinned buffers every step "
+                                    "(C++, all host threads of the rank)"},
             # k_pair_keys, k_bin_scan, k_bin_scatter, k_gjk_thread x2 (primitive / generic instance),
             # k_gjk_finish, k_gjk_warp
             "gpu_launches": 7 * args.steps,

@@ -12,47 +12,53 @@
 //   radix sort      hand-written LSD sort, 4 passes x 8 bits over the Morton bits:
 //                   per-block digit histogram, scan, stable scatter that ranks with
 //                   __match_any_sync (no CUB)
-//   k_leaves        leaf records in sorted order
-//   k_karras        Karras 2012 hierarchy: one thread per internal node, binary
-//                   search on the common prefix of the (unique) keys; also emits the
-//                   "rope" (next node in depth-first order when a subtree is skipped)
+//   k_blocks        the sorted boxes are cut into BLOCKS of 32 neighbours (one warp's worth):
+//                   64-byte leaf records (exact fp64 box + object index) in sorted order, the
+//                   union box of every block, and the block's key (Morton code of its first box)
+//   k_hierarchy     Karras 2012 hierarchy over the BLOCKS: one thread per internal node, binary
+//                   search on the common prefix of the (unique) keys; k_ropes adds the "rope"
+//                   (next node in depth-first order when a subtree is skipped)
 //   k_refit         bottom-up AABB union, second arrival proceeds (atomic flags)
-//   k_overlap<F>    stackless traversal: node = overlap ? first child : rope.  Two passes:
-//                   count hits per query, exclusive scan, then fill -- no atomics, exact
-//                   count before anything is written, deterministic order
+//   k_tile<M,SELF>  the query kernel.  A warp owns 32 queries that are neighbours in space; it
+//                   walks the block tree ONCE for all of them with the union of their boxes
+//                   (stackless: node = overlap ? first child : rope; 32-byte fp32 node records
+//                   rounded outward, warp-uniform) and at every block whose box meets the union
+//                   it stages the block's 32 exact boxes in shared memory and tests the 32 x 32
+//                   tile: each lane compares its own query with the 32 staged boxes (broadcast
+//                   reads, the reference's closed-interval fp64 predicate) and collects a 32-bit
+//                   hit mask.  Hits are staged per warp and flushed with one reservation on the
+//                   output cursor and coalesced 8-byte stores.
+//   k_thread<M>     one independent traversal per thread (query sets without spatial order)
 //   k_brute         brute force; its pairs are appended with a warp-aggregated atomic
-//                   (ballot + one atomic per converged group)
 //
-// Build record = 64 bytes: exact fp64 lo[3], hi[3], left, right, rope, parent.  Internal node
-// i in [0, n-1), leaf j (sorted position) at n-1+j; a leaf stores left = -(object index + 1).
-//
-// The queries read a second, compact copy of the tree.  Internal nodes: 32-byte records (two
-// 128-bit loads) with the box rounded OUTWARD to fp32 plus left / rope; the six comparisons of
-// a step are fp32 and the box is conservative, it can only add candidates.  Leaves: 64-byte
-// records with the exact fp64 box of the object, its index and the rope, so a leaf is decided
-// by the reference's closed-interval fp64 predicate in the same single fetch.  96 MB for 1 M
-// boxes instead of 128 MB: the whole tree stays in the 126 MB L2.
+// The tree over 1 M boxes has 31 250 leaves (2 MB of node records, L1 / L2 resident), the hierarchy
+// and refit kernels work on 32x fewer nodes, and a leaf visit does 1024 box tests in ~500 warp
+// instructions instead of one node fetch per box and packet.
 #include "d3d_common.cuh"
 
 namespace {
 
-struct __align__(16) BvhNode {
+#ifndef BLOCK_LEAVES
+#define BLOCK_LEAVES 8  // boxes per block (leaf of the tree); 32 / BLOCK_LEAVES blocks per warp of queries
+#endif
+
+struct __align__(16) BvhNode {  // build record of the block tree (exact fp64 boxes)
     double lo[3];
     double hi[3];
     int left, right, rope, parent;
 };
 static_assert(sizeof(BvhNode) == 64, "node record must be 64 bytes");
 
-struct __align__(16) TNode {  // traversal record of an internal node
+struct __align__(16) TNode {  // traversal record of a node of the block tree
     float lo[3];
     float hi[3];
-    int left, rope;
+    int left, rope;  // left >= 0: first child; left < 0: leaf = block -left - 1
 };
 static_assert(sizeof(TNode) == 32, "traversal record must be 32 bytes");
-struct __align__(16) LeafRec {  // traversal record of a leaf (sorted position): the exact box
+struct __align__(16) LeafRec {  // one box in sorted order: the exact box and its object
     double box[6];              // lo.x hi.x lo.y hi.y lo.z hi.z (the (3,2) layout of the input)
-    int obj, rope;
-    int pad[2];
+    int obj;
+    int pad[3];
 };
 static_assert(sizeof(LeafRec) == 64, "leaf record must be 64 bytes");
 
@@ -73,25 +79,32 @@ struct BvhLayout {
     unsigned long long *keys[2];  // [n] each
     unsigned *hist;               // [256][sort_blocks]
     unsigned *digit_totals;       // [256]
-    int *flags;                   // [n-1]
-    int *range_last;              // [2n-1] last sorted leaf covered by each node
-    BvhNode *nodes;               // [2n-1]
-    TNode *tnodes;                // [n-1] compact internal nodes for the queries
-    LeafRec *leaves;              // [n] leaf records in sorted order
+    unsigned long long *bkeys;    // [nb] key of every block
+    int *flags;                   // [nb-1]
+    int *range_first;             // [nb-1]
+    int *range_last;              // [2nb-1] last block covered by each node
+    BvhNode *nodes;               // [2nb-1] block tree, build records
+    TNode *tnodes;                // [2nb-1] block tree, traversal records
+    LeafRec *leaves;              // [n] boxes in sorted order
     int sort_blocks;
+    int nb;                       // number of blocks
 };
 
 inline size_t au(size_t x) { return (x + 255) / 256 * 256; }
+inline size_t n_blocks_of(int64_t n) { return (size_t)((n > 0 ? n : 1) + BLOCK_LEAVES - 1) / BLOCK_LEAVES; }
 
 inline size_t bvh_ws_bytes(int64_t n) {
     size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t nb = n_blocks_of(n);
     size_t sort_blocks = (nn + SORT_TILE - 1) / SORT_TILE;
-    return 256 + au(1024 * 6 * 8) + 1024 + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nn * 4) +
-           au(2 * nn * 4) + au(2 * nn * sizeof(BvhNode)) + au(nn * sizeof(TNode)) + au(nn * sizeof(LeafRec));
+    return 256 + au(1024 * 6 * 8) + 1024 + 2 * au(nn * 8) + au(256 * sort_blocks * 4) + au(nb * 8) +
+           2 * au(nb * 4) + au(2 * nb * 4) + au(2 * nb * sizeof(BvhNode)) + au(2 * nb * sizeof(TNode)) +
+           au(nn * sizeof(LeafRec));
 }
 
 inline BvhLayout bvh_carve(void *ws, int64_t n) {
     size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t nb = n_blocks_of(n);
     BvhLayout L;
     char *p = reinterpret_cast<char *>(ws);
     L.hdr = reinterpret_cast<BvhHeader *>(p); p += 256;
@@ -101,11 +114,14 @@ inline BvhLayout bvh_carve(void *ws, int64_t n) {
     L.keys[1] = reinterpret_cast<unsigned long long *>(p); p += au(nn * 8);
     L.sort_blocks = (int)((nn + SORT_TILE - 1) / SORT_TILE);
     L.hist = reinterpret_cast<unsigned *>(p); p += au(256 * (size_t)L.sort_blocks * 4);
-    L.flags = reinterpret_cast<int *>(p); p += au(nn * 4);
-    L.range_last = reinterpret_cast<int *>(p); p += au(2 * nn * 4);
-    L.nodes = reinterpret_cast<BvhNode *>(p); p += au(2 * nn * sizeof(BvhNode));
-    L.tnodes = reinterpret_cast<TNode *>(p); p += au(nn * sizeof(TNode));
+    L.bkeys = reinterpret_cast<unsigned long long *>(p); p += au(nb * 8);
+    L.flags = reinterpret_cast<int *>(p); p += au(nb * 4);
+    L.range_first = reinterpret_cast<int *>(p); p += au(nb * 4);
+    L.range_last = reinterpret_cast<int *>(p); p += au(2 * nb * 4);
+    L.nodes = reinterpret_cast<BvhNode *>(p); p += au(2 * nb * sizeof(BvhNode));
+    L.tnodes = reinterpret_cast<TNode *>(p); p += au(2 * nb * sizeof(TNode));
     L.leaves = reinterpret_cast<LeafRec *>(p);
+    L.nb = (int)nb;
     return L;
 }
 
@@ -308,14 +324,12 @@ k_sort_scatter(const unsigned long long *__restrict__ in, unsigned long long *__
     }
 }
 
-// ---------------------------------------------------------------- hierarchy
+// ---------------------------------------------------------------- blocks + hierarchy
 __device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    return __clzll(keys[i] ^ keys[j]);  // keys are unique (object index in the low bits)
+    return __clzll(keys[i] ^ keys[j]);  // keys are unique (index in the low bits)
 }
 
-// Leaf records (thread j < n) and the Karras hierarchy (thread i < n - 1) in one launch.  The
-// leaf part does not touch `parent`: that field is written by the internal node that adopts it.
 __device__ __forceinline__ void store_tbox(TNode *t, const double *lo, const double *hi) {
     float4 a = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]),
                            __double2float_ru(hi[0]));
@@ -324,28 +338,54 @@ __device__ __forceinline__ void store_tbox(TNode *t, const double *lo, const dou
     *reinterpret_cast<float2 *>(&t->hi[1]) = b;
 }
 
-__global__ void k_hierarchy(const double *__restrict__ aabb, const unsigned long long *__restrict__ keys,
-                            int n, BvhNode *nodes, TNode *tnodes, LeafRec *leaves, int *range_first,
-                            int *range_last, int *flags) {
+// Thread i = sorted position i: writes its leaf record; warp b = block b: union box and key of the
+// block, the block's leaf record of the tree (build + traversal copy).  256 threads = 8 blocks.
+__global__ void __launch_bounds__(256)
+k_blocks(const double *__restrict__ aabb, const unsigned long long *__restrict__ keys, int n, int nb,
+         LeafRec *leaves, unsigned long long *bkeys, BvhNode *nodes, TNode *tnodes, int *range_last) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    {
-        int obj = (int)(unsigned)(keys[i] & 0xffffffffull);
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double lo[3] = {1e308, 1e308, 1e308}, hi[3] = {-1e308, -1e308, -1e308};
+    unsigned long long key = 0;
+    if (i < n) {
+        key = keys[i];
+        int obj = (int)(unsigned)(key & 0xffffffffull);
         const double2 *b = reinterpret_cast<const double2 *>(aabb + 6 * (int64_t)obj);
         double2 x = __ldg(b), y = __ldg(b + 1), z = __ldg(b + 2);
         double2 *lb = reinterpret_cast<double2 *>(leaves + i);
         lb[0] = x; lb[1] = y; lb[2] = z;
         leaves[i].obj = obj;
-        if (n == 1) leaves[0].rope = -1;
-        BvhNode *nd = nodes + (n - 1 + i);
-        nd->lo[0] = x.x; nd->lo[1] = y.x; nd->lo[2] = z.x;
-        nd->hi[0] = x.y; nd->hi[1] = y.y; nd->hi[2] = z.y;
-        nd->left = -(obj + 1);
+        lo[0] = x.x; hi[0] = x.y; lo[1] = y.x; hi[1] = y.y; lo[2] = z.x; hi[2] = z.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int off = BLOCK_LEAVES / 2; off > 0; off >>= 1) {  // reduction inside the block's lanes
+            lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], off));
+        }
+    int b = i / BLOCK_LEAVES;
+    if (lane % BLOCK_LEAVES == 0 && b < nb) {
+        bkeys[b] = (key & 0xffffffff00000000ull) | (unsigned long long)(unsigned)b;
+        BvhNode *nd = nodes + (nb - 1 + b);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nd->lo[k] = lo[k]; nd->hi[k] = hi[k]; }
+        nd->left = -(b + 1);
         nd->right = -1;
         nd->rope = -1;
-        if (n == 1) nd->parent = -1;
-        range_last[n - 1 + i] = i;
+        if (nb == 1) nd->parent = -1;
+        store_tbox(tnodes + (nb - 1 + b), lo, hi);
+        tnodes[nb - 1 + b].left = -(b + 1);
+        if (nb == 1) tnodes[0].rope = -1;
+        range_last[nb - 1 + b] = b;
     }
+}
+
+// Karras hierarchy over the nb block keys (thread i < nb - 1 = internal node i).
+__global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes, TNode *tnodes,
+                            int *range_first, int *range_last, int *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     flags[i] = 0;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -379,7 +419,7 @@ __global__ void k_hierarchy(const double *__restrict__ aabb, const unsigned long
 // rope(node covering [a, b]) = node that starts at b + 1: internal node b + 1 when its
 // range grows to the right, else leaf b + 1; -1 behind the last leaf.
 __global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhNode *nodes, TNode *tnodes,
-                        LeafRec *leaves, const int *__restrict__ range_last) {
+                        const int *__restrict__ range_last) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * n - 1) return;
     int b = range_last[v];
@@ -392,15 +432,14 @@ __global__ void k_ropes(const unsigned long long *__restrict__ keys, int n, BvhN
         rope = d > 0 ? t : n - 1 + t;
     }
     nodes[v].rope = rope;
-    if (v < n - 1) tnodes[v].rope = rope;
-    else leaves[v - (n - 1)].rope = rope;
+    tnodes[v].rope = rope;
 }
 
 // Bottom-up refit: every leaf thread climbs, the second thread to arrive at a node merges the
 // two child boxes and goes on.  A node whose leaf range lies inside the 256 leaves of this
 // block can only be reached by threads of this block: its arrival flag lives in shared memory
-// and block-scope fences order the box stores (99.6 % of the nodes); only the nodes that span
-// blocks pay for device-scope fences and global atomics.
+// and block-scope fences order the box stores; only the nodes that span blocks pay for
+// device-scope fences and global atomics.
 __global__ void __launch_bounds__(256)
 k_refit(int n, BvhNode *nodes, TNode *tnodes, int *flags, const int *__restrict__ range_first,
         const int *__restrict__ range_last) {
@@ -452,248 +491,148 @@ __device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, in
     if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(a, b);
 }
 
-// One traversal step on the compact tree.  q*: exact fp64 query box ((lo, hi) per axis),
-// f*: the same box rounded outward to fp32.
-struct QueryBox {
-    double2 x, y, z;
-    float lox, loy, loz, hix, hiy, hiz;
-    __device__ __forceinline__ void set(double2 qx, double2 qy, double2 qz) {
-        x = qx; y = qy; z = qz;
-        lox = __double2float_rd(qx.x); hix = __double2float_ru(qx.y);
-        loy = __double2float_rd(qy.x); hiy = __double2float_ru(qy.y);
-        loz = __double2float_rd(qz.x); hiz = __double2float_ru(qz.y);
-    }
-    __device__ __forceinline__ void set_empty() {  // never overlaps anything
-        x = y = z = make_double2(1e308, -1e308);
-        lox = loy = loz = 3.0e38f; hix = hiy = hiz = -3.0e38f;
-    }
-};
-struct Step {
-    bool ov;      // internal node: the fp32 boxes overlap (conservative); leaf: the exact boxes overlap
-    int left;     // >= 0: first child; < 0: leaf of object -left - 1
-    int rope;
-};
 struct Tree {
     const TNode *__restrict__ tnodes;
     const LeafRec *__restrict__ leaves;
-    int leaf0;  // node index of the first leaf (n - 1)
+    int nb;  // blocks; leaf node of block b = nb - 1 + b
+    int n;   // boxes
 };
-// Whether `node` is a leaf is known from its index, so a leaf costs ONE fetch: its 64-byte
-// record holds the exact box (aabb_tree.py:520-527, closed intervals), the object and the rope.
-__device__ __forceinline__ Step visit(const Tree &T, int node, const QueryBox &q) {
-    Step s;
-    if (node >= T.leaf0) {
-        const double2 *lb = reinterpret_cast<const double2 *>(T.leaves + (node - T.leaf0));
-        double2 x = __ldg(lb), y = __ldg(lb + 1), z = __ldg(lb + 2);
-        int2 link = __ldg(reinterpret_cast<const int2 *>(lb + 3));
-        s.ov = x.x <= q.x.y && x.y >= q.x.x && y.x <= q.y.y && y.y >= q.y.x && z.x <= q.z.y && z.y >= q.z.x;
-        s.left = -link.x - 1;
-        s.rope = link.y;
-    } else {
-        const float4 *p = reinterpret_cast<const float4 *>(T.tnodes + node);
-        float4 a = __ldg(p), b = __ldg(p + 1);  // lo.x lo.y lo.z hi.x | hi.y hi.z left rope
-        s.ov = a.x <= q.hix && a.w >= q.lox && a.y <= q.hiy && b.x >= q.loy && a.z <= q.hiz && b.y >= q.loz;
-        s.left = __float_as_int(b.z);
-        s.rope = __float_as_int(b.w);
-    }
-    return s;
+
+// aabb_tree.py:520-527 (closed intervals) on exact boxes in the (3,2) layout
+__device__ __forceinline__ bool boxes_overlap(double2 ax, double2 ay, double2 az, double2 bx, double2 by,
+                                              double2 bz) {
+    return ax.x <= bx.y && ax.y >= bx.x && ay.x <= by.y && ay.y >= by.x && az.x <= bz.y && az.y >= bz.x;
 }
 
-static inline Tree tree_of(const BvhLayout &L, int64_t n) {
-    Tree T;
-    T.tnodes = L.tnodes; T.leaves = L.leaves; T.leaf0 = (int)n - 1;
-    return T;
-}
-
-// Traversal of one query box.  FILL = false: count the overlapping leaves;
-// FILL = true: write (object, query) pairs to out[offset ..).  Two passes instead of an
-// atomic append: no atomics, an exact count before anything is written, and a deterministic
-// output order (queries in the given order, leaves in depth-first order).
-template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_overlap(Tree T, const BvhHeader *hdr,
-          const double *__restrict__ query, const int32_t *__restrict__ order, int64_t n_query,
-          unsigned *__restrict__ counts, const unsigned long long *__restrict__ offsets,
-          int32_t *out_pairs, int64_t cap, unsigned long long *visits) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_query) return;
-    int qi = order ? order[t] : (int)t;
-    const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
-    QueryBox q;
-    q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
-    int node = hdr->n > 0 ? hdr->root : -1;
-    unsigned n_hits = 0, n_visited = 0;
-    unsigned long long pos = FILL ? offsets[t] : 0ull;
-    while (node >= 0) {
-        Step s = visit(T, node, q);
-        if (s.ov && s.left < 0) {
-            if (FILL) {
-                if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-s.left - 1, qi);
-                ++pos;
-            } else {
-                ++n_hits;
-            }
-        }
-        node = (s.ov && s.left >= 0) ? s.left : s.rope;
-        ++n_visited;
-    }
-    if (!FILL) counts[t] = n_hits;
-    if (!FILL && visits) {  // measurement only: node records fetched (roofline traffic term)
-        unsigned total = n_visited;
-        unsigned m = __activemask();
-        if (m == 0xffffffffu) {
-            for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(m, total, off);
-            if ((threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)total);
-        } else {
-            atomicAdd(visits, (unsigned long long)n_visited);
-        }
-    }
-}
-
-// Packet traversal: the 32 queries of a warp (neighbours in Morton order) walk the tree
-// TOGETHER.  The node is fetched once per warp (uniform address, one wavefront) and every
-// lane tests its own box; the warp descends when ANY lane overlaps.  The union of the
-// nodes seen by 32 coherent queries is a small multiple of what one query sees, so the
-// L2 traffic drops by an order of magnitude on dense scenes.  Same results as k_overlap.
-template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_overlap_packet(Tree T, const BvhHeader *hdr,
-                 const double *__restrict__ query, const int32_t *__restrict__ order, int64_t n_query,
-                 unsigned *__restrict__ counts, const unsigned long long *__restrict__ offsets,
-                 int32_t *out_pairs, int64_t cap, unsigned long long *visits) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool valid = t < n_query;
-    int qi = valid ? (order ? order[t] : (int)t) : 0;
-    QueryBox q;
-    q.set_empty();
-    if (valid) {
-        const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
-        q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
-    }
-    int node = hdr->n > 0 ? hdr->root : -1;  // warp-uniform
-    unsigned n_hits = 0, n_visited = 0;
-    unsigned long long pos = (FILL && valid) ? offsets[t] : 0ull;
-    while (node >= 0) {
-        Step s = visit(T, node, q);
-        if (s.left < 0) {  // leaf (uniform branch)
-            if (s.ov) {
-                if (FILL) {
-                    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(-s.left - 1, qi);
-                    ++pos;
-                } else {
-                    ++n_hits;
-                }
-            }
-            node = s.rope;
-        } else {
-            node = __any_sync(0xffffffffu, s.ov) ? s.left : s.rope;
-        }
-        ++n_visited;
-    }
-    if (!FILL && valid) counts[t] = n_hits;
-    if (!FILL && visits && (threadIdx.x & 31) == 0) atomicAdd(visits, (unsigned long long)n_visited);
-}
-
-// Single-pass query: hits are staged per warp in shared memory and flushed with ONE atomic
-// reservation per APPEND_STAGE pairs and coalesced 8-byte stores (the first version of this
-// file reserved per leaf hit and waited on that atomic 80 % of the time).  The pair order
-// depends on the order of the reservations; callers that need a reproducible order use the
-// count / fill passes.  *cursor ends up as the exact number of pairs even when `cap` is too
-// small (the excess is dropped).
-//
-// PW = packet width: groups of PW neighbouring queries (Morton order) walk the tree together
-// and descend when ANY query of the group overlaps.  PW = 1 is the independent traversal,
-// PW = 32 the full-warp packet; in between, the union of the nodes a group must see shrinks
-// faster than the number of groups per warp grows (dense capsule set: 8-wide groups need
-// ~2x fewer warp steps than 32-wide ones), while the PW lanes of a group still fetch one node.
-//
-// SELF = true: the queries are the tree's own leaves (sorted positions) and every unordered pair
-// is wanted ONCE, without (i, i).  The leaves are dealt to `n_parts` parts (one per GPU) in
-// blocks of 128 = one CTA, round-robin: CTA b of part p walks leaves (b * n_parts + p) * 128 ...
-// (a contiguous split would give the part with the early leaves most of the pairs, because a
-// pair belongs to its earlier leaf).  The depth-first
-// order of the tree is the sorted leaf order, so query s only needs the part of the walk that
-// lies to the right of leaf s: its group starts AT the leaf record of the group's first query
-// and follows the ropes from there (a rope always leads to the subtree that begins behind the
-// current one).  Half the nodes, half the output; pairs are written as (min, max) of the two
-// object indices.
-#ifndef APPEND_STAGE
-#define APPEND_STAGE 512  // pairs per warp; dense / sparse ms at 128, 256, 512, 1024: 14.6 14.3 14.2 20.2 / 0.50 0.50 0.47 0.66
+enum { Q_APPEND = 0, Q_COUNT = 1, Q_FILL = 2 };
+#ifndef TILE_STAGE
+#define TILE_STAGE (512 + BLOCK_LEAVES * 32)  // staged pairs per warp: flushed when less than one full tile is free
 #endif
-#ifndef D3D_BVH_PACKET_WIDTH
-#define D3D_BVH_PACKET_WIDTH 8  // width used for packet = 1; 1 M capsules, ms dense / sparse at
-// widths 1, 2, 4, 8, 16, 32: 34.8 23.0 16.7 14.0 15.5 14.9 / 0.61 0.54 0.48 0.47 0.58 0.65
-#endif
-template <int PW, bool SELF>
-__global__ void __launch_bounds__(128)
-k_overlap_append(Tree T, const BvhHeader *hdr,
-                 const double *__restrict__ query, const int32_t *__restrict__ order, int part, int n_parts,
-                 int64_t n_query, int32_t *out_pairs, int64_t cap, unsigned long long *cursor,
-                 unsigned long long *visits) {
-    __shared__ int2 stage_all[4][APPEND_STAGE];
-    int2 *stage = stage_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1;
-    const unsigned group_mask = (PW == 32) ? FULL : (((1u << PW) - 1u) << (lane & ~(PW - 1)));
-    // SELF: t = sorted position of this thread's leaf, n_query = number of leaves of the tree
-    int64_t t = (SELF ? (int64_t)blockIdx.x * n_parts + part : (int64_t)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
-    bool valid = t < n_query;
+#define TILE_WARPS 4
+
+// The query kernel (see the file header).  M: Q_APPEND = one pass, hits appended through the
+// per-warp stage (pair order depends on scheduling, *cursor = exact count even when cap is
+// too small); Q_COUNT / Q_FILL = the two passes of the ordered query (per-query counts, then
+// every lane writes its pairs behind its own offset: queries in processing order, boxes in
+// sorted order).  SELF: the queries are the tree's own boxes and every unordered pair is wanted
+// once, without (i, i): warp w of part p owns block (CTA * n_parts + p) * 4 + w, starts AT its own
+// block (the depth-first order of the tree is the sorted order, so everything behind a block is
+// reached by following ropes from it) and keeps pairs whose partner lies behind the query.
+template <int M, bool SELF>
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_tile(Tree T, const BvhHeader *hdr, const double *__restrict__ query, const int32_t *__restrict__ order,
+       int part, int n_parts, int64_t n_query, unsigned *__restrict__ counts,
+       const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
+       unsigned long long *cursor, unsigned long long *visits) {
+    extern __shared__ double tile_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    // per warp: 32 staged boxes (6 doubles each) + 32 object indices + the pair stage
+    double *sbox = tile_smem + wid * (BLOCK_LEAVES * 6);
+    int *sobj = reinterpret_cast<int *>(tile_smem + TILE_WARPS * BLOCK_LEAVES * 6) + wid * BLOCK_LEAVES;
+    int2 *stage = reinterpret_cast<int2 *>(tile_smem + TILE_WARPS * BLOCK_LEAVES * 6 + TILE_WARPS * BLOCK_LEAVES / 2) +
+                  (M == Q_APPEND ? wid * TILE_STAGE : 0);
+    const int64_t warp_id = SELF ? ((int64_t)blockIdx.x * n_parts + part) * TILE_WARPS + wid
+                                 : (int64_t)blockIdx.x * TILE_WARPS + wid;
+    const int64_t t = warp_id * 32 + lane;
+    const bool valid = t < n_query;
     int qi = 0;
-    int my_leaf = 0x7fffffff;  // SELF: node index of this query's own leaf record
-    QueryBox q;
-    q.set_empty();
+    double2 qx = make_double2(1e308, -1e308), qy = qx, qz = qx;  // empty box: never overlaps
     if (valid) {
         const double2 *qb;
         if (SELF) {
-            my_leaf = T.leaf0 + (int)t;
             qi = __ldg(&T.leaves[t].obj);
             qb = reinterpret_cast<const double2 *>(T.leaves + t);
         } else {
             qi = order ? order[t] : (int)t;
             qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
         }
-        q.set(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2));
+        qx = __ldg(qb); qy = __ldg(qb + 1); qz = __ldg(qb + 2);
     }
-    // group-uniform; a group with no valid query at all never starts
-    bool group_valid = PW == 1 ? valid : (__ballot_sync(FULL, valid) & group_mask) != 0;
+    // this lane's box rounded outward to fp32; the warp descends where ANY of its queries overlaps
+    // (a union box would blow up for the warps that straddle a jump of the Morton curve)
+    float mlo[3] = {__double2float_rd(qx.x), __double2float_rd(qy.x), __double2float_rd(qz.x)};
+    float mhi[3] = {__double2float_ru(qx.y), __double2float_ru(qy.y), __double2float_ru(qz.y)};
+    if (!valid) { mlo[0] = mlo[1] = mlo[2] = 3.0e38f; mhi[0] = mhi[1] = mhi[2] = -3.0e38f; }
+    const bool warp_valid = __any_sync(FULL, valid);
+    const int my_block = (int)(t / BLOCK_LEAVES);  // SELF: the block this lane's query sits in
     int node = -1;
-    if (hdr->n > 0 && group_valid) {
-        if (SELF) node = T.leaf0 + (int)(t & ~(int64_t)(PW - 1));  // the group's first leaf (always valid)
-        else node = hdr->root;
-    }
+    if (hdr->n > 0 && warp_valid) node = SELF ? T.nb - 1 + (int)(warp_id * (32 / BLOCK_LEAVES)) : hdr->root;
     int staged = 0;  // warp-uniform
-    unsigned n_visited = 0;
-    while (__any_sync(FULL, node >= 0)) {
-        bool ov = false, hit = false;
-        int left = 0, rope = -1;
-        if (node >= 0) {
-            Step s = visit(T, node, q);
-            ov = s.ov; left = s.left; rope = s.rope;
-            ++n_visited;
-        }
-        bool any = PW == 1 ? ov : (__ballot_sync(FULL, ov) & group_mask) != 0;
-        int leaf = -left - 1;
-        if (node >= 0) {
-            hit = ov && left < 0 && (!SELF || node > my_leaf);
-            node = (any && left >= 0) ? left : rope;
-        }
-        unsigned m = __ballot_sync(FULL, hit);
-        if (m) {
-            if (hit) stage[staged + __popc(m & lt)] = SELF ? make_int2(min(leaf, qi), max(leaf, qi)) : make_int2(leaf, qi);
-            staged += __popc(m);
-        }
-        if (staged > APPEND_STAGE - 32) {
+    unsigned n_hits = 0, n_nodes = 0, n_tiles = 0;
+    unsigned long long pos = (M == Q_FILL && valid) ? offsets[t] : 0ull;
+    while (node >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(T.tnodes + node);
+        float4 a = __ldg(p), b = __ldg(p + 1);  // lo.x lo.y lo.z hi.x | hi.y hi.z left rope (same address: broadcast)
+        const bool mine = a.x <= mhi[0] && a.w >= mlo[0] && a.y <= mhi[1] && b.x >= mlo[1] && a.z <= mhi[2] && b.y >= mlo[2];
+        const bool ov = __any_sync(FULL, mine);
+        const int left = __float_as_int(b.z), rope = __float_as_int(b.w);
+        ++n_nodes;
+        if (ov && left < 0) {
+            // ---- 32 x 32 tile: this warp's queries against the boxes of block blk
+            const int blk = -left - 1;
+            const int first = blk * BLOCK_LEAVES;
+            const int cnt = min(BLOCK_LEAVES, T.n - first);
             __syncwarp();
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
-            base = __shfl_sync(FULL, base, 0);
-            for (int i = lane; i < staged; i += 32)
-                if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
-            staged = 0;
+            if (lane < cnt) {
+                const double2 *lb = reinterpret_cast<const double2 *>(T.leaves + first + lane);
+                double2 x = __ldg(lb), y = __ldg(lb + 1), z = __ldg(lb + 2);
+                double2 *sb = reinterpret_cast<double2 *>(sbox + 6 * lane);
+                sb[0] = x; sb[1] = y; sb[2] = z;
+                sobj[lane] = __ldg(&T.leaves[first + lane].obj);
+            }
             __syncwarp();
+            unsigned mask = 0;
+            if (mine) {
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const double2 *sb = reinterpret_cast<const double2 *>(sbox + 6 * k);
+                    if (boxes_overlap(sb[0], sb[1], sb[2], qx, qy, qz)) mask |= 1u << k;
+                }
+                if (SELF) {  // partners behind the query only
+                    if (blk < my_block) mask = 0;
+                    else if (blk == my_block) mask &= ~((2u << (lane % BLOCK_LEAVES)) - 1u);
+                }
+            }
+            ++n_tiles;
+            const int c = __popc(mask);
+            if (M == Q_COUNT) {
+                n_hits += c;
+            } else if (M == Q_FILL) {
+                for (unsigned m = mask; m; m &= m - 1) {
+                    int k = __ffs(m) - 1;
+                    if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(sobj[k], qi);
+                    ++pos;
+                }
+            } else {
+                int incl = c;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    int y = __shfl_up_sync(FULL, incl, off);
+                    if (lane >= off) incl += y;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                int at = staged + incl - c;
+                for (unsigned m = mask; m; m &= m - 1) {
+                    int k = __ffs(m) - 1, o = sobj[k];
+                    stage[at++] = SELF ? make_int2(min(o, qi), max(o, qi)) : make_int2(o, qi);
+                }
+                staged += total;
+                if (staged > TILE_STAGE - BLOCK_LEAVES * 32) {  // room for one more full tile
+                    __syncwarp();
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
+                    base = __shfl_sync(FULL, base, 0);
+                    for (int i = lane; i < staged; i += 32)
+                        if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+                    staged = 0;
+                    __syncwarp();  // the stage is rewritten from slot 0
+                }
+            }
         }
+        node = (ov && left >= 0) ? left : rope;
     }
-    if (staged) {
+    if (M == Q_APPEND && staged) {
         __syncwarp();
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
@@ -701,11 +640,56 @@ k_overlap_append(Tree T, const BvhHeader *hdr,
         for (int i = lane; i < staged; i += 32)
             if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
     }
-    if (visits) {  // node records fetched: one per group and step
-        unsigned total = (lane & (PW - 1)) == 0 ? n_visited : 0u;
-        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
-        if (lane == 0) atomicAdd(visits, (unsigned long long)total);
+    if (M == Q_COUNT && valid) counts[t] = n_hits;
+    // measurement: 32-byte node records + 64-byte leaf records fetched, in units of 32 bytes
+    if (visits && M != Q_FILL && lane == 0 && warp_valid)
+        atomicAdd(visits, (unsigned long long)n_nodes + (unsigned long long)n_tiles * (2 * BLOCK_LEAVES));
+}
+
+// One independent traversal per thread, for query sets without spatial order (a warp's union box
+// would cover everything).  At a block the thread tests the block's boxes itself.
+template <int M>
+__global__ void __launch_bounds__(128)
+k_thread(Tree T, const BvhHeader *hdr, const double *__restrict__ query, const int32_t *__restrict__ order,
+         int64_t n_query, unsigned *__restrict__ counts, const unsigned long long *__restrict__ offsets,
+         int32_t *out_pairs, int64_t cap, unsigned long long *cursor, unsigned long long *visits) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_query) return;
+    int qi = order ? order[t] : (int)t;
+    const double2 *qb = reinterpret_cast<const double2 *>(query + 6 * (int64_t)qi);
+    double2 qx = __ldg(qb), qy = __ldg(qb + 1), qz = __ldg(qb + 2);
+    const float lox = __double2float_rd(qx.x), hix = __double2float_ru(qx.y), loy = __double2float_rd(qy.x),
+                hiy = __double2float_ru(qy.y), loz = __double2float_rd(qz.x), hiz = __double2float_ru(qz.y);
+    int node = hdr->n > 0 ? hdr->root : -1;
+    unsigned n_hits = 0, n_visited = 0;
+    unsigned long long pos = M == Q_FILL ? offsets[t] : 0ull;
+    while (node >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(T.tnodes + node);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        const bool ov = a.x <= hix && a.w >= lox && a.y <= hiy && b.x >= loy && a.z <= hiz && b.y >= loz;
+        const int left = __float_as_int(b.z), rope = __float_as_int(b.w);
+        ++n_visited;
+        if (ov && left < 0) {
+            const int first = (-left - 1) * BLOCK_LEAVES;
+            const int cnt = min(BLOCK_LEAVES, T.n - first);
+            n_visited += 2 * cnt;
+#pragma unroll 1
+            for (int k = 0; k < cnt; ++k) {
+                const double2 *lb = reinterpret_cast<const double2 *>(T.leaves + first + k);
+                if (boxes_overlap(__ldg(lb), __ldg(lb + 1), __ldg(lb + 2), qx, qy, qz)) {
+                    int o = __ldg(&T.leaves[first + k].obj);
+                    if (M == Q_COUNT) ++n_hits;
+                    else if (M == Q_FILL) {
+                        if ((int64_t)pos < cap) reinterpret_cast<int2 *>(out_pairs)[pos] = make_int2(o, qi);
+                        ++pos;
+                    } else append_pair(o, qi, out_pairs, cap, cursor);
+                }
+            }
+        }
+        node = (ov && left >= 0) ? left : rope;
     }
+    if (M == Q_COUNT) counts[t] = n_hits;
+    if (visits && M != Q_FILL) atomicAdd(visits, (unsigned long long)n_visited);
 }
 
 // ---- exclusive scan counts[u32] -> offsets[u64] (three small kernels) ----------
@@ -845,6 +829,38 @@ __global__ void k_root_aabb(const BvhNode *nodes, const BvhHeader *hdr, double *
     }
 }
 
+static inline Tree tree_of(const BvhLayout &L, int64_t n) {
+    Tree T;
+    T.tnodes = L.tnodes; T.leaves = L.leaves; T.nb = L.nb; T.n = (int)n;
+    return T;
+}
+
+static const size_t TILE_SMEM_FIXED = (size_t)TILE_WARPS * BLOCK_LEAVES * 6 * 8 + (size_t)TILE_WARPS * BLOCK_LEAVES * 4;
+static const size_t TILE_SMEM_APPEND = TILE_SMEM_FIXED + (size_t)TILE_WARPS * TILE_STAGE * 8;
+
+template <int M, bool SELF>
+static int launch_tile(const BvhLayout &L, int64_t n, const double *query, const int32_t *order, int part,
+                       int n_parts, int64_t n_query, unsigned *counts, const unsigned long long *offsets,
+                       int32_t *out_pairs, int64_t cap, unsigned long long *cursor, unsigned long long *visits,
+                       cudaStream_t stream) {
+    const size_t smem = M == Q_APPEND ? TILE_SMEM_APPEND : TILE_SMEM_FIXED;
+    static bool attr_set[64] = {false};  // per instance of this template, per device
+    int dev = 0;
+    D3D_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_tile<M, SELF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    int64_t all_ctas = (n_query + TILE_WARPS * 32 - 1) / (TILE_WARPS * 32);
+    int64_t ctas = SELF ? (all_ctas - part + n_parts - 1) / n_parts : all_ctas;
+    if (ctas <= 0) return 0;
+    k_tile<M, SELF><<<(unsigned)ctas, TILE_WARPS * 32, smem, stream>>>(tree_of(L, n), L.hdr, query, order, part, n_parts,
+                                                                      n_query, counts, offsets, out_pairs, cap,
+                                                                      cursor, visits);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -865,8 +881,8 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
     int pb = (int)d3d_min64((n + 255) / 256, 1024);
     k_bounds_partial<<<pb, 256, 0, stream>>>(aabb, n, L.partials);
     k_bounds_final<<<1, 256, 0, stream>>>(L.partials, pb, L.hdr, n);
-    unsigned nb = (unsigned)((n + 255) / 256);
-    k_morton<<<nb, 256, 0, stream>>>(aabb, n, L.hdr, L.keys[0]);
+    unsigned nblk = (unsigned)((n + 255) / 256);
+    k_morton<<<nblk, 256, 0, stream>>>(aabb, n, L.hdr, L.keys[0]);
     int cur = 0;
     for (int shift = 32; shift < 64; shift += 8) {
         k_sort_hist<<<L.sort_blocks, SORT_THREADS, 0, stream>>>(L.keys[cur], n, shift, L.hist, L.sort_blocks);
@@ -876,14 +892,13 @@ int d3d_bvh_build(const double *aabb, int64_t n, void *workspace, size_t ws_byte
         cur ^= 1;
     }
     // 4 passes: sorted keys are back in keys[0]
-    // the second key buffer is free after the sort: it holds the first leaf of every internal node
-    int *range_first = reinterpret_cast<int *>(L.keys[1]);
-    k_hierarchy<<<nb, 256, 0, stream>>>(aabb, L.keys[0], (int)n, L.nodes, L.tnodes, L.leaves, range_first,
-                                        L.range_last, L.flags);
-    if (n > 1) {
-        k_ropes<<<(unsigned)((2 * n - 1 + 255) / 256), 256, 0, stream>>>(L.keys[0], (int)n, L.nodes, L.tnodes,
-                                                                       L.leaves, L.range_last);
-        k_refit<<<nb, 256, 0, stream>>>((int)n, L.nodes, L.tnodes, L.flags, range_first, L.range_last);
+    const int nb = L.nb;
+    k_blocks<<<nblk, 256, 0, stream>>>(aabb, L.keys[0], (int)n, nb, L.leaves, L.bkeys, L.nodes, L.tnodes, L.range_last);
+    if (nb > 1) {
+        unsigned hb = (unsigned)((nb + 255) / 256);
+        k_hierarchy<<<hb, 256, 0, stream>>>(L.bkeys, nb, L.nodes, L.tnodes, L.range_first, L.range_last, L.flags);
+        k_ropes<<<(unsigned)((2 * nb - 1 + 255) / 256), 256, 0, stream>>>(L.bkeys, nb, L.nodes, L.tnodes, L.range_last);
+        k_refit<<<hb, 256, 0, stream>>>(nb, L.nodes, L.tnodes, L.flags, L.range_first, L.range_last);
     }
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -905,12 +920,14 @@ int d3d_bvh_overlap_count(const void *workspace, int64_t n, const double *query,
     if (query_ws_size < query_ws_bytes(n_query)) return d3d_set_error("d3d_bvh_overlap_count: query workspace too small");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
     QueryLayout Q = query_carve(query_ws, n_query);
-    if (packet)
-        k_overlap_packet<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            tree_of(L, n), L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
-    else
-        k_overlap<false><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            tree_of(L, n), L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, out_visits);
+    if (packet) {
+        int rc = launch_tile<Q_COUNT, false>(L, n, query, order, 0, 1, n_query, Q.counts, nullptr, nullptr, 0,
+                                             nullptr, out_visits, stream);
+        if (rc) return rc;
+    } else {
+        k_thread<Q_COUNT><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+            tree_of(L, n), L.hdr, query, order, n_query, Q.counts, nullptr, nullptr, 0, nullptr, out_visits);
+    }
     k_scan_tiles<<<Q.n_tiles, 1024, 0, stream>>>(Q.counts, n_query, Q.offsets, Q.tile_sums);
     k_scan_top<<<1, 1024, 0, stream>>>(Q.tile_sums, Q.n_tiles, out_count);
     k_scan_add<<<(unsigned)((n_query + 255) / 256), 256, 0, stream>>>(Q.offsets, n_query, Q.tile_sums);
@@ -928,43 +945,10 @@ int d3d_bvh_overlap_fill(const void *workspace, int64_t n, const double *query, 
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
     QueryLayout Q = query_carve(const_cast<void *>(query_ws), n_query);
     if (packet)
-        k_overlap_packet<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            tree_of(L, n), L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
-    else
-        k_overlap<true><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
-            tree_of(L, n), L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr);
-    D3D_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
-static int launch_append(const BvhLayout &L, int64_t n, bool self, const double *query, const int32_t *order,
-                         int part, int n_parts, int64_t n_query, int packet, int32_t *out_pairs, int64_t cap,
-                         unsigned long long *out_count, unsigned long long *out_visits, cudaStream_t stream) {
-    int64_t all_blocks = (n_query + 127) / 128;
-    unsigned blocks = (unsigned)(self ? (all_blocks - part + n_parts - 1) / n_parts : all_blocks);
-    if (blocks == 0) return 0;
-#define D3D_APPEND(PW)                                                                                  \
-    do {                                                                                                \
-        if (self)                                                                                       \
-            k_overlap_append<PW, true><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
-                                                                   part, n_parts, n_query, out_pairs, cap, \
-                                                                   out_count, out_visits);             \
-        else                                                                                            \
-            k_overlap_append<PW, false><<<blocks, 128, 0, stream>>>(tree_of(L, n), L.hdr, query, order, \
-                                                                    part, n_parts, n_query, out_pairs, cap, \
-                                                                    out_count, out_visits);            \
-    } while (0)
-    switch (packet) {  // 0 / 1 = per thread / default packet; 2, 4, 8, 16, 32 = explicit width
-    case 0: D3D_APPEND(1); break;
-    case 1: D3D_APPEND(D3D_BVH_PACKET_WIDTH); break;
-    case 2: D3D_APPEND(2); break;
-    case 4: D3D_APPEND(4); break;
-    case 8: D3D_APPEND(8); break;
-    case 16: D3D_APPEND(16); break;
-    case 32: D3D_APPEND(32); break;
-    default: return d3d_set_error("d3d_bvh_overlap: packet must be 0, 1, 2, 4, 8, 16 or 32");
-    }
-#undef D3D_APPEND
+        return launch_tile<Q_FILL, false>(L, n, query, order, 0, 1, n_query, nullptr, Q.offsets, out_pairs, cap,
+                                          nullptr, nullptr, stream);
+    k_thread<Q_FILL><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+        tree_of(L, n), L.hdr, query, order, n_query, nullptr, Q.offsets, out_pairs, cap, nullptr, nullptr);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -982,16 +966,24 @@ int d3d_bvh_overlap(const void *workspace, int64_t n, const double *query, const
     if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
     if (n_query == 0 || n == 0) return 0;
     if (!query || (cap > 0 && !out_pairs)) return d3d_set_error("d3d_bvh_overlap: null query / output");
+    if (packet < 0 || packet > 32) return d3d_set_error("d3d_bvh_overlap: packet must be 0 (per thread) or 1 (warp tiles)");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    return launch_append(L, n, false, query, order, 0, 1, n_query, packet, out_pairs, cap, out_count, out_visits, stream);
+    if (packet)
+        return launch_tile<Q_APPEND, false>(L, n, query, order, 0, 1, n_query, nullptr, nullptr, out_pairs, cap,
+                                            out_count, out_visits, stream);
+    k_thread<Q_APPEND><<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(
+        tree_of(L, n), L.hdr, query, order, n_query, nullptr, nullptr, out_pairs, cap, out_count, out_visits);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
-/* the tree against its own leaves: every unordered pair once, as (smaller, larger) object index,
- * no (i, i).  Part `part` of `n_parts` (one per GPU; 0 of 1 = everything) takes the 128-leaf
- * blocks part, part + n_parts, ... of the sorted order. */
+/* the tree against its own boxes: every unordered pair once, as (smaller, larger) object index,
+ * no (i, i).  Part `part` of `n_parts` (one per GPU; 0 of 1 = everything) takes the 128-box
+ * groups part, part + n_parts, ... of the sorted order. */
 int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts, int packet,
                          int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
                          unsigned long long *out_visits, void *stream_) {
+    (void)packet;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!workspace || !out_count) return d3d_set_error("d3d_bvh_overlap_self: null argument");
     D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
@@ -1000,8 +992,8 @@ int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts
     if (n_parts < 1 || part < 0 || part >= n_parts) return d3d_set_error("d3d_bvh_overlap_self: part out of range");
     if (cap > 0 && !out_pairs) return d3d_set_error("d3d_bvh_overlap_self: null output");
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
-    return launch_append(L, n, true, nullptr, nullptr, part, n_parts, n, packet, out_pairs, cap, out_count,
-                         out_visits, stream);
+    return launch_tile<Q_APPEND, true>(L, n, nullptr, nullptr, part, n_parts, n, nullptr, nullptr, out_pairs, cap,
+                                       out_count, out_visits, stream);
 }
 
 /* count + fill in one call: reproducible pair order (queries in the given order, leaves in

@@ -141,48 +141,34 @@ class ColliderSet:
                            graph=self.graph,
                            mesh_start=None if self.mesh_start is None else self.mesh_start[idx])
 
-    def wire(self):
+    def wire(self, out=None, n_threads=None):
         """Compact wire records (include/d3d_b200.h d3d_unpack_colliders): ``(wire_type uint8[n],
-        wire_off int32[n], wire f64[total])``.  Built with array operations per type."""
+        wire_off int32[n], wire f64[total])``, packed by the library's host-side packer
+        (`d3d_pack_wire_host`, multi-threaded C++).  `out`: three arrays to fill in place (e.g.
+        views of pinned buffers)."""
+        import os
+        from . import _lib
+        L = _lib.lib()
+        L.d3d_wire_size.restype = ctypes.c_int64
         n = len(self)
-        size_of = np.zeros(D3D_NUM_TYPES, dtype=np.int64)
-        size_of[[SPHERE, CAPSULE, BOX, ELLIPSOID, CYLINDER, HULL, MESH, DISK, ELLIPSE, CONE]] = \
-            [4, 14, 16, 15, 14, 1, 13, 7, 11, 14]
-        sizes = size_of[self.type]
-        off = np.zeros(n, dtype=np.int64)
-        if n:
-            off[1:] = np.cumsum(sizes[:-1])
-        total = int(sizes.sum())
-        if total >= 2 ** 31:
-            raise ValueError("wire buffer exceeds int32 offsets; split the batch")
-        wire = np.empty(max(total, 1))
-        rows = self.pose[:, :3, :].reshape(n, 12)
-        ranges = np.stack((self.vert_off, self.vert_len), axis=1).astype(np.int32).view(np.float64).reshape(n)
-
-        def put(idx, col, values):
-            wire[off[idx][:, None] + col + np.arange(values.shape[1])[None, :]] = values
-
-        for t in np.unique(self.type):
-            idx = np.nonzero(self.type == t)[0]
-            if t == SPHERE:
-                put(idx, 0, self.pose[idx, :3, 3])
-                put(idx, 3, self.param[idx, :1])
-            elif t in (CAPSULE, CYLINDER, CONE):
-                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx, :2])
-            elif t == ELLIPSOID:
-                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx])
-            elif t == BOX:
-                put(idx, 0, rows[idx]); put(idx, 12, self.param[idx]); put(idx, 15, ranges[idx, None])
-            elif t == HULL:
-                put(idx, 0, ranges[idx, None])
-            elif t == MESH:
-                put(idx, 0, rows[idx]); put(idx, 12, ranges[idx, None])
-            elif t == DISK:
-                put(idx, 0, self.pose[idx, :3, 3]); put(idx, 3, self.pose[idx, :3, 2]); put(idx, 6, self.param[idx, :1])
-            elif t == ELLIPSE:
-                put(idx, 0, self.pose[idx, :3, 3]); put(idx, 3, self.pose[idx, :3, 0])
-                put(idx, 6, self.pose[idx, :3, 1]); put(idx, 9, self.param[idx, :2])
-        return self.type.astype(np.uint8), off.astype(np.int32), wire[:max(total, 1)]
+        total = int(L.d3d_wire_size(ctypes.c_void_p(self.type.ctypes.data), ctypes.c_int64(n)))
+        if total < 0:
+            raise _lib.D3DError(L.d3d_last_error_string().decode())
+        if out is None:
+            out = (np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.int32), np.empty(max(total, 1)))
+        wt, wo, w = out
+        if len(wt) < n or len(wo) < n or len(w) < total:
+            raise ValueError("wire output buffers are too small")
+        s = self.host_struct()
+        if n_threads is None:
+            try:
+                n_threads = len(os.sched_getaffinity(0))
+            except AttributeError:
+                n_threads = os.cpu_count() or 1
+        _lib._check(L.d3d_pack_wire_host(ctypes.byref(s), ctypes.c_void_p(wt.ctypes.data),
+                                         ctypes.c_void_p(wo.ctypes.data), ctypes.c_void_p(w.ctypes.data),
+                                         ctypes.c_int(int(n_threads))))
+        return wt[:n], wo[:n], w[:max(total, 1)]
 
     def commit_mesh_state(self, device=None):
         """Scalar API: copy the vertex every MeshGraph ended on back into the objects

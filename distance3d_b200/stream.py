@@ -38,6 +38,13 @@ def pin_batch(cs, pairs, wire=True, out=None):
     if cs.margin is not None or cs.graph_off is not None:
         raise NotImplementedError("GjkDistanceStream batches carry no Margin / MeshGraph fields; "
                                   "use gjk_distance_batch")
+    if wire and out is not None:
+        # pack straight into the pinned buffers of an earlier batch of the same shape
+        cs.wire(out=(out["wire_type"].numpy(), out["wire_off"].numpy(), out["wire"].numpy()))
+        if out.get("has_vertex_data", True):
+            out["verts"].numpy()[...] = cs.verts
+        out["pairs"].numpy()[...] = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        return out
     if wire:
         wt, wo, w = cs.wire()
         arrays = {"wire_type": wt, "wire_off": wo, "wire": w, "verts": cs.verts}

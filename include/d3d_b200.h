@@ -58,6 +58,12 @@ int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream);
 int d3d_unpack_colliders(const uint8_t *wire_type, const int32_t *wire_off, const double *wire,
                          int64_t n, int32_t *type, double *pose, double *param, int32_t *vert_off,
                          int32_t *vert_len, void *stream);
+/* HOST functions (no CUDA call): number of doubles the records of `type[n]` take (-1: unknown
+ * type), and the packer itself - `c` holds HOST pointers, the three outputs are host buffers
+ * (pinned for the upload) with n, n and d3d_wire_size() entries; n_threads host threads. */
+int64_t d3d_wire_size(const int32_t *type, int64_t n);
+int d3d_pack_wire_host(const d3d_colliders *c, uint8_t *wire_type, int32_t *wire_off, double *wire,
+                       int n_threads);
 
 /* colliders.py:131,221,272,326,374,426,479,533,590,629 <collider>.support_function(d):
  * out[k,:] = support of collider idx[k] in direction dirs[k,:]. */

@@ -34,12 +34,9 @@ if "bvh" in what:
         print(name, "ordered-form pairs", count, "unique pairs", cu, "visits other", v_other, "self", v_self)
         assert 2 * cu + n == count
         buf = torch.empty((count, 2), dtype=torch.int32, device="cuda")
-        for w in (1, 8, 32):
-            timed(name + " other-mode all boxes, width %d" % w,
-                  lambda: bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=(w if w > 1 else 0)))
-        for w in (1, 2, 4, 8, 16, 32):
-            timed(name + " self-mode (unique pairs), width %d" % w,
-                  lambda: bvh.overlap_unique_async(buf, packet=(w if w > 1 else 0)))
+        timed(name + " other-mode all boxes, warp tiles", lambda: bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=1))
+        timed(name + " other-mode all boxes, per thread", lambda: bvh.overlap_async(bvh.aabbs, buf, order=bvh.leaf_order(), packet=0), reps=2)
+        timed(name + " self-mode (unique pairs), warp tiles", lambda: bvh.overlap_unique_async(buf))
         timed(name + " ordered two-pass packet", lambda: bvh.overlap_self(packet=True), reps=2)
         del buf, pairs, pu, bvh
         torch.cuda.empty_cache()
