@@ -247,6 +247,26 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
             gather()
         gather_ms = timed_steps(torch, dist, world, dev, gather, steps, 3) if world > 1 else 0.0
         whole_ms = timed_steps(torch, dist, world, dev, whole, steps, 3)
+        fused = None
+        if world > 1:
+            # the all-gather fused into the traversal kernel: peer stores over NVLink into a
+            # symmetric buffer (parallel.PeerPairBuffer), no separate collective
+            cmax = torch.tensor([count], dtype=torch.int64, device=dev)
+            dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+            pbuf = parallel.PeerPairBuffer(int(cmax.item()) + 1024)
+            parallel.overlap_unique_fused_gather(bvh, pbuf)
+            segs, seg_counts = pbuf.segments()
+            fused_ok = sum(seg_counts) == total and bool(
+                torch.equal(torch.sort(pair_keys(torch, torch.cat(segs), n))[0],
+                            torch.sort(pair_keys(torch, parallel.all_gather_varlen(buf[:count])[0], n))[0]))
+            fused_ms = timed_steps(torch, dist, world, dev,
+                                   lambda: parallel.overlap_unique_fused_gather(bvh, pbuf), steps, 3)
+            fused = {"query_and_gather_ms": fused_ms, "overlap_pairs_per_s": total / (fused_ms * 1e-3),
+                     "nvlink_gbs_received_per_gpu": (total - count) * 8.0 / (fused_ms * 1e-3) / 1e9,
+                     "equals_nccl_gather": fused_ok,
+                     "how": "d3d_bvh_overlap_self_gather: the traversal kernel stores every flushed chunk into all "
+                            "GPUs' buffers through peer pointers; two stream barriers included"}
+            del pbuf, segs
         recv_bytes = (total - count) * 8.0
         # the ordered form the reference returns (both orientations + (i, i)) for continuity with round 1
         full_buf = torch.empty((2 * total + n, 2), dtype=torch.int32, device=dev) if world == 1 else None
@@ -286,6 +306,8 @@ def block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak):
         }
         if ordered_ms is not None:
             entry["ordered_form_query_ms"] = ordered_ms   # d3d_bvh_overlap of all boxes (round-1 metric)
+        if fused is not None:
+            entry["fused_gather"] = fused
         if world > 1:   # the gathered list is the union of the ranks' disjoint lists
             keys = pair_keys(torch, res["g"][0], n)
             entry["gathered_pairs_unique"] = bool(torch.unique(keys).numel() == total)

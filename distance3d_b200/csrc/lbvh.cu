@@ -505,6 +505,35 @@ __device__ __forceinline__ bool boxes_overlap(double2 ax, double2 ay, double2 az
 }
 
 enum { Q_APPEND = 0, Q_COUNT = 1, Q_FILL = 2 };
+
+// Fused all-gather: when `bufs` is set, a flushed chunk is stored into the pair buffer of EVERY
+// GPU of the job (peer pointers over NVLink / NVSwitch, this GPU's own buffer included) at this
+// rank's segment, so the list is complete everywhere when the traversals end and the transfer
+// overlaps the walk chunk by chunk.
+struct PeerOut {
+    int32_t *const *bufs;  // device array of n pointers (symmetric allocation), or nullptr
+    int n, self;
+    int64_t seg_base;      // first pair slot of this rank's segment
+};
+
+__device__ __forceinline__ void flush_stage(const int2 *stage, int staged, int lane, int32_t *out_pairs,
+                                            int64_t cap, unsigned long long *cursor, const PeerOut &peers) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (peers.bufs == nullptr) {
+        for (int i = lane; i < staged; i += 32)
+            if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+    } else {
+        for (int q = 0; q < peers.n; ++q) {  // start behind myself so that the ranks do not all hit one peer
+            int p = peers.self + 1 + q;
+            if (p >= peers.n) p -= peers.n;
+            int2 *dst = reinterpret_cast<int2 *>(peers.bufs[p]) + peers.seg_base;
+            for (int i = lane; i < staged; i += 32)
+                if ((int64_t)(base + i) < cap) dst[base + i] = stage[i];
+        }
+    }
+}
 #ifndef TILE_STAGE
 #define TILE_STAGE (512 + BLOCK_LEAVES * 32)  // staged pairs per warp: flushed when less than one full tile is free
 #endif
@@ -523,7 +552,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile(Tree T, const BvhHeader *hdr, const double *__restrict__ query, const int32_t *__restrict__ order,
        int part, int n_parts, int64_t n_query, unsigned *__restrict__ counts,
        const unsigned long long *__restrict__ offsets, int32_t *out_pairs, int64_t cap,
-       unsigned long long *cursor, unsigned long long *visits) {
+       unsigned long long *cursor, unsigned long long *visits, PeerOut peers) {
     extern __shared__ double tile_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -620,11 +649,7 @@ k_tile(Tree T, const BvhHeader *hdr, const double *__restrict__ query, const int
                 staged += total;
                 if (staged > TILE_STAGE - BLOCK_LEAVES * 32) {  // room for one more full tile
                     __syncwarp();
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
-                    base = __shfl_sync(FULL, base, 0);
-                    for (int i = lane; i < staged; i += 32)
-                        if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+                    flush_stage(stage, staged, lane, out_pairs, cap, cursor, peers);
                     staged = 0;
                     __syncwarp();  // the stage is rewritten from slot 0
                 }
@@ -634,11 +659,7 @@ k_tile(Tree T, const BvhHeader *hdr, const double *__restrict__ query, const int
     }
     if (M == Q_APPEND && staged) {
         __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)staged);
-        base = __shfl_sync(FULL, base, 0);
-        for (int i = lane; i < staged; i += 32)
-            if ((int64_t)(base + i) < cap) reinterpret_cast<int2 *>(out_pairs)[base + i] = stage[i];
+        flush_stage(stage, staged, lane, out_pairs, cap, cursor, peers);
     }
     if (M == Q_COUNT && valid) counts[t] = n_hits;
     // measurement: 32-byte node records + 64-byte leaf records fetched, in units of 32 bytes
@@ -817,6 +838,13 @@ k_brute(const double *__restrict__ a1, int64_t n1, const double *__restrict__ a2
     }
 }
 
+// after a fused traversal: every GPU learns this rank's pair count
+__global__ void k_publish_count(const unsigned long long *cursor, unsigned long long *const *peer_counts, int n,
+                                int self) {
+    int p = threadIdx.x;
+    if (p < n) peer_counts[p][self] = *cursor;
+}
+
 __global__ void k_leaf_order(const unsigned long long *__restrict__ keys, int64_t n, int32_t *out) {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j < n) out[j] = (int32_t)(unsigned)(keys[j] & 0xffffffffull);
@@ -842,7 +870,7 @@ template <int M, bool SELF>
 static int launch_tile(const BvhLayout &L, int64_t n, const double *query, const int32_t *order, int part,
                        int n_parts, int64_t n_query, unsigned *counts, const unsigned long long *offsets,
                        int32_t *out_pairs, int64_t cap, unsigned long long *cursor, unsigned long long *visits,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, PeerOut peers = PeerOut{nullptr, 0, 0, 0}) {
     const size_t smem = M == Q_APPEND ? TILE_SMEM_APPEND : TILE_SMEM_FIXED;
     static bool attr_set[64] = {false};  // per instance of this template, per device
     int dev = 0;
@@ -856,7 +884,7 @@ static int launch_tile(const BvhLayout &L, int64_t n, const double *query, const
     if (ctas <= 0) return 0;
     k_tile<M, SELF><<<(unsigned)ctas, TILE_WARPS * 32, smem, stream>>>(tree_of(L, n), L.hdr, query, order, part, n_parts,
                                                                       n_query, counts, offsets, out_pairs, cap,
-                                                                      cursor, visits);
+                                                                      cursor, visits, peers);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -994,6 +1022,31 @@ int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts
     BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
     return launch_tile<Q_APPEND, true>(L, n, nullptr, nullptr, part, n_parts, n, nullptr, nullptr, out_pairs, cap,
                                        out_count, out_visits, stream);
+}
+
+/* d3d_bvh_overlap_self fused with the all-gather of the ranks' pair lists: see include/d3d_b200.h */
+int d3d_bvh_overlap_self_gather(const void *workspace, int64_t n, int part, int n_parts,
+                                int32_t *const *peer_pairs, int64_t segment_cap,
+                                unsigned long long *const *peer_counts, unsigned long long *local_count,
+                                unsigned long long *out_visits, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace || !peer_pairs || !peer_counts || !local_count)
+        return d3d_set_error("d3d_bvh_overlap_self_gather: null argument");
+    if (n_parts < 1 || n_parts > 32 || part < 0 || part >= n_parts)
+        return d3d_set_error("d3d_bvh_overlap_self_gather: part out of range (at most 32 GPUs)");
+    D3D_CUDA_CHECK(cudaMemsetAsync(local_count, 0, sizeof(unsigned long long), stream));
+    if (out_visits) D3D_CUDA_CHECK(cudaMemsetAsync(out_visits, 0, sizeof(unsigned long long), stream));
+    if (n > 0) {
+        BvhLayout L = bvh_carve(const_cast<void *>(workspace), n);
+        PeerOut peers;
+        peers.bufs = peer_pairs; peers.n = n_parts; peers.self = part; peers.seg_base = (int64_t)part * segment_cap;
+        int rc = launch_tile<Q_APPEND, true>(L, n, nullptr, nullptr, part, n_parts, n, nullptr, nullptr, nullptr,
+                                             segment_cap, local_count, out_visits, stream, peers);
+        if (rc) return rc;
+    }
+    k_publish_count<<<1, 32, 0, stream>>>(local_count, peer_counts, n_parts, part);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 /* count + fill in one call: reproducible pair order (queries in the given order, leaves in

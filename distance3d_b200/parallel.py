@@ -114,3 +114,64 @@ def overlap_unique_sharded(bvh, gather=True, out=None):
         return pairs, count
     full, counts = all_gather_varlen(pairs)
     return full, int(sum(counts))
+
+
+class PeerPairBuffer:
+    """Symmetric pair buffer for the fused self query + all-gather (`d3d_bvh_overlap_self_gather`).
+
+    Every rank allocates ``int32[world * segment_cap, 2]`` and ``uint64[world]`` through
+    `torch.distributed._symmetric_memory` (CUDA virtual-memory handles exchanged between the
+    processes of one NVLink / NVSwitch domain), so each GPU holds device pointers to the buffers
+    of all GPUs.  The traversal kernel of rank r stores its pairs into segment r of EVERY buffer;
+    after `finish()` (a barrier on the stream) each rank holds the whole list as `world`
+    segments: ``pairs[r * segment_cap : r * segment_cap + counts[r]]``.
+    """
+
+    def __init__(self, segment_cap, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.segment_cap = int(segment_cap)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.pairs = symm.empty((self.world * self.segment_cap, 2), dtype=torch.int32, device=dev)
+        self.counts = symm.empty(self.world, dtype=torch.int64, device=dev)
+        self.counts.zero_()
+        self._h_pairs = symm.rendezvous(self.pairs, self.group)
+        self._h_counts = symm.rendezvous(self.counts, self.group)
+        self.local_count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    @property
+    def peer_pairs_ptr(self):
+        return self._h_pairs.buffer_ptrs_dev
+
+    @property
+    def peer_counts_ptr(self):
+        return self._h_counts.buffer_ptrs_dev
+
+    def finish(self):
+        """All ranks' stores have landed when this returns control to the stream."""
+        self._h_pairs.barrier()
+
+    def segments(self):
+        """List of the ranks' pair lists (views; synchronises the host to read the counts)."""
+        counts = [int(c) for c in self.counts.cpu().tolist()]
+        return [self.pairs[r * self.segment_cap: r * self.segment_cap + min(c, self.segment_cap)]
+                for r, c in enumerate(counts)], counts
+
+
+def overlap_unique_fused_gather(bvh, buf, count_visits=False):
+    """Self query of a replicated BVH with the all-gather fused into the traversal kernel:
+    this rank walks its share of the leaves and stores its pairs into every GPU's
+    :class:`PeerPairBuffer` over NVLink.  Returns after the cross-GPU barrier was enqueued."""
+    import ctypes
+    from . import _lib
+    from ._lib import c_i64, ptr
+    buf.finish()   # nobody is still reading the previous round's segments
+    _lib._check(_lib.lib().d3d_bvh_overlap_self_gather(
+        ptr(bvh.workspace), c_i64(bvh.n), ctypes.c_int(buf.rank), ctypes.c_int(buf.world),
+        ctypes.c_void_p(buf.peer_pairs_ptr), c_i64(buf.segment_cap), ctypes.c_void_p(buf.peer_counts_ptr),
+        ptr(buf.local_count), ptr(bvh._visits) if count_visits else None, _lib.stream_ptr()))
+    buf.finish()
+    return buf

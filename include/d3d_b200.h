@@ -224,6 +224,22 @@ int d3d_bvh_overlap_self(const void *workspace, int64_t n, int part, int n_parts
                          int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
                          unsigned long long *out_visits, void *stream);
 
+/* d3d_bvh_overlap_self FUSED with the all-gather of the ranks' pair lists (the one collective of
+ * the multi-GPU design: "all-gather variable-length contact and result lists"): the traversal
+ * kernel itself stores every flushed chunk of pairs into the pair buffer of EVERY GPU through
+ * peer pointers over NVLink / NVSwitch, so the transfer overlaps the walk chunk by chunk and no
+ * separate collective runs afterwards.  peer_pairs: DEVICE array of n_parts pointers to the
+ * int32[n_parts * segment_cap, 2] buffers of all ranks (a symmetric allocation; entry `part` is
+ * this GPU's own); rank r's pairs land in rows [r * segment_cap, r * segment_cap + count_r) of
+ * every buffer.  peer_counts: device array of n_parts pointers to uint64[n_parts] arrays; entry
+ * [p][r] receives rank r's exact count (pairs beyond segment_cap are dropped).  local_count:
+ * this rank's cursor.  The caller synchronises the ranks afterwards (a barrier on the stream,
+ * e.g. torch symmetric memory's) before reading other ranks' segments. */
+int d3d_bvh_overlap_self_gather(const void *workspace, int64_t n, int part, int n_parts,
+                                int32_t *const *peer_pairs, int64_t segment_cap,
+                                unsigned long long *const *peer_counts, unsigned long long *local_count,
+                                unsigned long long *out_visits, void *stream);
+
 /* Morton order of the tree's objects: out[j] = object index of sorted leaf j. */
 int d3d_bvh_leaf_order(const void *workspace, int64_t n, int32_t *out, void *stream);
 

@@ -73,3 +73,15 @@ def test_all_gather_varlen_world_size_2(tmp_path):
         np.testing.assert_array_equal(np.load(tmp_path / ("full2_%d.npy" % rank)), expect2)
     c0 = np.load(tmp_path / "counts_0.npy")
     assert c0[0] + c0[1] == len(expect) and c0[3] == 0
+
+
+def test_peer_pair_buffer_contract_documented():
+    """The fused self query + all-gather needs >= 2 GPUs of one NVLink domain; its check lives in
+    scripts/check_fused_gather.py (run under torchrun on the GPU box).  Here: the C ABI exports it."""
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "distance3d_b200", "libd3d_b200.so")
+    lib = ctypes.CDLL(so)
+    assert hasattr(lib, "d3d_bvh_overlap_self_gather")
+    lib.d3d_last_error_string.restype = ctypes.c_char_p
+    assert lib.d3d_bvh_overlap_self_gather(None, ctypes.c_int64(0), 0, 1, None, ctypes.c_int64(0), None, None, None, None) == -1
+    assert b"null argument" in lib.d3d_last_error_string()
