@@ -93,7 +93,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -103,6 +103,16 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def wait_samples(self, n, timeout=15.0):
+        """Block until nvidia-smi has delivered n more samples (it takes a second to start,
+        longer when eight ranks start at once)."""
+        if self.proc is None:
+            return
+        target = len(self.lines) + n
+        t0 = time.time()
+        while len(self.lines) < target and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def stop(self):
         if self.proc is None:
@@ -690,15 +700,26 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
+        step()                      # keep the GPU under load while nvidia-smi starts
+        sampler.wait_samples(2)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    n_before = len(sampler.lines)
     ev[0].record()
     for k in range(args.steps):
         step()
         ev[k + 1].record()
     barrier()
-    clocks = sampler.stop()
+    if rank == 0:
+        sampler.lines = sampler.lines[n_before:]      # samples taken during the timed region
+        if len(sampler.lines) < 2:                    # a very short region: sample the same load again
+            for _ in range(args.steps):
+                step()
+            sampler.wait_samples(2, timeout=2.0)
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:

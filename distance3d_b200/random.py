@@ -285,7 +285,7 @@ def random_collider_set_device(seed, n, names=PRIMITIVES, center_scale=1.0, size
     `hull_library` the hulls are re-posed copies of that many shapes; the world-frame vertex
     pool is still unique per hull (the reference's ConvexHullVertices is a world-frame list)."""
     import torch
-    device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     gen = torch.Generator(device=device)
     gen.manual_seed(int(seed))
     f64 = dict(device=device, dtype=torch.float64)
@@ -347,7 +347,7 @@ def random_collider_set_device(seed, n, names=PRIMITIVES, center_scale=1.0, size
 def random_capsules_device(seed, n, center_scale=2.0, radius_scale=0.1, height_scale=0.5, device=None):
     """BASELINE configs[1] (vis_capsules_benchmark.py:22-30 scaled up) generated in HBM."""
     import torch
-    device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     gen = torch.Generator(device=device)
     gen.manual_seed(int(seed))
     pose = random_transforms_device(gen, n, device)

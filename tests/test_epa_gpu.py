@@ -103,3 +103,30 @@ def test_undefined_simplices_are_reported_not_run():
     assert not res["mtv"][bad].any() and not res["success"][bad].any()
     full = epa.epa_batch(cs, sub[~bad], g.simplex[hits][torch.from_numpy(~bad).cuda()]).cpu()
     assert np.array_equal(res["mtv"][~bad], full["mtv"]) and np.array_equal(res["status"][~bad], full["status"])
+
+
+def test_degenerate_simplices_match_the_oracle():
+    """Simplices with a duplicated point or two points closer than the edge-matching epsilon
+    (epa.py:189-191 matches loose edges by distance) exercise the coordinate-based edge matching
+    where it differs from matching by vertex identity; results are the oracle's bit for bit."""
+    import torch
+    rs = np.random.RandomState(9)
+    cs = d3random.random_collider_set(rs, 1200, names=d3random.PRIMITIVES + ("mesh",), center_scale=0.35,
+                                      hull_vertices=(6, 40))
+    pairs = d3random.random_pairs(rs, len(cs), 8000)
+    g = gjk.gjk_distance_batch(cs, pairs)
+    sel = torch.nonzero((g.dist == 0.0) & (g.n_points == 4)).flatten()
+    sub = pairs[sel.cpu().numpy()]
+    Y = g.simplex[sel].cpu().numpy().copy()
+    Y[::7, 1] = Y[::7, 0]
+    Y[3::11, 2] = Y[3::11, 3] + 1e-9
+    res = epa.epa_batch(cs, sub, Y, want_faces=True).cpu()
+    ref = O.epa(cs, sub, Y, return_faces=True, n_threads=O.max_threads())
+    assert np.array_equal(res["status"], ref["status"])
+    ok = ref["status"] != 7
+    assert np.array_equal(res["mtv"][ok], ref["mtv"][ok])
+    assert np.array_equal(res["n_faces"][ok], ref["n_faces"][ok]) and np.array_equal(res["iters"][ok], ref["iters"][ok])
+    for q in np.where(ok)[0][:300]:
+        n = ref["n_faces"][q]
+        assert np.array_equal(res["faces"][q, :n], ref["faces"][q, :n])
+    assert len(sub) > 1000 and ok.sum() > 500
