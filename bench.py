@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the broad-phase extra metrics")
     ap.add_argument("--capsules", type=int, default=1000000, help="C2: capsules in the broad phase")
-    ap.add_argument("--only", default="", choices=["", "broad", "epa", "selfcollision", "pipeline"],
+    ap.add_argument("--only", default="", choices=["", "broad", "epa", "selfcollision", "pipeline", "libccd", "hydroelastic"],
                     help="run one secondary block only and print it (development)")
     ap.add_argument("--epa-pairs", type=int, default=4 * 1024 * 1024, help="C3: EPA pairs per GPU")
     ap.add_argument("--configurations", type=int, default=10000000, help="C4: joint configurations per GPU")
@@ -550,6 +550,93 @@ def block_pipeline(args, torch, dist, rank, world, dev):
     return out
 
 
+def block_libccd(args, torch, dist, rank, world, dev):
+    """SURVEY 8f #4: the libccd-style boolean GJK as a batched cross-check of the Jolt kernel."""
+    from distance3d_b200 import gjk, random as d3random
+    n = 1 << 21
+    dc = d3random.random_collider_set_device(args.seed + 23 + 1000 * rank, 2 * n, names=d3random.PRIMITIVES,
+                                             center_scale=0.8, device=dev)
+    pairs = torch.arange(2 * n, dtype=torch.int32, device=dev).reshape(n, 2)
+    res = {}
+    ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=gjk.gjk_intersection_libccd_batch(dc, pairs)), 5, 3)
+    ms_jolt = timed_steps(torch, dist, world, dev, lambda: res.update(j=gjk.gjk_intersection_batch(dc, pairs)), 5, 3)
+    hit, jolt = res["r"][0], res["j"][0]
+    out = {"metric": "gjk_intersection_libccd_pairs_per_s", "value": world * n / (ms * 1e-3), "unit": "pairs/s",
+           "ms_per_step": ms, "pairs_per_gpu": n, "intersecting_fraction": float(hit.double().mean().item()),
+           "jolt_intersection_pairs_per_s": world * n / (ms_jolt * 1e-3),
+           "disagreements_with_jolt": int((hit != jolt).sum().item()),
+           "includes": "torch.argsort of the (typeA, typeB) keys for the processing order"}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_oracle
+        m = 200000
+        threads = cpu_oracle.max_threads()
+        cs = d3random.device_set_to_host(dc, torch.arange(2 * m, device=dev))
+        hp = np.arange(2 * m, dtype=np.int32).reshape(m, 2)
+        t0 = time.perf_counter()
+        ref = cpu_oracle.gjk_intersection_libccd(cs, hp, n_threads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "sample": "first %d pairs of rank 0" % m}
+        out["parity_on_cpu_sample"] = {"pairs": m, "booleans_equal": bool(np.array_equal(hit[:m].cpu().numpy(), ref["hit"]))}
+    del dc, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def block_hydroelastic(args, torch, dist, rank, world, dev):
+    """SURVEY 8f #3: the hydroelastic consumer of the broad phase: boxes of two tetrahedral meshes,
+    LBVH over mesh 2 queried with mesh 1, contact plane + polygon for every candidate pair."""
+    from distance3d_b200 import hydroelastic_contact as hc
+    n = 1 << 20   # tetrahedra per mesh and GPU
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed + 29 + 1000 * rank)
+    f64 = dict(device=dev, dtype=torch.float64)
+    side = float(n) ** (1.0 / 3.0) * 0.1      # ~ 8 candidate partners per tetrahedron
+
+    def mesh():
+        centre = torch.rand((n, 1, 3), generator=gen, **f64) * side
+        return (centre + (torch.rand((n, 4, 3), generator=gen, **f64) - 0.5) * 0.1).contiguous(), \
+            torch.rand((n, 4), generator=gen, **f64)
+    (tp1, e1), (tp2, e2) = mesh(), mesh()
+    res = {}
+    ms = timed_steps(torch, dist, world, dev, lambda: res.update(r=hc.find_contact_pairs(tp1, e1, tp2, e2)), 5, 3)
+    pairs, r = res["r"]
+    n_cand = int(pairs.shape[0])
+    ms_narrow = timed_steps(torch, dist, world, dev,
+                            lambda: hc.intersect_tetrahedron_pairs_batch(pairs, tp1, tp2, e1, e2), 5, 3)
+    out = {"metric": "tetrahedron_candidate_pairs_per_s", "value": all_sum(torch, dist, world, dev, n_cand) / (ms * 1e-3),
+           "unit": "pairs/s", "ms_per_step": ms, "tetrahedra_per_mesh_per_gpu": n, "candidate_pairs_per_gpu": n_cand,
+           "intersecting_fraction": float(r.hit.double().mean().item()),
+           "narrow_phase_only_pairs_per_s": all_sum(torch, dist, world, dev, n_cand) / (ms_narrow * 1e-3),
+           "stages": "d3d_tetra_aabb x2, d3d_bvh_build, d3d_bvh_overlap (per-thread walk, unsorted queries), "
+                     "d3d_tetra_intersect_pairs"}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_oracle
+        m = min(n_cand, 200000)
+        threads = cpu_oracle.max_threads()
+        sp = pairs[:m].cpu().numpy()
+        u1, i1 = np.unique(sp[:, 0], return_inverse=True)
+        u2, i2 = np.unique(sp[:, 1], return_inverse=True)
+        hp = np.stack((i1, i2), axis=1).astype(np.int32)
+        a1, b1 = tp1[torch.from_numpy(u1).to(dev).long()].cpu().numpy(), e1[torch.from_numpy(u1).to(dev).long()].cpu().numpy()
+        a2, b2 = tp2[torch.from_numpy(u2).to(dev).long()].cpu().numpy(), e2[torch.from_numpy(u2).to(dev).long()].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = cpu_oracle.tetra_pairs(hp, a1, b1, a2, b2, n_threads=threads)
+        dt = time.perf_counter() - t0
+        g = {k: v[:m].cpu().numpy() for k, v in r.__dict__.items()}
+        same = ref["hit"] == g["hit"]
+        both = (ref["hit"] == 1) & (g["hit"] == 1)
+        out["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "sample": "first %d candidate pairs of rank 0 (narrow phase only)" % m}
+        out["parity_on_cpu_sample"] = {
+            "pairs": m, "booleans_equal": bool(same.all()),
+            "max_plane_difference": float(np.abs(ref["plane"][both] - g["plane"][both]).max()) if both.any() else 0.0,
+            "max_polygon_difference": float(np.abs(ref["polygon"][both] - g["polygon"][both]).max()) if both.any() else 0.0}
+    del tp1, tp2, e1, e2, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def six_type_mix(args, torch, dist, world, dev):
     """SURVEY 8d "report both": C1 with 10-vertex convex hulls as the sixth type."""
     from distance3d_b200 import gjk, random as d3random
@@ -671,7 +758,9 @@ def main():
         block = {"broad": lambda: block_broad_phase(args, torch, dist, rank, world, dev, hbm_peak),
                  "epa": lambda: block_epa(args, torch, dist, rank, world, dev),
                  "selfcollision": lambda: block_self_collision(args, torch, dist, rank, world, dev),
-                 "pipeline": lambda: block_pipeline(args, torch, dist, rank, world, dev)}[args.only]()
+                 "pipeline": lambda: block_pipeline(args, torch, dist, rank, world, dev),
+                 "libccd": lambda: block_libccd(args, torch, dist, rank, world, dev),
+                 "hydroelastic": lambda: block_hydroelastic(args, torch, dist, rank, world, dev)}[args.only]()
         if rank == 0:
             block["n_gpus"] = world
             print(json.dumps(block))
@@ -820,6 +909,8 @@ def main():
         extras["epa"] = block_epa(args, torch, dist, rank, world, dev)
         extras["self_collision"] = block_self_collision(args, torch, dist, rank, world, dev)
         extras["pipeline"] = block_pipeline(args, torch, dist, rank, world, dev)
+        extras["libccd"] = block_libccd(args, torch, dist, rank, world, dev)
+        extras["hydroelastic"] = block_hydroelastic(args, torch, dist, rank, world, dev)
 
     if rank == 0:
         fp64_peak = measure_fp64_peak(torch, _lib)

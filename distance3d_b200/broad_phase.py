@@ -82,6 +82,8 @@ class BoundingVolumeHierarchy:
         except (OSError, ValueError, IndexError) as e:  # unreadable or malformed file: a warning
             # (fill_tree_with_colliders), the other colliders of the robot are still loaded
             raise RuntimeError("mesh collider '%s' could not be loaded: %s" % (obj.filename, e))
+        if len(vertices) == 0 or len(triangles) == 0:
+            raise RuntimeError("mesh collider '%s' has no triangles" % obj.filename)
         return MeshGraph(A2B, vertices, triangles)
 
     def add_collider(self, frame, collider):

@@ -64,7 +64,7 @@ def _load_stl(filename):
 
 def _load_obj(filename):
     vertices, triangles = [], []
-    with open(filename, "r") as f:
+    with open(filename, "r", errors="replace") as f:
         for line in f:
             parts = line.split()
             if not parts:
