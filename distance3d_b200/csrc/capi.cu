@@ -43,22 +43,6 @@ __global__ void k_prepare(d3d_colliders c, double *verts_out) {
 
 // Compact wire records -> the structure-of-arrays collider set (include/d3d_b200.h
 // d3d_unpack_colliders).  One thread per collider; the record is at wire[wire_off[i]].
-__device__ __forceinline__ int wire_doubles(int type) {
-    switch (type) {
-    case D3D_SPHERE: return 4;     // centre, radius
-    case D3D_CAPSULE: return 14;   // pose rows 0-2, radius, height
-    case D3D_CYLINDER: return 14;  // pose rows 0-2, radius, length
-    case D3D_ELLIPSOID: return 15; // pose rows 0-2, radii
-    case D3D_BOX: return 16;       // pose rows 0-2, size, (vert_off, vert_len)
-    case D3D_HULL: return 1;       // (vert_off, vert_len)
-    case D3D_MESH: return 13;      // pose rows 0-2, (vert_off, vert_len)
-    case D3D_DISK: return 7;       // centre, normal, radius
-    case D3D_ELLIPSE: return 11;   // centre, axis 0, axis 1, radii
-    case D3D_CONE: return 14;      // pose rows 0-2, radius, height
-    }
-    return 0;
-}
-
 __global__ void k_unpack(const uint8_t *__restrict__ wtype, const int32_t *__restrict__ woff,
                          const double *__restrict__ wire, int64_t n, int32_t *type, double *pose,
                          double *param, int32_t *vert_off, int32_t *vert_len) {
@@ -252,6 +236,11 @@ __global__ void k_debug_norm(const double *v, int64_t n, double *out, int mode) 
     if (t >= n) return;
     double x = v[3 * t], y = v[3 * t + 1], z = v[3 * t + 2];
     if (mode == 0) { out[t] = norm_x87(x, y, z); return; }
+    if (mode == 2) {  // the integer emulation seeded by the double-double estimate, for every vector
+        double big = fmax(fabs(x), fmax(fabs(y), fabs(z)));
+        out[t] = (big > 1e-140 && big < 1e140) ? norm_x87_core_t<true>(x, y, z) : norm_x87(x, y, z);
+        return;
+    }
     // exact emulation alone, seeded with a plain fp64 estimate
     double g = sqrt(x * x + y * y + z * z);
     out[t] = (g > 1e-140 && g < 1e140) ? norm_x87_exact(x, y, z, g, 0.0) : norm_x87(x, y, z);

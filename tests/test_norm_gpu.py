@@ -39,6 +39,20 @@ def test_exact_emulation_path_alone_is_bit_exact():
     np.testing.assert_array_equal(_lib.debug_norm(v, 1), O.norm(v))
 
 
+def test_exact_path_seeded_by_the_double_double_estimate():
+    """The hazard path as production runs it (integer root seeded by the double-double estimate),
+    forced for every vector: unit vectors whose norm rounds to 1.0 from below take it every
+    other time (EPA hands unit face normals to the sphere / ellipsoid supports)."""
+    v = _vectors()
+    np.testing.assert_array_equal(_lib.debug_norm(v, 2), O.norm(v))
+    rs = np.random.RandomState(5)
+    n = rs.randn(200000, 3)
+    n /= np.sqrt((n * n).sum(axis=1))[:, None]
+    n *= 2.0 ** rs.randint(-3, 4, size=(200000, 1))      # norms next to other powers of two as well
+    np.testing.assert_array_equal(_lib.debug_norm(n, 2), O.norm(n))
+    np.testing.assert_array_equal(_lib.debug_norm(n, 0), O.norm(n))
+
+
 def test_vector_division_equals_ieee_division():
     """v / s on the device (three quotients sharing one reciprocal refinement, d3d_math.cuh)
     is bit for bit the correctly rounded quotient, including signed zeros, subnormals,
