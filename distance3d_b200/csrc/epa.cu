@@ -22,6 +22,8 @@
 // D3D_EPA_MAX_FACES, and after max_iter iterations the result is read from the slot
 // that held the last closest face as it looks THEN.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "d3d_common.cuh"
 #include "d3d_support.cuh"
@@ -42,7 +44,8 @@ struct EpaParams {
     int32_t *out_status;
     double *out_faces;
     int *counter;
-    const int *perm;  // processing order: pairs grouped by (typeA, typeB)
+    const int *perm;   // processing order: pairs grouped by (typeA, typeB)
+    const int *n_dev;  // non-null: the length of `perm` is read from the device (fallback pass)
 };
 
 // ---------------------------------------------------------------------------
@@ -110,7 +113,9 @@ __global__ void __launch_bounds__(256) k_epa_scatter(int64_t n, EpaOrder w) {
 }
 
 inline size_t epa_au(size_t x) { return (x + 255) / 256 * 256; }
-inline size_t epa_ws_bytes(int64_t n) { return 2048 + epa_au((size_t)n) + epa_au((size_t)n * 4); }
+// counters + histogram | keys | order | fallback list | thread-kernel state
+inline size_t epa_ws_base(int64_t n) { return 2048 + epa_au((size_t)n) + 2 * epa_au((size_t)n * 4); }
+inline size_t epa_ws_bytes(int64_t n);
 
 #ifndef EPA_WARPS
 #define EPA_WARPS 4
@@ -140,6 +145,21 @@ D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v
 #ifndef EPA_BLOCKS_PER_SM
 #define EPA_BLOCKS_PER_SM 6  // 80 registers, 24 warps per SM; r02 sweep (scripts/r02_run2.sh) C3 / C5 ms at 4,5,6,8: 7.3 7.7 7.2 7.8 / 493 491 481 494
 #endif
+// -DEPA_PROFILE (development builds only, scripts/build_variant_epa.sh): cycles per phase of the
+// iteration and a few event counts, summed over all warps; read with d3d_debug_epa_profile.
+#ifdef EPA_PROFILE
+__device__ unsigned long long g_epa_prof[16];
+#define EPA_PROF_DECL long long prof_t = clock64(); unsigned long long prof[16] = {0}
+#define EPA_PROF(slot) { long long t_ = clock64(); prof[slot] += (unsigned long long)(t_ - prof_t); prof_t = t_; }
+#define EPA_COUNT(slot, v) prof[slot] += (unsigned long long)(v)
+#define EPA_PROF_FLUSH if (lane == 0) { for (int q_ = 0; q_ < 16; ++q_) if (prof[q_]) atomicAdd(&g_epa_prof[q_], prof[q_]); }
+#else
+#define EPA_PROF_DECL
+#define EPA_PROF(slot)
+#define EPA_COUNT(slot, v)
+#define EPA_PROF_FLUSH
+#endif
+
 template <int MF>
 __global__ void __launch_bounds__(EPA_WARPS * 32, EPA_BLOCKS_PER_SM)
 k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm) {
@@ -159,11 +179,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
     W.mf_rt = mf;
     const double eps = prm.epsilon;
 
+    const int64_t n_items = prm.n_dev ? (int64_t)__ldg(prm.n_dev) : n_pairs;
     for (;;) {
         int k = 0;
         if (lane == 0) {
             k = atomicAdd(prm.counter, 1);
-            k = k < n_pairs ? __ldg(prm.perm + k) : -1;
+            k = k < n_items ? __ldg(prm.perm + k) : -1;
         }
         k = __shfl_sync(FULL, k, 0);
         if (k < 0) break;
@@ -177,6 +198,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             }
             continue;
         }
+        EPA_PROF_DECL;
         int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
         __syncwarp();  // the previous pair's records are no longer read
         ColliderSmem<1> A = stage_collider_warp(c, pr.x, recA, lane), B = stage_collider_warp(c, pr.y, recB, lane);
@@ -196,6 +218,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
         int n_faces = 4, closest = 0, it = 0, status = D3D_INTERSECTION;
         bool done = false, success = false;
         v3 mtv = V3(0.0, 0.0, 0.0);
+        EPA_PROF(0);
 
         for (it = 0; it < prm.max_iter; ++it) {
             // ---- A: closest face, first arg-min of sum(v0 * n) (epa.py:104-109)
@@ -208,11 +231,13 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             }
             closest = warp_first_extreme<false>(best, bi, bi != 0x7fffffff);
             double min_dist = __shfl_sync(FULL, best, closest & 31);  // the owner's local best IS slot `closest`
+            EPA_PROF(1);
             // ---- B: support point of A - B in the face normal (epa.py:62-65)
             v3 sd = W.fget(closest, 3);
             v3 new_point = support_call<32, 1, D3D_ALL_TYPES_MASK>(A.type, A.nv, A.V, recA, c.graph, sd.x, sd.y, sd.z, lane) -
                            support_call<32, 1, D3D_ALL_TYPES_MASK>(B.type, B.nv, B.V, recB, c.graph, -sd.x, -sd.y, -sd.z, lane);
             __syncwarp();  // MeshGraph: lane 0 stored the vertex the climb ended on
+            EPA_PROF(2);
             // ---- C: convergence (epa.py:67-70)
             double proj = dot_blas(new_point, sd);
             if (proj - min_dist < eps) {
@@ -240,6 +265,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
             int n_loose = 0;
             v3 la = V3(0.0, 0.0, 0.0), lb = la;
             int nf = n_faces;
+            EPA_PROF(3);
+            EPA_COUNT(8, 1); EPA_COUNT(9, n_faces); EPA_COUNT(10, __popc(vis_lo) + __popc(vis_hi));
             {
                 // visibility by SLOT: perm is the identity here, and removing slot i moves the
                 // face (and its bit) of slot nf-1 into slot i.  The scan jumps from one visible
@@ -288,6 +315,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     --nf;
                 }
             }
+            EPA_PROF(4);
+            EPA_COUNT(11, n_faces - nf); EPA_COUNT(12, n_loose);
             // apply the permutation: slot s <- original slot perm[s] (reads before writes)
 #pragma unroll 1
             for (int base = 0; base < n_faces; base += 32) {
@@ -301,6 +330,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 __syncwarp();
             }
             n_faces = nf;
+            EPA_PROF(5);
             // ---- E: one new face per loose edge (epa.py:126-146)
             bool overflow = false;
             if (n_loose > 0) {
@@ -333,6 +363,7 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                 n_faces += n_new;
                 __syncwarp();
             }
+            EPA_PROF(6);
             if (overflow) { status = D3D_EPA_MAX_FACES; done = true; ++it; break; }
             __syncwarp();
         }
@@ -358,9 +389,365 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #pragma unroll 1
                 for (int w = 0; w < 4; ++w) st3(o + 12 * i + 3 * w, W.fget(i, w));
         }
+        EPA_PROF(7);
+        EPA_PROF_FLUSH;
         __syncwarp();
     }
 }
+
+
+// ---------------------------------------------------------------------------
+// Thread-per-pair EPA (the default limits max_faces = 64, max_loose_edges = 32, max_iter <= 64).
+//
+// The warp kernel above spends most of its issue slots on work that one lane could do: the two
+// support calls, the convergence test and the edge bookkeeping are replicated on 32 lanes
+// (profiles/r02_epa_phases.txt: ~2000 warp instructions per expanding iteration).  Here a thread
+// owns a pair and replays epa.py:9-202 sequentially, 32 pairs per warp instruction:
+//   * polytope vertices get small integer ids (table of <= 4 + max_iter points); a face is three
+//     ids, its normal and its cached distance np.sum(v0 * n) (the value find_face_closest_to_origin
+//     recomputes every iteration from the same two vectors); a loose edge is two ids.
+//   * the reference matches edges by COORDINATES with a tolerance (epa.py:189-191).  A new vertex
+//     is compared with every vertex of the table: bit-equal -> it re-uses that id; closer than
+//     epsilon but not equal -> the pair is handed to the warp kernel.  So distinct ids are at
+//     least epsilon apart and "ids equal" is exactly the reference's test.
+//   * state lives in global memory, element e of thread t at [e * T + t]: the threads of a warp
+//     walk their face lists in step, so the accesses coalesce, and L1 / L2 hold the working set
+//     (~2.5 KB per pair in use).  Collider records and the loose-edge list are in shared memory.
+//   * pairs the thread kernel does not finish (MeshGraph colliders, near-duplicate vertices,
+//     max_iter reached - the reference then reads a face slot as it looks at that time) go to a
+//     list that the warp kernel processes afterwards from scratch.
+// A thread runs one iteration per trip of a flat loop and fetches its next pair at the loop head,
+// so the lanes of a warp stay converged on the iteration body whatever their pairs' lengths.
+#define EPAT_THREADS 128
+#ifndef EPAT_BLOCKS_PER_SM
+#define EPAT_BLOCKS_PER_SM 4
+#endif
+#define EPAT_MAX_BLOCKS (148 * EPAT_BLOCKS_PER_SM)
+#define EPAT_MAXV 68  // 4 + max_iter
+#define EPAT_MF 64
+#define EPAT_ML 32
+#define EPAT_TM (D3D_ALL_TYPES_MASK & ~(1 << D3D_MESH))
+#ifndef EPAT_MAX_VERTICES
+#define EPAT_MAX_VERTICES 32  // hulls with more vertices go to the warp kernel (cooperative vertex scan)
+#endif
+#define EPAT_STATE_BYTES ((size_t)(EPAT_MAXV * 24 + EPAT_MF * 24 + EPAT_MF * 8 + EPAT_MF * 4))
+#define EPAT_SMEM_BYTES ((size_t)EPAT_THREADS * (2 * D3D_COLLIDER_FIELDS * 8 + EPAT_ML * 2))
+
+struct EpaThreadState {
+    double *vtx;     // [EPAT_MAXV * 3][T]
+    double *fnrm;    // [EPAT_MF * 3][T]
+    double *fdist;   // [EPAT_MF][T]
+    uint32_t *fids;  // [EPAT_MF][T]  id0 | id1 << 8 | id2 << 16
+    int64_t T;
+    int *fb_count;
+    int *fb_list;
+};
+
+static __device__ __noinline__ v3 face_normal_call(v3 v0, v3 v1, v3 v2) { return face_normal(v0, v1, v2); }
+
+__global__ void __launch_bounds__(EPAT_THREADS, EPAT_BLOCKS_PER_SM)
+k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm, EpaThreadState S) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int64_t T = S.T;
+    double *recA = smem + tid, *recB = recA + D3D_COLLIDER_FIELDS * EPAT_THREADS;
+    uint16_t *loose = reinterpret_cast<uint16_t *>(smem + 2 * D3D_COLLIDER_FIELDS * EPAT_THREADS) + tid;
+    double *vtx = S.vtx + blockIdx.x * (int64_t)EPAT_THREADS + tid;
+    double *fnrm = S.fnrm + blockIdx.x * (int64_t)EPAT_THREADS + tid;
+    double *fdist = S.fdist + blockIdx.x * (int64_t)EPAT_THREADS + tid;
+    uint32_t *fids = S.fids + blockIdx.x * (int64_t)EPAT_THREADS + tid;
+    const double eps = prm.epsilon;
+#define VT(j) V3(vtx[(3 * (j)) * T], vtx[(3 * (j) + 1) * T], vtx[(3 * (j) + 2) * T])
+#define FN(i) V3(fnrm[(3 * (i)) * T], fnrm[(3 * (i) + 1) * T], fnrm[(3 * (i) + 2) * T])
+#define SET_FACE(i, ids_, n_, d_)                                                        \
+    {                                                                                    \
+        fids[(i) * T] = (ids_);                                                          \
+        fnrm[(3 * (i)) * T] = (n_).x; fnrm[(3 * (i) + 1) * T] = (n_).y; fnrm[(3 * (i) + 2) * T] = (n_).z; \
+        fdist[(i) * T] = (d_);                                                           \
+    }
+    int k = -1, n_faces = 0, it = 0, nv = 0, closest = 0;
+    double vmax = 0.0;  // largest |coordinate| in the vertex table
+    double min_dist = 0.0;
+    bool need_scan = true;
+    ColliderSmem<EPAT_THREADS> A, B;
+    A.base = recA; B.base = recB; A.gpool = B.gpool = c.graph;
+    A.type = B.type = 0; A.nv = B.nv = 0; A.V = B.V = nullptr;
+    const unsigned FULL = 0xffffffffu;
+    bool exhausted = false;
+
+    // Near pairs: two DIFFERENT table entries closer than epsilon (the reference's edge test would
+    // call them equal).  Up to four pairs (a | b << 8) are remembered per polytope; with none -
+    // nearly always - "ids equal" is the whole test.
+    unsigned long long near_pairs = 0ull, near_ids = 0ull;  // near_ids: bit i = vertex i is in a near pair
+    int n_near = 0;
+    auto same_vertex = [&](uint32_t x, uint32_t y) -> bool {
+        if (x == y) return true;
+        const unsigned long long a = x | (y << 8), b = y | (x << 8);
+        bool hit = false;
+        for (int q = 0; q < n_near; ++q) {
+            const unsigned long long e = (near_pairs >> (16 * q)) & 0xffffull;
+            hit |= e == a || e == b;
+        }
+        return hit;
+    };
+    // id of point p in the vertex table: an existing bit-equal vertex or a new entry; -1 when the
+    // near-pair list is full (-> warp kernel)
+    auto vertex_id = [&](v3 p) -> int {
+        int same_as = -1, n_close = 0;
+        unsigned close_ids = 0u;  // up to four table entries within epsilon of p
+        for (int j0 = 0; j0 < nv; j0 += 4) {  // four table entries per trip: their 12 loads are in flight together
+            v3 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = VT(min(j0 + u, EPAT_MAXV - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v3 d = q[u] - p;
+                if (j0 + u < nv && dot_blas(d, d) < prm.eps_sq_thr) {
+                    bool same = __double_as_longlong(q[u].x) == __double_as_longlong(p.x) &&
+                                __double_as_longlong(q[u].y) == __double_as_longlong(p.y) &&
+                                __double_as_longlong(q[u].z) == __double_as_longlong(p.z);
+                    if (same && same_as < 0) same_as = j0 + u;
+                    if (!same) {
+                        if (n_close < 4) close_ids |= (unsigned)(j0 + u) << (8 * n_close);
+                        ++n_close;
+                    }
+                }
+            }
+        }
+        if (same_as >= 0) return same_as;
+        if (n_near + n_close > 4) return -1;
+        for (int q = 0; q < n_close; ++q) {
+            const unsigned other = (close_ids >> (8 * q)) & 0xffu;
+            near_pairs |= (unsigned long long)(other | ((unsigned)nv << 8)) << (16 * n_near);
+            near_ids |= (1ull << min(other, 63u)) | (1ull << min(nv, 63));  // ids 63.. share the last bit
+            ++n_near;
+        }
+        vtx[(3 * nv) * T] = p.x; vtx[(3 * nv + 1) * T] = p.y; vtx[(3 * nv + 2) * T] = p.z;
+        vmax = fmax(vmax, fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z))));
+        return nv++;
+    };
+    auto fall_back = [&]() { S.fb_list[atomicAdd(S.fb_count, 1)] = k; k = -1; };
+    auto finish = [&](v3 mtv, bool success, int status) {
+        st3(prm.out_mtv + 3 * (int64_t)k, mtv);
+        prm.out_success[k] = success ? 1 : 0;
+        if (prm.out_nfaces) prm.out_nfaces[k] = n_faces;
+        if (prm.out_iters) prm.out_iters[k] = it + 1;
+        if (prm.out_status) prm.out_status[k] = status;
+        k = -1;
+    };
+
+    // Every trip of this loop is one EPA iteration of every lane that owns a pair.  The loop is
+    // warp-uniform (ballots at its head, no lane leaves early) so the lanes re-converge on each
+    // phase; idle lanes are refilled once EPAT_REFILL_MIN of them wait (32: a warp takes 32 pairs
+    // and runs them to the end together - lanes that started together have polytopes of similar
+    // size, which keeps the face loops of a warp the same length; C5 mix, ms at 8 / 16 / 24 / 32:
+    // 53.0 45.3 41.1 39.0).
+#ifndef EPAT_REFILL_MIN
+#define EPAT_REFILL_MIN 32
+#endif
+    for (;;) {
+        unsigned run_mask = __ballot_sync(FULL, k >= 0);
+        if (32 - __popc(run_mask) >= EPAT_REFILL_MIN || run_mask == 0) {
+            if (k < 0 && !exhausted) do {  // next pair (epa.py:83-97)
+                int q = atomicAdd(prm.counter, 1);
+                if (q >= n_pairs) { exhausted = true; break; }
+                k = __ldg(prm.perm + q);
+                n_faces = 0; it = -1; nv = 0; vmax = 0.0; near_pairs = 0ull; near_ids = 0ull; n_near = 0;
+                if (prm.npoints && __ldg(prm.npoints + k) != 4) {  // undefined in the reference (np.empty rows)
+                    finish(V3(0.0, 0.0, 0.0), false, D3D_EPA_BAD_SIMPLEX);
+                    break;
+                }
+                it = 0;
+                int2 pr = __ldg(reinterpret_cast<const int2 *>(pairs) + k);
+                A = stage_collider<EPAT_THREADS>(c, pr.x, recA);
+                B = stage_collider<EPAT_THREADS>(c, pr.y, recB);
+                if (A.type == D3D_MESH || B.type == D3D_MESH || A.nv > EPAT_MAX_VERTICES || B.nv > EPAT_MAX_VERTICES) {
+                    fall_back();
+                    break;
+                }
+                const double *Y = prm.Y + 12 * (int64_t)k;
+                int id[4];
+                bool near = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    id[i] = vertex_id(ld3(Y + 3 * i));
+                    near |= id[i] < 0;
+                }
+                if (near) { fall_back(); break; }
+#pragma unroll 1
+                for (int f = 0; f < 4; ++f) {  // faces ABC, ACD, ADB, BDC
+                    const int a = id[(0x1000 >> (4 * f)) & 3], b = id[(0x3321 >> (4 * f)) & 3], cc = id[(0x2132 >> (4 * f)) & 3];
+                    v3 v0 = VT(a);
+                    v3 n = face_normal_call(v0, VT(b), VT(cc));
+                    const double d = dot_plain(v0, n);
+                    SET_FACE(f, (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)cc << 16), n, d);
+                    if (f == 0 || d < min_dist) { min_dist = d; closest = f; }  // first arg-min, in slot order
+                }
+                n_faces = 4;
+                need_scan = false;
+            } while (0);
+            run_mask = __ballot_sync(FULL, k >= 0);
+            if (run_mask == 0) {
+                if (__all_sync(FULL, exhausted)) break;
+                continue;
+            }
+        }
+        bool go = k >= 0;
+        // ---- closest face, first arg-min (epa.py:104-109).  The minimum over the faces that
+        // survive an iteration is collected while their visibility is tested, and the new faces
+        // are compared as they are made; only an exact tie between two survivors (whose slot
+        // order changes with the removals) needs the scan over all faces.
+        if (go && need_scan) {
+            min_dist = fdist[0];
+            closest = 0;
+#pragma unroll 4
+            for (int i = 1; i < n_faces; ++i) {
+                double d = fdist[i * T];
+                if (d < min_dist) { min_dist = d; closest = i; }
+            }
+        }
+        __syncwarp();
+        // ---- support point of A - B in the face normal (epa.py:62-65), convergence (epa.py:67-70)
+        v3 p = V3(0.0, 0.0, 0.0);
+        int pid = 0;
+        if (go) {
+            v3 sd = FN(closest);
+            p = support_call<1, EPAT_THREADS, EPAT_TM>(A.type, A.nv, A.V, recA, c.graph, sd.x, sd.y, sd.z, 0) -
+                support_call<1, EPAT_THREADS, EPAT_TM>(B.type, B.nv, B.V, recB, c.graph, -sd.x, -sd.y, -sd.z, 0);
+            double proj = dot_blas(p, sd);
+            if (proj - min_dist < eps) {
+                finish(sd * proj, true, D3D_INTERSECTION);
+                go = false;
+            }
+        }
+        __syncwarp();
+        if (go) {
+            pid = vertex_id(p);
+            if (pid < 0) { fall_back(); go = false; }
+        }
+        __syncwarp();
+        // ---- faces that see the new point (epa.py:122-124).  dot(n, p) - dist differs from the
+        // reference's dot(n, p - v0) by rounding only (< 29 ulp of the largest coordinate); the
+        // exact expression, which needs the face's first vertex, is evaluated inside that band.
+        unsigned long long vis = 0ull;
+        double smin = D3D_MAX_FLOAT;  // minimum of dist over the survivors, its slot, exact tie seen
+        int smin_slot = 0;
+        bool tie = false;
+        if (go) {
+            const double margin = 1e-13 * vmax;
+            unsigned long long amb = 0ull;
+            for (int i0 = 0; i0 < n_faces; i0 += 4) {  // four faces per trip: 16 loads in flight together
+                v3 n[4];
+                double dd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + u, EPAT_MF - 1);
+                    n[u] = FN(i);
+                    dd[u] = fdist[i * T];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u;
+                    if (i < n_faces) {
+                        double sgn = dot_blas(n[u], p) - dd[u];
+                        if (sgn > eps + margin) vis |= 1ull << i;
+                        else if (sgn >= eps - margin) amb |= 1ull << i;
+                        else if (dd[u] < smin) { smin = dd[u]; smin_slot = i; tie = false; }
+                        else if (dd[u] == smin) tie = true;
+                    }
+                }
+            }
+            while (amb) {  // rare: inside the rounding band, the reference's own expression decides
+                const int i = __ffsll((long long)amb) - 1;
+                amb &= amb - 1ull;
+                const double d = fdist[i * T];
+                if (dot_blas(FN(i), p - VT(fids[i * T] & 0xffu)) > eps) vis |= 1ull << i;
+                else if (d < smin) { smin = d; smin_slot = i; tie = false; }
+                else if (d == smin) tie = true;
+            }
+        }
+        __syncwarp();
+        // ---- remove them, loose edges (epa.py:157-202): removing slot i moves the last face (and
+        // its visibility bit) into slot i
+        int n_loose = 0;
+        if (go) {
+            int i = 0;
+            for (;;) {
+                unsigned long long rest = (vis >> i) << i;
+                if (n_faces < 64) rest &= (1ull << n_faces) - 1ull;
+                if (rest == 0ull) break;
+                i = __ffsll((long long)rest) - 1;
+                const uint32_t ids = fids[i * T];
+                uint32_t ring = ids | (ids << 24);  // id0 id1 id2 id0
+#pragma unroll 1
+                for (int j = 0; j < 3; ++j, ring >>= 8) {
+                    // entry = la | lb << 8; it matches when lb == e0 and la == e1 (epa.py:189-191)
+                    const uint32_t e0 = ring & 0xffu, e1 = (ring >> 8) & 0xffu;
+                    const uint16_t want = (uint16_t)(e1 | (e0 << 8));
+                    int e = 0;
+                    if ((((near_ids >> min(e0, 63u)) | (near_ids >> min(e1, 63u))) & 1ull) == 0ull) {
+                        // neither end of this edge has a near twin: equal ids is the whole test
+                        while (e < n_loose && loose[e * EPAT_THREADS] != want) ++e;
+                    } else {
+                        for (; e < n_loose; ++e) {
+                            const uint32_t le = loose[e * EPAT_THREADS];
+                            if (same_vertex(le >> 8, e0) && same_vertex(le & 0xffu, e1)) break;
+                        }
+                    }
+                    if (e < n_loose) {  // overwrite_edge_with_last_edge (epa.py:200-202)
+                        --n_loose;
+                        loose[e * EPAT_THREADS] = loose[n_loose * EPAT_THREADS];
+                    } else {            // add_edge_to_list (epa.py:193-198)
+                        if (n_loose >= EPAT_ML) break;
+                        loose[n_loose * EPAT_THREADS] = (uint16_t)(e0 | (e1 << 8));
+                        ++n_loose;
+                    }
+                }
+                const int last = n_faces - 1;  // remove_face (epa.py:118-120)
+                const unsigned long long last_bit = (vis >> last) & 1ull;
+                if (i != last) {
+                    v3 n = FN(last);
+                    SET_FACE(i, fids[last * T], n, fdist[last * T]);
+                    if (smin_slot == last) smin_slot = i;
+                }
+                vis = (vis & ~(1ull << i) & ~(1ull << last)) | (i < last ? (last_bit << i) : 0ull);
+                n_faces = last;
+            }
+        }
+        __syncwarp();
+        // ---- one new face per loose edge (epa.py:126-146)
+        if (go) {
+            bool overflow = false;
+#pragma unroll 1
+            for (int e = 0; e < n_loose; ++e) {
+                if (n_faces >= EPAT_MF) { overflow = true; break; }  // assert self.n_faces < self.max_faces
+                const uint32_t ed = loose[e * EPAT_THREADS];
+                uint32_t id0 = ed & 0xffu;
+                const uint32_t id1 = ed >> 8;
+                v3 v0 = VT(id0), v1 = VT(id1);
+                v3 n = face_normal_call(v0, v1, p);
+                if (dot_blas(n, n) < prm.half_sq_thr) continue;
+                if (dot_blas(v0, n) + 1e-6 < 0.0) { id0 = id1; v0 = v1; n = -n; }  // epa.py:139-146
+                const double d = dot_plain(v0, n);
+                SET_FACE(n_faces, id0 | (id1 << 8) | ((uint32_t)pid << 16), n, d);
+                if (d < smin) { smin = d; smin_slot = n_faces; }  // survivors sit in lower slots: they win ties
+                ++n_faces;
+            }
+            min_dist = smin; closest = smin_slot; need_scan = tie;
+            if (overflow) finish(V3(0.0, 0.0, 0.0), false, D3D_EPA_MAX_FACES);
+            else if (++it >= prm.max_iter) fall_back();  // epa.py:76-78 reads the last closest slot as it is now
+        }
+    }
+#undef VT
+#undef FN
+#undef SET_FACE
+}
+
+inline int64_t epat_threads_for(int64_t n) {
+    int64_t blocks = d3d_min64((n + EPAT_THREADS - 1) / EPAT_THREADS, EPAT_MAX_BLOCKS);
+    return blocks * EPAT_THREADS;
+}
+inline size_t epa_ws_bytes(int64_t n) { return epa_ws_base(n) + epa_au((size_t)epat_threads_for(n) * EPAT_STATE_BYTES); }
 
 // smallest double t with sqrt(t) >= x (sqrt is correctly rounded and monotone on host and device)
 double sqrt_threshold(double x) {
@@ -373,6 +760,18 @@ double sqrt_threshold(double x) {
 }  // namespace
 
 extern "C" {
+
+#ifdef EPA_PROFILE
+int d3d_debug_epa_profile(unsigned long long *out16, int reset) {
+    D3D_CUDA_CHECK(cudaDeviceSynchronize());
+    D3D_CUDA_CHECK(cudaMemcpyFromSymbol(out16, g_epa_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        D3D_CUDA_CHECK(cudaMemcpyToSymbol(g_epa_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
 
 size_t d3d_epa_workspace_bytes(int64_t n_pairs) { return epa_ws_bytes(n_pairs); }
 
@@ -404,16 +803,40 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
         ord.perm = reinterpret_cast<int *>(p + 2048 + epa_au((size_t)n_pairs));
     }
     prm.perm = ord.perm;
+    prm.n_dev = nullptr;
+    const int sms = d3d_sm_count();
     {
-        int sms = d3d_sm_count();
         int kb = (int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8);
         k_epa_keys<<<kb, 256, 0, stream>>>(*c, pairs, npoints, n_pairs, ord);
         k_epa_scan<<<1, 32, 0, stream>>>(ord);
         k_epa_scatter<<<(int)d3d_min64((n_pairs + 2047) / 2048, (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, ord);
     }
+    // Thread-per-pair kernel first (reference default limits, no polytope output); what it hands
+    // back is finished by the warp kernel.  D3D_EPA_KERNEL=warp forces the warp kernel alone (tests
+    // compare the two).
+    const char *mode = getenv("D3D_EPA_KERNEL");
+    const bool warp_only = mode && strcmp(mode, "warp") == 0;
+    if (!warp_only && max_faces == EPAT_MF && max_loose_edges == EPAT_ML && max_iter <= EPAT_MAXV - 4 && !out_faces) {
+        char *p = reinterpret_cast<char *>(workspace);
+        EpaThreadState S;
+        S.T = epat_threads_for(n_pairs);
+        S.fb_count = reinterpret_cast<int *>(p + 8);
+        S.fb_list = reinterpret_cast<int *>(p + 2048 + epa_au((size_t)n_pairs) + epa_au((size_t)n_pairs * 4));
+        char *st = p + epa_ws_base(n_pairs);
+        S.vtx = reinterpret_cast<double *>(st);
+        S.fnrm = S.vtx + (size_t)EPAT_MAXV * 3 * S.T;
+        S.fdist = S.fnrm + (size_t)EPAT_MF * 3 * S.T;
+        S.fids = reinterpret_cast<uint32_t *>(S.fdist + (size_t)EPAT_MF * S.T);
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPAT_SMEM_BYTES));
+        k_epa_thread<<<(int)(S.T / EPAT_THREADS), EPAT_THREADS, EPAT_SMEM_BYTES, stream>>>(*c, pairs, n_pairs, prm, S);
+        D3D_CUDA_CHECK(cudaGetLastError());
+        prm.perm = S.fb_list;
+        prm.n_dev = S.fb_count;
+        prm.counter = reinterpret_cast<int *>(p + 16);
+    }
     size_t per_warp = (size_t)12 * max_faces + (max_faces + 1) / 2 + 2 + 2 * D3D_COLLIDER_FIELDS;
     size_t smem = per_warp * EPA_WARPS * sizeof(double);
-    int blocks = (int)d3d_min64((n_pairs + EPA_WARPS - 1) / EPA_WARPS, (int64_t)d3d_sm_count() * (EPA_BLOCKS_PER_SM + 2));
+    int blocks = (int)d3d_min64((n_pairs + EPA_WARPS - 1) / EPA_WARPS, (int64_t)sms * (EPA_BLOCKS_PER_SM + 2));
     if (max_faces == 64) {
         D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_epa<64><<<blocks, EPA_WARPS * 32, smem, stream>>>(*c, pairs, n_pairs, prm);

@@ -15,13 +15,15 @@ from .pack import pack_colliders
 
 
 class EpaResult:
-    def __init__(self, mtv, success, n_faces, iters, status, faces=None):
+    def __init__(self, mtv, success, n_faces, iters, status, faces=None, deferred=None):
         self.mtv = mtv
         self.success = success
         self.n_faces = n_faces
         self.iters = iters
         self.status = status
         self.faces = faces
+        # int32[1]: pairs the thread-per-pair kernel handed to the warp kernel (diagnostic)
+        self.deferred = deferred
 
     def cpu(self):
         return {k: (v.cpu().numpy() if v is not None else None) for k, v in self.__dict__.items()}
@@ -59,6 +61,7 @@ def epa_batch(colliders, pairs, simplices, max_iter=64, max_loose_edges=32, max_
         c_int(max_loose_edges), c_int(max_faces), c_dbl(epsilon), ptr(res.mtv), ptr(res.success),
         ptr(res.n_faces), ptr(res.iters), ptr(res.status), ptr(res.faces), ptr(ws),
         c_size(ws.numel()), _lib.stream_ptr()))
+    res.deferred = ws[8:12].view(torch.int32).clone()
     return res
 
 

@@ -5,9 +5,9 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
 python -m distance3d_b200.build > /dev/null
-mkdir -p /tmp/d3dvar
+mkdir -p gpurun_out/d3dvar
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC "$@" \
-  -c ${SRC:-distance3d_b200/csrc}/gjk.cu -o /tmp/d3dvar/gjk_$name.o
+  -c ${SRC:-distance3d_b200/csrc}/gjk.cu -o gpurun_out/d3dvar/gjk_$name.o
 objs=$(ls distance3d_b200/build/*.o | grep -v '/gjk.o')
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o scripts/lib_$name.so $objs /tmp/d3dvar/gjk_$name.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o scripts/lib_$name.so $objs gpurun_out/d3dvar/gjk_$name.o
 echo scripts/lib_$name.so

@@ -1,4 +1,6 @@
-"""GPU: warp-cooperative EPA against the oracle and the real reference's outputs.
+"""GPU: EPA (thread-per-pair kernel + warp kernel) against the oracle and the real reference's outputs.
+`want_faces=True` runs the warp kernel alone (the thread kernel does not keep the polytope in the
+reference's layout); without it the thread kernel runs first and hands over what it cannot finish.
 
 Tolerance from BASELINE.json: penetration depth and normal within 1e-7; the
 implementation is in fact bit-exact (asserted)."""
@@ -28,6 +30,19 @@ def test_golden_epa_vs_reference_outputs():
     for q in np.where(m)[0]:
         n = res["n_faces"][q]
         assert np.array_equal(res["faces"][q, :n], g["faces"][sel[q], :n])
+
+
+def test_golden_epa_thread_kernel():
+    cs, g = load_golden("epa.npz")
+    sel = np.where(g["status"] >= 0)[0]
+    res = epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel]).cpu()
+    asserted = g["status"][sel] == 7
+    assert np.array_equal(res["status"] == 7, asserted)
+    m = ~asserted
+    assert np.array_equal(res["mtv"][m], g["mtv"][sel][m])
+    assert np.array_equal(res["success"][m], g["success"][sel][m])
+    assert np.array_equal(res["n_faces"][m], g["n_faces"][sel][m])
+    assert int(res["deferred"][0]) < 0.2 * len(sel)
 
 
 def test_golden_wide_hulls():
@@ -67,6 +82,15 @@ def test_random_pipeline_gjk_then_epa(names, scale, hv):
     # property (reference test_epa.py:37-60): translating B by mtv separates the shapes
     conv = ok & (ref["success"] == 1)
     assert conv.sum() > 100
+    # the same batch through the thread-per-pair kernel
+    thr = epa.epa_batch(cs, pairs[sel], g.simplex[sel.tolist()]).cpu()
+    assert np.array_equal(thr["status"], ref["status"])
+    for key in ("mtv", "success", "n_faces", "iters"):
+        assert np.array_equal(thr[key][ok], ref[key][ok]), key
+    if hv[0] > 32:   # hulls with more than 32 vertices are the warp kernel's (cooperative vertex scan)
+        assert int(thr["deferred"][0]) == len(sel)
+    else:
+        assert int(thr["deferred"][0]) < 0.5 * len(sel)
 
 
 def test_scalar_epa_known_answer():
@@ -130,3 +154,31 @@ def test_degenerate_simplices_match_the_oracle():
         n = ref["n_faces"][q]
         assert np.array_equal(res["faces"][q, :n], ref["faces"][q, :n])
     assert len(sub) > 1000 and ok.sum() > 500
+    # thread-per-pair kernel: duplicated points share a vertex id, near-duplicates are kept as
+    # "near pairs" that the edge matching treats as equal, like the reference's distance test
+    thr = epa.epa_batch(cs, sub, Y).cpu()
+    assert np.array_equal(thr["status"], ref["status"])
+    for key in ("mtv", "success", "n_faces", "iters"):
+        assert np.array_equal(thr[key][ok], ref[key][ok]), key
+    assert int(thr["deferred"][0]) < 0.15 * len(sub)   # near-pair list full or max_iter reached
+
+
+def test_thread_and_warp_kernels_agree_on_a_large_mixed_batch(monkeypatch):
+    import torch
+    rs = np.random.RandomState(31)
+    cs = d3random.random_collider_set(rs, 20000, names=d3random.PRIMITIVES + ("mesh", "cone"),
+                                      center_scale=0.9, hull_vertices=(4, 60))
+    pairs = d3random.random_pairs(rs, len(cs), 400000)
+    g = gjk.gjk_distance_batch(cs, pairs)
+    hits = torch.nonzero(g.dist == 0.0).flatten()
+    sub, Y, npts = pairs[hits.cpu().numpy()], g.simplex[hits], g.n_points[hits]
+    assert len(sub) > 50000
+    thr = epa.epa_batch(cs, sub, Y, n_points=npts).cpu()
+    monkeypatch.setenv("D3D_EPA_KERNEL", "warp")
+    wrp = epa.epa_batch(cs, sub, Y, n_points=npts).cpu()
+    assert int(wrp["deferred"][0]) == 0 and int(thr["deferred"][0]) < 0.6 * len(sub)   # hulls of 33..60 vertices
+    assert np.array_equal(thr["status"], wrp["status"])
+    ok = wrp["status"] != 7
+    for key in ("mtv", "success", "n_faces", "iters"):
+        assert np.array_equal(thr[key][ok], wrp[key][ok]), key
+    assert np.array_equal(thr["iters"], wrp["iters"])
