@@ -281,9 +281,10 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                     int f = W.perm[i];
                     // epa.py:167-187: edges of the removed face against the loose-edge list
                     v3 fv0 = W.fget(f, 0), fv1 = W.fget(f, 1), fv2 = W.fget(f, 2);  // broadcast reads
-#pragma unroll 1
-                    for (int j = 0; j < 3; ++j) {
-                        v3 e0 = j == 0 ? fv0 : (j == 1 ? fv1 : fv2), e1 = j == 0 ? fv1 : (j == 1 ? fv2 : fv0);
+                    // one edge against the list; false when the list is full (epa.py:193-198, the
+                    // caller then drops the remaining edges of this face).  Three inlined copies:
+                    // selecting the end points by a loop index cost 9 % of the kernel's instructions.
+                    auto edge = [&](v3 e0, v3 e1) -> bool {
                         // np.linalg.norm(x) < eps without the square root (exactly equivalent)
                         v3 d0 = lb - e0, d1 = la - e1;
                         bool match = lane < n_loose && dot_blas(d0, d0) < prm.eps_sq_thr &&
@@ -298,11 +299,13 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
                             if (lane == found) { la = ta; lb = tb; }
                             --n_loose;
                         } else {  // add_edge_to_list (epa.py:193-198)
-                            if (n_loose >= ml) break;
+                            if (n_loose >= ml) return false;
                             if (lane == n_loose) { la = e0; lb = e1; }
                             ++n_loose;
                         }
-                    }
+                        return true;
+                    };
+                    if (edge(fv0, fv1) && edge(fv1, fv2)) edge(fv2, fv0);
                     // remove_face (epa.py:118-120): slot i takes the last face, re-test slot i.
                     // Every lane stores the same value; the barriers only order the uniform
                     // reads and writes of the other lanes (racecheck-clean).
@@ -428,7 +431,14 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #define EPAT_ML 32
 #define EPAT_TM (D3D_ALL_TYPES_MASK & ~(1 << D3D_MESH))
 #ifndef EPAT_MAX_VERTICES
-#define EPAT_MAX_VERTICES 32  // hulls with more vertices go to the warp kernel (cooperative vertex scan)
+// Hulls with more vertices go to the warp kernel (cooperative vertex scan).  Measured on C3 (hulls
+// of 64-256 vertices, 4 Mi pairs): warp kernel 243 ms; thread kernel with a serial scan per thread
+// 266 ms; thread kernel whose warp scans the wide hulls of its 32 lanes one after the other 268 ms
+// (64 dependent scans per warp and iteration) - both rejected.
+#define EPAT_MAX_VERTICES 32
+#endif
+#ifndef EPAT_MIN_PAIRS
+#define EPAT_MIN_PAIRS 20000
 #endif
 #define EPAT_STATE_BYTES ((size_t)(EPAT_MAXV * 24 + EPAT_MF * 24 + EPAT_MF * 8 + EPAT_MF * 4))
 #define EPAT_SMEM_BYTES ((size_t)EPAT_THREADS * (2 * D3D_COLLIDER_FIELDS * 8 + EPAT_ML * 2))
@@ -812,10 +822,14 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
         k_epa_scatter<<<(int)d3d_min64((n_pairs + 2047) / 2048, (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, ord);
     }
     // Thread-per-pair kernel first (reference default limits, no polytope output); what it hands
-    // back is finished by the warp kernel.  D3D_EPA_KERNEL=warp forces the warp kernel alone (tests
-    // compare the two).
+    // back is finished by the warp kernel.  A thread works through its pair alone, so the kernel
+    // needs many pairs per SM to pay off (measured cross-over ~2e4 pairs on B200); smaller
+    // batches go to the warp kernel directly.  D3D_EPA_KERNEL=warp / thread overrides the choice
+    // (tests compare the two kernels).
     const char *mode = getenv("D3D_EPA_KERNEL");
-    const bool warp_only = mode && strcmp(mode, "warp") == 0;
+    const bool warp_only = mode ? strcmp(mode, "warp") == 0 : n_pairs < EPAT_MIN_PAIRS;
+    if (mode && strcmp(mode, "warp") != 0 && strcmp(mode, "thread") != 0)
+        return d3d_set_error("d3d_epa: D3D_EPA_KERNEL must be 'warp' or 'thread'");
     if (!warp_only && max_faces == EPAT_MF && max_loose_edges == EPAT_ML && max_iter <= EPAT_MAXV - 4 && !out_faces) {
         char *p = reinterpret_cast<char *>(workspace);
         EpaThreadState S;

@@ -1,6 +1,7 @@
 """GPU: EPA (thread-per-pair kernel + warp kernel) against the oracle and the real reference's outputs.
-`want_faces=True` runs the warp kernel alone (the thread kernel does not keep the polytope in the
-reference's layout); without it the thread kernel runs first and hands over what it cannot finish.
+`want_faces=True` and batches below 20000 pairs run the warp kernel alone; D3D_EPA_KERNEL=thread
+forces the thread kernel (which hands over what it cannot finish) so that it is tested on the small
+fixtures as well.
 
 Tolerance from BASELINE.json: penetration depth and normal within 1e-7; the
 implementation is in fact bit-exact (asserted)."""
@@ -32,7 +33,8 @@ def test_golden_epa_vs_reference_outputs():
         assert np.array_equal(res["faces"][q, :n], g["faces"][sel[q], :n])
 
 
-def test_golden_epa_thread_kernel():
+def test_golden_epa_thread_kernel(monkeypatch):
+    monkeypatch.setenv("D3D_EPA_KERNEL", "thread")
     cs, g = load_golden("epa.npz")
     sel = np.where(g["status"] >= 0)[0]
     res = epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel]).cpu()
@@ -60,7 +62,7 @@ def test_golden_wide_hulls():
     (("mesh",), 0.6, (64, 256)),
     (("mesh", "box", "capsule"), 0.4, (8, 40)),
 ])
-def test_random_pipeline_gjk_then_epa(names, scale, hv):
+def test_random_pipeline_gjk_then_epa(names, scale, hv, monkeypatch):
     rs = np.random.RandomState(21)
     cs = d3random.random_collider_set(rs, 1500, names=names, center_scale=scale, hull_vertices=hv)
     pairs = d3random.random_pairs(rs, len(cs), 12000)
@@ -83,6 +85,7 @@ def test_random_pipeline_gjk_then_epa(names, scale, hv):
     conv = ok & (ref["success"] == 1)
     assert conv.sum() > 100
     # the same batch through the thread-per-pair kernel
+    monkeypatch.setenv("D3D_EPA_KERNEL", "thread")
     thr = epa.epa_batch(cs, pairs[sel], g.simplex[sel.tolist()]).cpu()
     assert np.array_equal(thr["status"], ref["status"])
     for key in ("mtv", "success", "n_faces", "iters"):
@@ -129,7 +132,7 @@ def test_undefined_simplices_are_reported_not_run():
     assert np.array_equal(res["mtv"][~bad], full["mtv"]) and np.array_equal(res["status"][~bad], full["status"])
 
 
-def test_degenerate_simplices_match_the_oracle():
+def test_degenerate_simplices_match_the_oracle(monkeypatch):
     """Simplices with a duplicated point or two points closer than the edge-matching epsilon
     (epa.py:189-191 matches loose edges by distance) exercise the coordinate-based edge matching
     where it differs from matching by vertex identity; results are the oracle's bit for bit."""
@@ -156,6 +159,7 @@ def test_degenerate_simplices_match_the_oracle():
     assert len(sub) > 1000 and ok.sum() > 500
     # thread-per-pair kernel: duplicated points share a vertex id, near-duplicates are kept as
     # "near pairs" that the edge matching treats as equal, like the reference's distance test
+    monkeypatch.setenv("D3D_EPA_KERNEL", "thread")
     thr = epa.epa_batch(cs, sub, Y).cpu()
     assert np.array_equal(thr["status"], ref["status"])
     for key in ("mtv", "success", "n_faces", "iters"):

@@ -150,7 +150,7 @@ def test_scalar_api_matches_reference_semantics():
     np.testing.assert_allclose(box.support_function(np.array([1.0, 1.0, 1.0])), [0.5, 0.5, 0.5])
 
 
-def test_meshgraph_hill_climbing_bit_exact_vs_reference_outputs():
+def test_meshgraph_hill_climbing_bit_exact_vs_reference_outputs(monkeypatch):
     """MeshGraph support = hill climbing over the triangle graph from the vertex the
     previous support call ended on (mesh.py:12-139).  The fixture holds the outputs of the
     real reference with a fresh object per call; everything is bit-exact (contract: 1e-9)."""
@@ -180,6 +180,13 @@ def test_meshgraph_hill_climbing_bit_exact_vs_reference_outputs():
     assert np.array_equal(e["mtv"][~asserted], g["epa_mtv"][sel][~asserted])
     assert np.array_equal(e["success"][~asserted], g["epa_success"][sel][~asserted])
     assert np.array_equal(e["n_faces"][~asserted], g["epa_n_faces"][sel][~asserted])
+    # the thread-per-pair EPA kernel hands MeshGraph pairs to the warp kernel (hill-climbing state)
+    monkeypatch.setenv("D3D_EPA_KERNEL", "thread")
+    e2 = d3epa.epa_batch(cs, g["pairs"][sel], g["Y"][sel]).cpu()
+    monkeypatch.delenv("D3D_EPA_KERNEL")
+    assert int(e2["deferred"][0]) > 0
+    for key in ("status", "mtv", "success", "n_faces", "iters"):
+        assert np.array_equal(e2[key], e[key]), key
     m = d3mpr.mpr_batch(cs, g["pairs"], penetration=True)
     mh = m["hit"].cpu().numpy()
     assert np.array_equal(mh, g["mpr_hit"])
