@@ -240,9 +240,22 @@ D3D_DEV int argmax_dot(const double *V, int n, v3 d, int lane) {
     real best = R(0.0);
     int bi = 0x7fffffff;
     bool have = false;
-    for (int i = lane; i < n; i += G) {
-        real val = gemv_row(__ldg(V + 3 * i), __ldg(V + 3 * i + 1), __ldg(V + 3 * i + 2), d);
-        if (!have || val > best) { best = val; bi = i; have = true; }
+    // four rounds per trip: the twelve loads of a lane are in flight together (the scan is
+    // bound by the latency of the vertex loads, not by their number)
+#pragma unroll 1
+    for (int i0 = lane; i0 < n; i0 += 4 * G) {
+        real x[4], y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * G, n - 1);
+            x[u] = __ldg(V + 3 * i); y[u] = __ldg(V + 3 * i + 1); z[u] = __ldg(V + 3 * i + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * G;
+            real val = gemv_row(x[u], y[u], z[u], d);
+            if (i < n && (!have || val > best)) { best = val; bi = i; have = true; }
+        }
     }
 #ifndef D3D_F32
     if (G == 32) return warp_first_extreme<true>(best, bi, have);
