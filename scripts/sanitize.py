@@ -15,6 +15,13 @@ gjk.gjk_distance_batch(cs, pairs, dtype="f32")
 sel = torch.nonzero(g.dist == 0).flatten()
 epa.epa_batch(cs, torch.from_numpy(pairs).cuda()[sel], g.simplex[sel], want_faces=True, n_points=g.n_points[sel])
 epa.epa_batch(cs, torch.from_numpy(pairs).cuda()[sel], g.simplex[sel], max_faces=48, n_points=g.n_points[sel])
+# the thread-per-pair EPA kernel (batches this small go to the warp kernel unless forced)
+os.environ["D3D_EPA_KERNEL"] = "thread"
+epa.epa_batch(cs, torch.from_numpy(pairs).cuda()[sel], g.simplex[sel], n_points=g.n_points[sel])
+Yd = g.simplex[sel].clone()
+Yd[::5, 1] = Yd[::5, 0]; Yd[2::7, 2] = Yd[2::7, 3] + 1e-9   # shared vertex ids, near pairs
+epa.epa_batch(cs, torch.from_numpy(pairs).cuda()[sel], Yd)
+os.environ.pop("D3D_EPA_KERNEL")
 gjk.gjk_intersection_libccd_batch(cs, pairs)
 # MeshGraph colliders: hill climbing in the thread kernel, the warp kernel, EPA and MPR
 mg = R.random_meshgraph_set(rs, 6, 60, 60, hull_vertices=(8, 150), center_scale=0.8)
@@ -23,6 +30,9 @@ gm = gjk.gjk_distance_batch(mg, mp)
 gjk.gjk_intersection_batch(mg, mp)
 selm = torch.nonzero(gm.dist == 0).flatten()
 epa.epa_batch(mg, torch.from_numpy(mp).cuda()[selm], gm.simplex[selm], n_points=gm.n_points[selm])
+os.environ["D3D_EPA_KERNEL"] = "thread"   # MeshGraph pairs are handed to the warp kernel
+epa.epa_batch(mg, torch.from_numpy(mp).cuda()[selm], gm.simplex[selm], n_points=gm.n_points[selm])
+os.environ.pop("D3D_EPA_KERNEL")
 mpr.mpr_batch(mg, mp)
 mpr.mpr_batch(cs, pairs)
 A = _lib.aabb_device(cs.device())
