@@ -459,21 +459,27 @@ __global__ void __launch_bounds__(EPAT_THREADS, EPAT_BLOCKS_PER_SM)
 k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm, EpaThreadState S) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
-    const int64_t T = S.T;
+    // element e of this thread's state sits at [e * T]; rows x threads < 2^31, so the index
+    // arithmetic is 32-bit (one IMAD.WIDE per access)
+    const unsigned T = (unsigned)S.T;
     double *recA = smem + tid, *recB = recA + D3D_COLLIDER_FIELDS * EPAT_THREADS;
-    uint16_t *loose = reinterpret_cast<uint16_t *>(smem + 2 * D3D_COLLIDER_FIELDS * EPAT_THREADS) + tid;
+    // loose edges: 16 bits each (la | lb << 8), four to a 64-bit word, word w of this thread at
+    // [w * EPAT_THREADS] (conflict free); the search compares four entries per load
+    unsigned long long *loose64 = reinterpret_cast<unsigned long long *>(smem + 2 * D3D_COLLIDER_FIELDS * EPAT_THREADS) + tid;
+    uint16_t *loose16 = reinterpret_cast<uint16_t *>(loose64);
+#define LOOSE(e) loose16[(((e) >> 2) * EPAT_THREADS) * 4 + ((e) & 3)]
     double *vtx = S.vtx + blockIdx.x * (int64_t)EPAT_THREADS + tid;
     double *fnrm = S.fnrm + blockIdx.x * (int64_t)EPAT_THREADS + tid;
     double *fdist = S.fdist + blockIdx.x * (int64_t)EPAT_THREADS + tid;
     uint32_t *fids = S.fids + blockIdx.x * (int64_t)EPAT_THREADS + tid;
     const double eps = prm.epsilon;
-#define VT(j) V3(vtx[(3 * (j)) * T], vtx[(3 * (j) + 1) * T], vtx[(3 * (j) + 2) * T])
-#define FN(i) V3(fnrm[(3 * (i)) * T], fnrm[(3 * (i) + 1) * T], fnrm[(3 * (i) + 2) * T])
+#define VT(j) V3(vtx[(unsigned)(3 * (j)) * T], vtx[(unsigned)(3 * (j) + 1) * T], vtx[(unsigned)(3 * (j) + 2) * T])
+#define FN(i) V3(fnrm[(unsigned)(3 * (i)) * T], fnrm[(unsigned)(3 * (i) + 1) * T], fnrm[(unsigned)(3 * (i) + 2) * T])
 #define SET_FACE(i, ids_, n_, d_)                                                        \
     {                                                                                    \
-        fids[(i) * T] = (ids_);                                                          \
-        fnrm[(3 * (i)) * T] = (n_).x; fnrm[(3 * (i) + 1) * T] = (n_).y; fnrm[(3 * (i) + 2) * T] = (n_).z; \
-        fdist[(i) * T] = (d_);                                                           \
+        fids[(unsigned)(i) * T] = (ids_);                                                          \
+        fnrm[(unsigned)(3 * (i)) * T] = (n_).x; fnrm[(unsigned)(3 * (i) + 1) * T] = (n_).y; fnrm[(unsigned)(3 * (i) + 2) * T] = (n_).z; \
+        fdist[(unsigned)(i) * T] = (d_);                                                           \
     }
     int k = -1, n_faces = 0, it = 0, nv = 0, closest = 0;
     double vmax = 0.0;  // largest |coordinate| in the vertex table
@@ -532,7 +538,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             near_ids |= (1ull << min(other, 63u)) | (1ull << min(nv, 63));  // ids 63.. share the last bit
             ++n_near;
         }
-        vtx[(3 * nv) * T] = p.x; vtx[(3 * nv + 1) * T] = p.y; vtx[(3 * nv + 2) * T] = p.z;
+        vtx[(unsigned)(3 * nv) * T] = p.x; vtx[(unsigned)(3 * nv + 1) * T] = p.y; vtx[(unsigned)(3 * nv + 2) * T] = p.z;
         vmax = fmax(vmax, fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z))));
         return nv++;
     };
@@ -612,7 +618,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             closest = 0;
 #pragma unroll 4
             for (int i = 1; i < n_faces; ++i) {
-                double d = fdist[i * T];
+                double d = fdist[(unsigned)i * T];
                 if (d < min_dist) { min_dist = d; closest = i; }
             }
         }
@@ -653,7 +659,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
                 for (int u = 0; u < 4; ++u) {
                     const int i = min(i0 + u, EPAT_MF - 1);
                     n[u] = FN(i);
-                    dd[u] = fdist[i * T];
+                    dd[u] = fdist[(unsigned)i * T];
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -670,8 +676,8 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             while (amb) {  // rare: inside the rounding band, the reference's own expression decides
                 const int i = __ffsll((long long)amb) - 1;
                 amb &= amb - 1ull;
-                const double d = fdist[i * T];
-                if (dot_blas(FN(i), p - VT(fids[i * T] & 0xffu)) > eps) vis |= 1ull << i;
+                const double d = fdist[(unsigned)i * T];
+                if (dot_blas(FN(i), p - VT(fids[(unsigned)i * T] & 0xffu)) > eps) vis |= 1ull << i;
                 else if (d < smin) { smin = d; smin_slot = i; tie = false; }
                 else if (d == smin) tie = true;
             }
@@ -687,7 +693,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
                 if (n_faces < 64) rest &= (1ull << n_faces) - 1ull;
                 if (rest == 0ull) break;
                 i = __ffsll((long long)rest) - 1;
-                const uint32_t ids = fids[i * T];
+                const uint32_t ids = fids[(unsigned)i * T];
                 uint32_t ring = ids | (ids << 24);  // id0 id1 id2 id0
 #pragma unroll 1
                 for (int j = 0; j < 3; ++j, ring >>= 8) {
@@ -697,19 +703,30 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
                     int e = 0;
                     if ((((near_ids >> min(e0, 63u)) | (near_ids >> min(e1, 63u))) & 1ull) == 0ull) {
                         // neither end of this edge has a near twin: equal ids is the whole test
-                        while (e < n_loose && loose[e * EPAT_THREADS] != want) ++e;
+                        const unsigned long long pat = want * 0x0001000100010001ull;
+                        e = n_loose;
+                        for (int w = 0; 4 * w < n_loose; ++w) {
+                            const unsigned long long x = loose64[w * EPAT_THREADS] ^ pat;
+                            // lowest flagged field = first 16-bit field of x that is zero
+                            const unsigned long long z = (x - 0x0001000100010001ull) & ~x & 0x8000800080008000ull;
+                            if (z) {
+                                const int hit = 4 * w + ((__ffsll((long long)z) - 1) >> 4);
+                                if (hit < n_loose) e = hit;  // else: a stale entry behind the end of the list
+                                break;
+                            }
+                        }
                     } else {
                         for (; e < n_loose; ++e) {
-                            const uint32_t le = loose[e * EPAT_THREADS];
+                            const uint32_t le = LOOSE(e);
                             if (same_vertex(le >> 8, e0) && same_vertex(le & 0xffu, e1)) break;
                         }
                     }
                     if (e < n_loose) {  // overwrite_edge_with_last_edge (epa.py:200-202)
                         --n_loose;
-                        loose[e * EPAT_THREADS] = loose[n_loose * EPAT_THREADS];
+                        LOOSE(e) = LOOSE(n_loose);
                     } else {            // add_edge_to_list (epa.py:193-198)
                         if (n_loose >= EPAT_ML) break;
-                        loose[n_loose * EPAT_THREADS] = (uint16_t)(e0 | (e1 << 8));
+                        LOOSE(n_loose) = (uint16_t)(e0 | (e1 << 8));
                         ++n_loose;
                     }
                 }
@@ -717,7 +734,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
                 const unsigned long long last_bit = (vis >> last) & 1ull;
                 if (i != last) {
                     v3 n = FN(last);
-                    SET_FACE(i, fids[last * T], n, fdist[last * T]);
+                    SET_FACE(i, fids[(unsigned)last * T], n, fdist[(unsigned)last * T]);
                     if (smin_slot == last) smin_slot = i;
                 }
                 vis = (vis & ~(1ull << i) & ~(1ull << last)) | (i < last ? (last_bit << i) : 0ull);
@@ -731,7 +748,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
 #pragma unroll 1
             for (int e = 0; e < n_loose; ++e) {
                 if (n_faces >= EPAT_MF) { overflow = true; break; }  // assert self.n_faces < self.max_faces
-                const uint32_t ed = loose[e * EPAT_THREADS];
+                const uint32_t ed = LOOSE(e);
                 uint32_t id0 = ed & 0xffu;
                 const uint32_t id1 = ed >> 8;
                 v3 v0 = VT(id0), v1 = VT(id1);
@@ -751,6 +768,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
 #undef VT
 #undef FN
 #undef SET_FACE
+#undef LOOSE
 }
 
 inline int64_t epat_threads_for(int64_t n) {
@@ -833,7 +851,7 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     if (!warp_only && max_faces == EPAT_MF && max_loose_edges == EPAT_ML && max_iter <= EPAT_MAXV - 4 && !out_faces) {
         char *p = reinterpret_cast<char *>(workspace);
         EpaThreadState S;
-        S.T = epat_threads_for(n_pairs);
+        S.T = epat_threads_for(n_pairs);  // <= 148 * 4 * 128 threads, 204 rows each: 32-bit element indices
         S.fb_count = reinterpret_cast<int *>(p + 8);
         S.fb_list = reinterpret_cast<int *>(p + 2048 + epa_au((size_t)n_pairs) + epa_au((size_t)n_pairs * 4));
         char *st = p + epa_ws_base(n_pairs);

@@ -1,0 +1,3 @@
+python -m pytest tests/test_epa_gpu.py tests/test_gjk_gpu.py tests/test_pipeline_gpu.py -x -q 2>&1 | grep -E "^E|passed|failed" | head -20
+python scripts/epa_thread_dev.py c5 2>&1 | tail -1
+python scripts/r02_dev.py pipe 2>&1 | grep -E "epa|EPA|C5 shapes|gjk"
