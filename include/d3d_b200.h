@@ -137,7 +137,12 @@ int d3d_gjk_intersection_libccd(const d3d_colliders *c, const int32_t *pairs, co
  *   out_nfaces[k], out_iters[k] (may be NULL); out_faces[k,max_faces,4,3] (may be NULL)
  *   out_status[k]  D3D_INTERSECTION, or D3D_EPA_MAX_FACES where the reference raises
  *                  AssertionError (epa.py:128)
- * Limits: 4 <= max_faces <= 64, 1 <= max_loose_edges <= 32 (the reference's defaults). */
+ * Limits: 4 <= max_faces <= 64, 1 <= max_loose_edges <= 32 (the reference's defaults).
+ * For status D3D_EPA_MAX_FACES only the status is defined (mtv 0, success 0).
+ * Two kernels with identical results: a thread-per-pair kernel (default limits, out_faces NULL,
+ * n_pairs >= 20000) followed by the warp-per-pair kernel on what it hands over, or the warp
+ * kernel alone; the environment variable D3D_EPA_KERNEL=warp|thread overrides the choice.
+ * Workspace: 9 bytes per pair + 3.9 KB per thread of the thread kernel (<= 298 MB). */
 size_t d3d_epa_workspace_bytes(int64_t n_pairs);
 int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const double *Y,
             const int32_t *npoints, int max_iter, int max_loose_edges, int max_faces, double epsilon, double *out_mtv,
