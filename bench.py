@@ -37,6 +37,9 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# stdout carries the ONE JSON line; whatever NCCL logs ("NCCL version ..." at NCCL_DEBUG=VERSION)
+# goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOP_PER_ITER = 350.0  # algorithmic flop per GJK iteration (primitives)
 BYTES_PER_PAIR = 496.0  # 336 B in + 160 B out

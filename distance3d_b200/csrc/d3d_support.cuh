@@ -87,6 +87,13 @@ struct ColliderSmem {
     D3D_DEV real margin() const { return f(15); }
 };
 
+// A hull / mesh without vertices (outside the contract of d3d_types.h) is read as this one point
+// instead of whatever lies next to its empty range.
+__device__ const double d3d_origin_vertex[3] = {0.0, 0.0, 0.0};
+D3D_DEV void guard_empty_range(int &nv, const double *&V) {
+    if (nv < 1) { nv = 1; V = d3d_origin_vertex; }
+}
+
 // MeshGraph: offset of the adjacency record and the vertex a pair starts from.
 D3D_DEV void mesh_graph_of(const d3d_colliders &c, int64_t i, int &off, int &start) {
     off = c.graph_off ? __ldg(c.graph_off + i) : -1;
@@ -107,6 +114,7 @@ D3D_DEV Collider load_collider(const d3d_colliders &c, int64_t i) {
     }
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
+    guard_empty_range(o.nv, o.V);
     o.m_margin = c.margin ? __ldg(c.margin + i) : R(0.0);
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
 #pragma unroll
@@ -127,6 +135,7 @@ D3D_DEV ColliderSmem<STRIDE> stage_collider(const d3d_colliders &c, int64_t i, r
     o.type = __ldg(c.type + i);
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
+    guard_empty_range(o.nv, o.V);
     o.base = base;
     o.gpool = c.graph;
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);
@@ -158,6 +167,7 @@ D3D_DEV ColliderSmem<1> stage_collider_warp(const d3d_colliders &c, int64_t i, r
     o.type = __ldg(c.type + i);
     o.nv = __ldg(c.vert_len + i);
     o.V = c.verts + 3 * (int64_t)__ldg(c.vert_off + i);
+    guard_empty_range(o.nv, o.V);
     o.base = base;
     o.gpool = c.graph;
     const double2 *T = reinterpret_cast<const double2 *>(c.pose + 16 * i);

@@ -35,7 +35,10 @@ enum {
  * param: sphere (r,-,-); capsule (r,h,-); box (sx,sy,sz); ellipsoid (rx,ry,rz);
  *        cylinder (r,L,-); disk (r,-,-); ellipse (r0,r1,-); cone (r,h,-).
  * vert_off/vert_len: range into verts[M,3] (box: 8 world-frame vertices written
- *        by d3d_prepare; hull: world frame; mesh: local frame).
+ *        by d3d_prepare; hull: world frame; mesh: local frame).  A hull / mesh has at least
+ *        one vertex: the reference's np.argmax raises on an empty array (colliders.py:131-132)
+ *        and the Python layer rejects it; the kernels read vert_len < 1 as the single point
+ *        (0,0,0) of the collider's frame instead of reading outside the range.
  * margin: optional per-collider Margin (colliders.py:606), NULL = none.
  *
  * MeshGraph support = hill climbing over the triangle graph (mesh.py:12-139).
