@@ -17,6 +17,17 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline int max(int a, int b) { return a > b ? a : b; }
+// the device's reciprocal estimate is "about 2^-38"; the host stand-in is deliberately worse and
+// biased (truncated to 24 bits, then pushed off by RCP_BIAS units of 2^-36) - the result of the
+// norm must not depend on it
+#ifndef RCP_BIAS
+#define RCP_BIAS 0.0
+#endif
+static inline double rcp_rough(double x) {
+    double y = __longlong_as_double(__double_as_longlong(1.0 / x) & ~0x1fffffffLL);  // 24 bits
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y * (1.0 + RCP_BIAS * 1.4551915228366852e-11);
+}
 static __attribute__((noinline)) double ddiv(double a, double b) { return a / b; }
 static __attribute__((noinline)) double dsqrt(double a) { return sqrt(a); }
 #include NORM_SECTION
@@ -26,8 +37,11 @@ extern "C" void host_norm(const double *v, int64_t n, int mode, double *out) {
         if (mode == 2) {
             double big = fmax(fabs(x), fmax(fabs(y), fabs(z)));
             out[i] = (big > 1e-140 && big < 1e140) ? norm_x87_core_t<true>(x, y, z) : norm_x87(x, y, z);
-        } else if (mode == 3) {  // how often the production path leaves for the integer emulation
-            out[i] = 0.0;
+        } else if (mode == 1) {  // integer emulation alone, seeded by a plain double (off by up to
+            // 2^11 units of the 64-bit mantissa: exercises the bit-by-bit rebuild of the root)
+            double big = fmax(fabs(x), fmax(fabs(y), fabs(z)));
+            out[i] = (big > 1e-140 && big < 1e140) ? norm_x87_exact(x, y, z, sqrt(x * x + y * y + z * z), 0.0)
+                                                   : norm_x87(x, y, z);
         } else {
             out[i] = norm_x87(x, y, z);
         }

@@ -15,8 +15,11 @@ HEADER = os.path.join(HERE, "..", "distance3d_b200", "csrc", "d3d_math.cuh")
 BEGIN, END = "// ---- exact emulation", "D3D_DEV real norm_dd("
 
 
-@pytest.fixture(scope="module")
-def host_norm(tmp_path_factory):
+@pytest.fixture(scope="module", params=[0.0, 3.0, -3.0])
+def host_norm(tmp_path_factory, request):
+    """params: bias of the stand-in for the device's reciprocal estimate (units of 2^-36); the
+    sqrt correction of the fast path tolerates a quotient good to 2^-38, so every bias must give
+    the same bits."""
     text = open(HEADER).read()
     b, e = text.index(BEGIN), text.index(END)
     d = tmp_path_factory.mktemp("norm_host")
@@ -24,6 +27,7 @@ def host_norm(tmp_path_factory):
     section.write_text(text[b:e])
     so = d / "norm_host.so"
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-mfma", "-ffp-contract=off", "-w",
+                           "-DRCP_BIAS=%r" % request.param,
                            '-DNORM_SECTION="%s"' % section, os.path.join(HERE, "host_shim", "norm_host.cpp"),
                            "-o", str(so)])
     lib = ctypes.CDLL(str(so))
@@ -63,3 +67,8 @@ def test_production_path_matches_the_long_double_norm(host_norm):
 def test_integer_emulation_seeded_by_the_estimate_matches(host_norm):
     v = vectors()
     np.testing.assert_array_equal(host_norm(v, 2), O.norm(v))
+
+
+def test_integer_emulation_with_a_coarse_seed_matches(host_norm):
+    v = vectors()[::4]
+    np.testing.assert_array_equal(host_norm(v, 1), O.norm(v))
