@@ -26,16 +26,22 @@
 // warp kernel wins 3x at 64-256 vertices)
 // (runtime override for tuning: environment variable D3D_THREAD_HULL_MAX)
 #define D3D_THREAD_HULL_MAX_DEFAULT 64
+// Instances of the thread kernel by the types their support switch compiles in (the kernel is
+// instruction-fetch bound, unused cases cost run time): analytic primitives, + ConvexHullVertices
+// (the mixed-shape pipeline: C5 GJK stage 56.0 -> 51.1 ms against running its hull pairs on the
+// all-types instance), everything.
+#define GJK_CONVEX_MASK (D3D_PRIMITIVE_MASK | (1 << D3D_HULL))
+#define GJK_INSTANCE_OF(TM) ((TM) == D3D_PRIMITIVE_MASK ? 0 : ((TM) == GJK_CONVEX_MASK ? 1 : 2))
 #define D3D_NBINS (D3D_NUM_TYPES * D3D_NUM_TYPES + 1)
 #define D3D_WIDE_BIN (D3D_NUM_TYPES * D3D_NUM_TYPES)
 
 namespace {
 
 struct GjkWorkspace {
-    int *counters;  // sorted order = [primitive-only bins | other thread bins | wide bin]
-                    // [0] next index, primitive instance of the thread kernel
-                    // [1] next index, warp kernel      [5] next index, generic thread kernel
-                    // [4] end of the primitive range   [2] end of the thread ranges   [3] total
+    int *counters;  // sorted order = [primitive bins | primitive + hull bins | other thread bins | wide bin]
+                    // [0] [7] [5] next index of thread instance 0 / 1 / 2     [1] next index, warp kernel
+                    // [4] [6] [2] end of the range of instance 0 / 1 / 2 (2 = end of the thread ranges)
+                    // [3] total
     int *hist;      // [128]
     int *cursor;    // [128]
     uint8_t *keys;  // [P]
@@ -97,33 +103,55 @@ __global__ void k_bin_scan(GjkWorkspace w, int64_t n, int split_min) {
     for (int i = threadIdx.x; i < D3D_NBINS; i += blockDim.x) hist[i] = w.hist[i];
     __syncthreads();
     if (threadIdx.x == 0) {
-        // Split the thread-kernel bins into [two analytic primitives | the rest] when the
-        // rest is empty or both parts are large; for small mixed batches the second launch
-        // tail costs more than the primitive instance saves (1 Mi pairs with 30 % hulls:
-        // 1.73e8 split vs 1.90e8 unsplit) and everything goes to the generic instance.
-        int n_prim = 0, n_rest = 0;
+        // Class of a bin = the smallest instance whose switch covers both types.  Each class
+        // present starts as its own group (= one launch of its instance); a group below
+        // split_min pairs is merged with the group above it (or, at the top, below it) and the
+        // merged group runs on the larger instance: for small mixed batches the tail of a
+        // second launch costs more than the leaner instance saves (1 Mi pairs with 30 %
+        // hulls: 1.73e8 pairs/s split, 1.90e8 unsplit).
+        int cls[D3D_WIDE_BIN];
+        long long n_cls[3] = {0, 0, 0};
         for (int i = 0; i < D3D_WIDE_BIN; ++i) {
-            bool prim = ((D3D_PRIMITIVE_MASK >> (i / D3D_NUM_TYPES)) & 1) &&
-                        ((D3D_PRIMITIVE_MASK >> (i % D3D_NUM_TYPES)) & 1);
-            if (prim) n_prim += hist[i]; else n_rest += hist[i];
+            const int ta = i / D3D_NUM_TYPES, tb = i % D3D_NUM_TYPES;
+            const bool prim = ((D3D_PRIMITIVE_MASK >> ta) & 1) && ((D3D_PRIMITIVE_MASK >> tb) & 1);
+            const bool convex = ((GJK_CONVEX_MASK >> ta) & 1) && ((GJK_CONVEX_MASK >> tb) & 1);
+            cls[i] = prim ? 0 : (convex ? 1 : 2);
+            n_cls[cls[i]] += hist[i];
         }
-        const bool split = n_prim > 0 && (n_rest == 0 || (n_prim >= split_min && n_rest >= split_min));
+        int group_of[3] = {0, 1, 2};  // instance that runs class c
+        for (int round = 0; round < 2; ++round) {
+            long long size[3] = {0, 0, 0};
+            for (int c = 0; c < 3; ++c) size[group_of[c]] += n_cls[c];
+            int groups = (size[0] > 0) + (size[1] > 0) + (size[2] > 0);
+            if (groups < 2) break;
+            for (int g = 0; g < 3; ++g) {
+                if (size[g] == 0 || size[g] >= split_min) continue;
+                int up = -1, down = -1;
+                for (int h = g + 1; h < 3; ++h) if (size[h] > 0) { up = h; break; }
+                for (int h = g - 1; h >= 0; --h) if (size[h] > 0) { down = h; break; }
+                // merging down moves the lower group UP into this instance (it covers more types)
+                for (int c = 0; c < 3; ++c) {
+                    if (up >= 0 && group_of[c] == g) group_of[c] = up;
+                    else if (up < 0 && down >= 0 && group_of[c] == down) group_of[c] = g;
+                }
+                break;
+            }
+        }
         int acc = 0;
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int g = 0; g < 3; ++g) {
             for (int i = 0; i < D3D_WIDE_BIN; ++i) {
-                bool prim = split && ((D3D_PRIMITIVE_MASK >> (i / D3D_NUM_TYPES)) & 1) &&
-                            ((D3D_PRIMITIVE_MASK >> (i % D3D_NUM_TYPES)) & 1);
-                if (prim != (pass == 0)) continue;
+                if (group_of[cls[i]] != g) continue;
                 w.cursor[i] = acc;
                 acc += hist[i];
             }
-            w.counters[pass == 0 ? 4 : 2] = acc;
+            w.counters[g == 0 ? 4 : (g == 1 ? 6 : 2)] = acc;
         }
         w.cursor[D3D_WIDE_BIN] = acc;
         acc += hist[D3D_WIDE_BIN];
         w.counters[0] = 0;
         w.counters[1] = 0;
         w.counters[5] = 0;
+        w.counters[7] = 0;
         w.counters[3] = acc;
     }
 }
@@ -664,10 +692,11 @@ __global__ void __launch_bounds__(256) k_gjk_finish(GjkWorkspace w, GjkParams pr
     }
 }
 
-// One thread per pair, persistent, lanes refill from a warp-private chunk.  Two instances per
+// One thread per pair, persistent, lanes refill from a warp-private chunk.  Three instances per
 // mode: TM = D3D_PRIMITIVE_MASK walks the sorted range of primitive-only bins with a support
 // switch compiled for those five types (the kernel is instruction-fetch bound: +5 % on the C1
-// mix), TM = D3D_ALL_TYPES_MASK the remaining thread bins.  They are separate launches: one
+// mix), TM = GJK_CONVEX_MASK the bins of primitives and hulls, TM = D3D_ALL_TYPES_MASK the
+// remaining thread bins (k_bin_scan decides which ranges exist).  They are separate launches: one
 // kernel that runs both loops back to back measured 10 % SLOWER than the generic kernel alone
 // (2.40e8 vs 2.53e8 vs 2.66e8 pairs/s for the split), the larger kernel image costs more
 // than the saved launch tail.
@@ -690,10 +719,10 @@ k_gjk_thread(d3d_colliders c, const int32_t *__restrict__ pairs, GjkWorkspace w,
     }
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1;
-    const bool prim = (TM == D3D_PRIMITIVE_MASK);
-    const int first = prim ? 0 : w.counters[4];
-    const int total = prim ? w.counters[4] : w.counters[2];
-    int *next = &w.counters[prim ? 0 : 5];
+    const int inst = GJK_INSTANCE_OF(TM);
+    const int first = inst == 0 ? 0 : w.counters[inst == 1 ? 4 : 6];
+    const int total = w.counters[inst == 0 ? 4 : (inst == 1 ? 6 : 2)];
+    int *next = &w.counters[inst == 0 ? 0 : (inst == 1 ? 7 : 5)];
     bool exhausted = false;
 #if GJK_CHUNK > 0
     int chunk_pos = 0, chunk_end = 0;
@@ -821,6 +850,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     D3D_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_PRIMITIVE_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, GJK_CONVEX_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         D3D_CUDA_CHECK(cudaFuncSetAttribute(k_gjk_thread<MODE, D3D_ALL_TYPES_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
@@ -828,6 +858,7 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     int blocks_prim = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PRIM);
     // ranges are read on the device; an instance whose range is empty exits at once
     k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks_prim, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    k_gjk_thread<MODE, GJK_CONVEX_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     k_gjk_thread<MODE, D3D_ALL_TYPES_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     if (MODE == 0)
         k_gjk_finish<<<(int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8), 256, 0, stream>>>(w, prm);
