@@ -429,7 +429,9 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #define EPAT_MAXV 68  // 4 + max_iter
 #define EPAT_MF 64
 #define EPAT_ML 32
+#ifndef EPAT_TM
 #define EPAT_TM (D3D_ALL_TYPES_MASK & ~(1 << D3D_MESH))
+#endif
 #ifndef EPAT_MAX_VERTICES
 // Hulls with more vertices go to the warp kernel (cooperative vertex scan).  Measured on C3 (hulls
 // of 64-256 vertices, 4 Mi pairs): warp kernel 243 ms; thread kernel with a serial scan per thread
