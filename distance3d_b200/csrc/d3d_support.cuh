@@ -331,7 +331,7 @@ D3D_DEV void plane_basis(v3 n, v3 &x, v3 &y) {
 // TM = bit mask of the type tags this instance can meet: cases outside it are compiled out.
 // The GJK thread kernel has an instance for batches of analytic primitives only
 // (D3D_PRIMITIVE_MASK): the kernel is instruction-fetch bound and unused cases cost run time
-// (scripts/sweep_masks.sh: +6 % on the C1 mix, +13 % for a sphere-only instance).
+// (type-mask sweep of round 1: +6 % on the C1 mix, +13 % for a sphere-only instance).
 #define D3D_ALL_TYPES_MASK 0x3ff
 #define D3D_PRIMITIVE_MASK 0x1f  // sphere, capsule, box, ellipsoid, cylinder
 #define D3D_VERTEX_MASK 0x64     // box, hull, mesh: arg-max over a vertex list

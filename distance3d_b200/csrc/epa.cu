@@ -143,7 +143,7 @@ struct WarpMem {
 D3D_DEV v3 face_normal(v3 v0, v3 v1, v3 v2) { return normalized(cross(v1 - v0, v2 - v0)); }
 
 #ifndef EPA_BLOCKS_PER_SM
-#define EPA_BLOCKS_PER_SM 6  // 80 registers, 24 warps per SM; r02 sweep (scripts/r02_run2.sh) C3 / C5 ms at 4,5,6,8: 7.3 7.7 7.2 7.8 / 493 491 481 494
+#define EPA_BLOCKS_PER_SM 6  // 80 registers, 24 warps per SM; r02 sweep (scripts/gpu_sessions/r02_run2.sh) C3 / C5 ms at 4,5,6,8: 7.3 7.7 7.2 7.8 / 493 491 481 494
 #endif
 // -DEPA_PROFILE (development builds only, scripts/build_variant_epa.sh): cycles per phase of the
 // iteration and a few event counts, summed over all warps; read with d3d_debug_epa_profile.

@@ -841,7 +841,11 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
         hull_max = e ? atoi(e) : D3D_THREAD_HULL_MAX_DEFAULT;
     }
     k_pair_keys<<<bin_blocks, 256, 0, stream>>>(*c, pairs, n_pairs, w, hull_max);
-    k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs, sms * GJK_BLOCKS_PER_SM * GJK_THREADS * 8);
+    // smallest group of bins that gets a launch of its own (tests force 1 through the environment
+    // so that small batches exercise all three thread instances)
+    int split_min = sms * GJK_BLOCKS_PER_SM * GJK_THREADS * 8;
+    if (const char *e = getenv("D3D_GJK_SPLIT_MIN")) split_min = atoi(e);
+    k_bin_scan<<<1, 32, 0, stream>>>(w, n_pairs, split_min);
     k_bin_scatter<<<(int)d3d_min64((n_pairs + 256 * BIN_TILE_ITEMS - 1) / (256 * BIN_TILE_ITEMS), (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, w);
     size_t smem = sizeof(real) * GJK_FIELDS_THREAD * GJK_THREADS + (GJK_THREADS / 32) * GJK_SCRATCH_BYTES;
     // function attributes are per device: remember which devices have been set up

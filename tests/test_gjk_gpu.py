@@ -417,3 +417,19 @@ def test_libccd_boolean_gjk_vs_reference_outputs_and_as_cross_check():
     s1, s2 = C.Sphere(np.zeros(3), 1.0), C.Sphere(np.array([0.0, 0.0, 1.5]), 1.0)
     assert gjk.gjk_intersection_libccd(s1, s2) is True
     assert gjk.gjk_intersection_libccd(s1, C.Sphere(np.array([0.0, 0.0, 2.5]), 1.0)) is False
+
+
+@pytest.mark.parametrize("split_min", ["1", "100000000"])
+def test_all_thread_instances_and_the_warp_kernel_in_one_batch(monkeypatch, split_min):
+    """k_bin_scan sends a class of type bins (primitives / + hulls / everything) to its own
+    instance of the thread kernel only when the class is large; D3D_GJK_SPLIT_MIN=1 makes a small
+    batch run on all three instances plus the warp kernel (hulls above 64 vertices), a huge value
+    merges everything into one launch.  Both must reproduce the oracle bit for bit."""
+    monkeypatch.setenv("D3D_GJK_SPLIT_MIN", split_min)
+    rs = np.random.RandomState(77)
+    cs = d3random.random_collider_set(rs, 900, names=d3random.PRIMITIVES + ("mesh", "cone"), center_scale=0.9,
+                                      hull_vertices=(4, 120))
+    pairs = d3random.random_pairs(rs, len(cs), 9000)
+    res, ref = compare_distance(cs, pairs, exact_types=EXACT)
+    hit, _, _ = gjk.gjk_intersection_batch(cs, pairs, want_iters=True)
+    assert np.array_equal(hit.cpu().numpy().astype(bool), O.gjk_intersection(cs, pairs, n_threads=O.max_threads())["hit"].astype(bool))
