@@ -445,6 +445,21 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #define EPAT_STATE_BYTES ((size_t)(EPAT_MAXV * 24 + EPAT_MF * 24 + EPAT_MF * 8 + EPAT_MF * 4))
 #define EPAT_SMEM_BYTES ((size_t)EPAT_THREADS * (2 * D3D_COLLIDER_FIELDS * 8 + EPAT_ML * 2))
 
+// -DEPA_PROFILE: cycles per phase of the thread kernel's iteration loop (lane 0 of every warp;
+// slots 0-6 = refill, tie scan, support, vertex id, visibility, removal, new faces; 8 = lanes
+// owning a pair summed over the trips, 9 = trips); scripts/epa_thread_profile.py
+#ifdef EPA_PROFILE
+#define EPAT_PROF_DECL long long prof_t = clock64(); unsigned long long prof[16] = {0}
+#define EPAT_PROF(slot) { long long t_ = clock64(); prof[slot] += (unsigned long long)(t_ - prof_t); prof_t = t_; }
+#define EPAT_COUNT(slot, v) prof[slot] += (unsigned long long)(v)
+#define EPAT_PROF_FLUSH if ((threadIdx.x & 31) == 0) { for (int q_ = 0; q_ < 16; ++q_) if (prof[q_]) atomicAdd(&g_epa_prof[q_], prof[q_]); }
+#else
+#define EPAT_PROF_DECL
+#define EPAT_PROF(slot)
+#define EPAT_COUNT(slot, v)
+#define EPAT_PROF_FLUSH
+#endif
+
 struct EpaThreadState {
     double *vtx;     // [EPAT_MAXV * 3][T]
     double *fnrm;    // [EPAT_MF * 3][T]
@@ -563,6 +578,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
 #ifndef EPAT_REFILL_MIN
 #define EPAT_REFILL_MIN 32
 #endif
+    EPAT_PROF_DECL;
     for (;;) {
         unsigned run_mask = __ballot_sync(FULL, k >= 0);
         if (32 - __popc(run_mask) >= EPAT_REFILL_MIN || run_mask == 0) {
@@ -610,6 +626,8 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
                 continue;
             }
         }
+        EPAT_PROF(0);
+        EPAT_COUNT(8, __popc(run_mask)); EPAT_COUNT(9, 1);
         bool go = k >= 0;
         // ---- closest face, first arg-min (epa.py:104-109).  The minimum over the faces that
         // survive an iteration is collected while their visibility is tested, and the new faces
@@ -625,6 +643,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             }
         }
         __syncwarp();
+        EPAT_PROF(1);
         // ---- support point of A - B in the face normal (epa.py:62-65), convergence (epa.py:67-70)
         v3 p = V3(0.0, 0.0, 0.0);
         int pid = 0;
@@ -639,11 +658,13 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             }
         }
         __syncwarp();
+        EPAT_PROF(2);
         if (go) {
             pid = vertex_id(p);
             if (pid < 0) { fall_back(); go = false; }
         }
         __syncwarp();
+        EPAT_PROF(3);
         // ---- faces that see the new point (epa.py:122-124).  dot(n, p) - dist differs from the
         // reference's dot(n, p - v0) by rounding only (< 29 ulp of the largest coordinate); the
         // exact expression, which needs the face's first vertex, is evaluated inside that band.
@@ -685,6 +706,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             }
         }
         __syncwarp();
+        EPAT_PROF(4);
         // ---- remove them, loose edges (epa.py:157-202): removing slot i moves the last face (and
         // its visibility bit) into slot i
         int n_loose = 0;
@@ -744,6 +766,7 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             }
         }
         __syncwarp();
+        EPAT_PROF(5);
         // ---- one new face per loose edge (epa.py:126-146)
         if (go) {
             bool overflow = false;
@@ -766,7 +789,9 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
             if (overflow) finish(V3(0.0, 0.0, 0.0), false, D3D_EPA_MAX_FACES);
             else if (++it >= prm.max_iter) fall_back();  // epa.py:76-78 reads the last closest slot as it is now
         }
+        EPAT_PROF(6);
     }
+    EPAT_PROF_FLUSH;
 #undef VT
 #undef FN
 #undef SET_FACE
