@@ -439,6 +439,12 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 // (64 dependent scans per warp and iteration) - both rejected.
 #define EPAT_MAX_VERTICES 32
 #endif
+#ifndef EPAT_VB
+#define EPAT_VB 4
+#endif
+#ifndef EPAT_QB
+#define EPAT_QB 4
+#endif
 #ifndef EPAT_MIN_PAIRS
 #define EPAT_MIN_PAIRS 20000
 #endif
@@ -528,12 +534,12 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
     auto vertex_id = [&](v3 p) -> int {
         int same_as = -1, n_close = 0;
         unsigned close_ids = 0u;  // up to four table entries within epsilon of p
-        for (int j0 = 0; j0 < nv; j0 += 4) {  // four table entries per trip: their 12 loads are in flight together
-            v3 q[4];
+        for (int j0 = 0; j0 < nv; j0 += EPAT_QB) {  // EPAT_QB table entries per trip, loads in flight together
+            v3 q[EPAT_QB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = VT(min(j0 + u, EPAT_MAXV - 1));
+            for (int u = 0; u < EPAT_QB; ++u) q[u] = VT(min(j0 + u, EPAT_MAXV - 1));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < EPAT_QB; ++u) {
                 v3 d = q[u] - p;
                 if (j0 + u < nv && dot_blas(d, d) < prm.eps_sq_thr) {
                     bool same = __double_as_longlong(q[u].x) == __double_as_longlong(p.x) &&
@@ -675,17 +681,19 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
         if (go) {
             const double margin = 1e-13 * vmax;
             unsigned long long amb = 0ull;
-            for (int i0 = 0; i0 < n_faces; i0 += 4) {  // four faces per trip: 16 loads in flight together
-                v3 n[4];
-                double dd[4];
+            // EPAT_VB faces per trip, their 4 x EPAT_VB loads in flight together: a dependent round
+            // of state loads costs ~2000 cycles (profiles/r02_epa_thread_kernel_phases.txt)
+            for (int i0 = 0; i0 < n_faces; i0 += EPAT_VB) {
+                v3 n[EPAT_VB];
+                double dd[EPAT_VB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < EPAT_VB; ++u) {
                     const int i = min(i0 + u, EPAT_MF - 1);
                     n[u] = FN(i);
                     dd[u] = fdist[(unsigned)i * T];
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < EPAT_VB; ++u) {
                     const int i = i0 + u;
                     if (i < n_faces) {
                         double sgn = dot_blas(n[u], p) - dd[u];
