@@ -672,8 +672,15 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
         __syncwarp();
         EPAT_PROF(3);
         // ---- faces that see the new point (epa.py:122-124).  dot(n, p) - dist differs from the
-        // reference's dot(n, p - v0) by rounding only (< 29 ulp of the largest coordinate); the
-        // exact expression, which needs the face's first vertex, is evaluated inside that band.
+        // reference's dot(n, p - v0) by rounding only; the reference's expression, which needs the
+        // face's first vertex, is evaluated inside that band.  With u = 2^-53, M = largest
+        // |coordinate| in the vertex table (p included), |n| = 1 so sum |n_i| <= sqrt(3), and
+        // R = n . (p - v0) in exact arithmetic:
+        //   reference: d = fl(p - v0) (u per component), three-term fma chain (3 u)
+        //              -> |ref - R| <= 4.1 u sqrt(3) 2M = 14.2 u M
+        //   here:      |fl(n . p) - n . p| <= 3 u sqrt(3) M, the same for dist = fl(v0 . n),
+        //              the subtraction u |a - dist| <= 3.5 u M          -> |sgn - R| <= 13.9 u M
+        // so |sgn - ref| < 29 u M = 3.2e-15 M; the band is 1e-13 M (30 x that).
         unsigned long long vis = 0ull;
         double smin = D3D_MAX_FLOAT;  // minimum of dist over the survivors, its slot, exact tie seen
         int smin_slot = 0;
