@@ -77,6 +77,78 @@ __global__ void k_fk(FkModel m, const double *__restrict__ q, int64_t n_cfg, dou
     o[7] = make_double2(0.0, 1.0);
 }
 
+// The same product with the chains' common prefixes evaluated once: the steps of all frames form
+// a tree (urdf.compile_kinematics: a node = (parent node, fixed transform, joint), two chains
+// share a node when they agree in every step up to it), one thread walks the tree for one
+// configuration.  Every frame's pose is produced by exactly the operations k_fk performs for it
+// (same matrices, same order), so the results are bit-identical; a 6-joint arm with 8 collider
+// frames needs 6 joint steps per configuration instead of 27 (sin / cos in fp64 dominate).
+#define FK_MAX_KEEP 16  // nodes with children: their pose stays in the thread's local store
+struct FkTree {
+    int n_nodes, n_frames, n_joints;
+    const double *joint_axis, *joint_limits;
+    const int32_t *joint_type;
+    const int32_t *node_parent;  // [N] -1 = base frame
+    const double *node_fixed;    // [N,4,4]
+    const int32_t *node_joint;   // [N] -1 none
+    const int32_t *node_keep;    // [N] slot in the local store, -1 = no children
+    const int32_t *node_out_off; // [N+1] frames that END at the node ...
+    const int32_t *node_out;     // ... their indices
+};
+
+__global__ void __launch_bounds__(128) k_fk_tree(FkTree m, const double *__restrict__ q, int64_t n_cfg,
+                                                 double *__restrict__ out) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= n_cfg) return;
+    double S[FK_MAX_KEEP][12];
+    double T[12], U[12], J[12];
+    for (int node = 0; node < m.n_nodes; ++node) {
+        const int parent = m.node_parent[node];
+        if (parent < 0) {
+            const double I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = I[i];
+        } else {
+            const double *P = S[m.node_keep[parent]];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = P[i];
+        }
+        mat_mul(T, m.node_fixed + 16 * (int64_t)node, U);
+        const int j = m.node_joint[node];
+        if (j >= 0) {
+            double v = q[b * m.n_joints + j];
+            v = fmin(fmax(v, m.joint_limits[2 * j]), m.joint_limits[2 * j + 1]);
+            double ux = m.joint_axis[3 * j], uy = m.joint_axis[3 * j + 1], uz = m.joint_axis[3 * j + 2];
+            if (m.joint_type[j] == 0) {  // Rodrigues rotation about the unit axis
+                double c = cos(v), sn = sin(v), ci = 1.0 - c;
+                J[0] = ci * ux * ux + c;       J[1] = ci * ux * uy - uz * sn; J[2] = ci * ux * uz + uy * sn;  J[3] = 0.0;
+                J[4] = ci * uy * ux + uz * sn; J[5] = ci * uy * uy + c;       J[6] = ci * uy * uz - ux * sn;  J[7] = 0.0;
+                J[8] = ci * uz * ux - uy * sn; J[9] = ci * uz * uy + ux * sn; J[10] = ci * uz * uz + c;       J[11] = 0.0;
+            } else {
+                J[0] = 1; J[1] = 0; J[2] = 0; J[3] = v * ux;
+                J[4] = 0; J[5] = 1; J[6] = 0; J[7] = v * uy;
+                J[8] = 0; J[9] = 0; J[10] = 1; J[11] = v * uz;
+            }
+            mat_mul(U, J, T);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = U[i];
+        }
+        const int keep = m.node_keep[node];
+        if (keep >= 0) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) S[keep][i] = T[i];
+        }
+        for (int e = m.node_out_off[node]; e < m.node_out_off[node + 1]; ++e) {
+            double2 *o = reinterpret_cast<double2 *>(out + 16 * (b * m.n_frames + m.node_out[e]));
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o[i] = make_double2(T[2 * i], T[2 * i + 1]);
+            o[6] = make_double2(0.0, 0.0);
+            o[7] = make_double2(0.0, 1.0);
+        }
+    }
+}
+
 __device__ __forceinline__ void append_pair(int a, int b, int32_t *out_pairs, int64_t cap,
                                             unsigned long long *count) {
     unsigned m = __activemask();
@@ -260,6 +332,26 @@ int d3d_fk_urdf(int n_frames, int n_joints, const double *joint_axis, const doub
     m.chain_fixed = chain_fixed; m.chain_joint = chain_joint;
     int64_t threads = n_cfg * n_frames;
     k_fk<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(m, q, n_cfg, out_pose);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_fk_urdf_tree(int n_frames, int n_joints, const double *joint_axis, const double *joint_limits,
+                     const int32_t *joint_type, int n_nodes, int n_keep, const int32_t *node_parent,
+                     const double *node_fixed, const int32_t *node_joint, const int32_t *node_keep,
+                     const int32_t *node_out_off, const int32_t *node_out, const double *q, int64_t n_cfg,
+                     double *out_pose, void *stream) {
+    if (n_cfg == 0 || n_frames == 0) return 0;
+    if (!node_parent || !node_fixed || !node_joint || !node_keep || !node_out_off || !node_out || !q || !out_pose)
+        return d3d_set_error("d3d_fk_urdf_tree: null argument");
+    if (n_keep > FK_MAX_KEEP)
+        return d3d_set_error("d3d_fk_urdf_tree: %d chain nodes with children, at most %d (use d3d_fk_urdf)", n_keep, FK_MAX_KEEP);
+    FkTree m;
+    m.n_nodes = n_nodes; m.n_frames = n_frames; m.n_joints = n_joints; m.joint_axis = joint_axis;
+    m.joint_limits = joint_limits; m.joint_type = joint_type; m.node_parent = node_parent;
+    m.node_fixed = node_fixed; m.node_joint = node_joint; m.node_keep = node_keep;
+    m.node_out_off = node_out_off; m.node_out = node_out;
+    k_fk_tree<<<(unsigned)((n_cfg + 127) / 128), 128, 0, (cudaStream_t)stream>>>(m, q, n_cfg, out_pose);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -196,8 +196,9 @@ class DeviceColliders:
 
     @classmethod
     def from_tensors(cls, type_, pose, param, vert_off=None, vert_len=None, verts=None, margin=None,
-                     graph_off=None, graph=None, mesh_start=None):
-        """Wrap device tensors that already live in HBM (no host round trip)."""
+                     graph_off=None, graph=None, mesh_start=None, has_boxes=True):
+        """Wrap device tensors that already live in HBM (no host round trip).  `has_boxes=False`:
+        the caller knows that no collider is a Box, the d3d_prepare pass (box vertices) is skipped."""
         import torch
         self = cls.__new__(cls)
         n = type_.shape[0]
@@ -210,11 +211,12 @@ class DeviceColliders:
             verts = torch.zeros((1, 3), dtype=torch.float64, device=dev)
         self._init(type_.to(torch.int32).contiguous(), pose.reshape(n, 4, 4).contiguous(),
                    param.reshape(n, 3).contiguous(), vert_off.contiguous(), vert_len.contiguous(),
-                   verts.reshape(-1, 3).contiguous(), margin, graph_off, graph, mesh_start)
+                   verts.reshape(-1, 3).contiguous(), margin, graph_off, graph, mesh_start,
+                   prepare=has_boxes)
         return self
 
     def _init(self, type_, pose, param, vert_off, vert_len, verts, margin, graph_off=None,
-              graph=None, mesh_start=None, mesh_last=None):
+              graph=None, mesh_start=None, mesh_last=None, prepare=True):
         from . import _lib
         self.device = type_.device
         self.n = int(type_.shape[0])
@@ -238,7 +240,8 @@ class DeviceColliders:
                 raise TypeError("%s must be an int32 tensor" % name)
             setattr(self.struct, name, None if t is None else t.data_ptr())
         # box vertices are generated on the device (geometry.py:138-157)
-        _lib.prepare(self)
+        if prepare:
+            _lib.prepare(self)
 
 
 def concat_sets(sets):

@@ -135,7 +135,8 @@ class RobotModel:
         self.n_frames = len(self.frames)
         self.n_joints = len(self.joint_names)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-        self.kin = {k: t(v) for k, v in kin.items() if k != "joint_names"}
+        self.n_keep = int(kin["n_keep"])
+        self.kin = {k: t(v) for k, v in kin.items() if k not in ("joint_names", "n_keep")}
         self.pattern, wl, self.symmetric = _candidate_pattern(self.frames, bvh.self_collision_whitelists_)
         self.pattern_t = t(self.pattern)
         self.wl_t = t(wl.view(np.int64))
@@ -151,8 +152,9 @@ class RobotModel:
                              graph=None if tp.graph is None else t(tp.graph))
         self.device = dev
 
-    def forward_kinematics(self, q):
-        """Poses of all collider frames: q[B,J] -> device tensor [B,K,4,4]."""
+    def forward_kinematics(self, q, shared_prefixes=True):
+        """Poses of all collider frames: q[B,J] -> device tensor [B,K,4,4].  `shared_prefixes=False`
+        evaluates every frame's chain on its own (d3d_fk_urdf); the poses are the same bit for bit."""
         torch = _lib.torch_cuda()
         if not isinstance(q, torch.Tensor):
             q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
@@ -160,6 +162,14 @@ class RobotModel:
         B = q.shape[0]
         out = torch.empty((B, self.n_frames, 4, 4), dtype=torch.float64, device=self.device)
         k = self.kin
+        if shared_prefixes and self.n_keep <= 16:
+            # one thread per configuration walks the tree of chain steps (common prefixes once)
+            _lib._check(_lib.lib().d3d_fk_urdf_tree(
+                c_int(self.n_frames), c_int(self.n_joints), ptr(k["joint_axis"]), ptr(k["joint_limits"]),
+                ptr(k["joint_type"]), c_int(int(k["node_parent"].shape[0])), c_int(self.n_keep),
+                ptr(k["node_parent"]), ptr(k["node_fixed"]), ptr(k["node_joint"]), ptr(k["node_keep"]),
+                ptr(k["node_out_off"]), ptr(k["node_out"]), ptr(q), c_i64(B), ptr(out), _lib.stream_ptr()))
+            return out
         _lib._check(_lib.lib().d3d_fk_urdf(
             c_int(self.n_frames), c_int(self.n_joints), ptr(k["joint_axis"]), ptr(k["joint_limits"]),
             ptr(k["joint_type"]), ptr(k["chain_off"]), ptr(k["chain_fixed"]), ptr(k["chain_joint"]),
@@ -171,12 +181,13 @@ class RobotModel:
         B = poses.shape[0]
         if self.mesh is None:
             return DeviceColliders.from_tensors(self.type_t.repeat(B), poses.reshape(-1, 4, 4),
-                                                self.param_t.repeat(B, 1))
+                                                self.param_t.repeat(B, 1), has_boxes=False)
         m = self.mesh
         return DeviceColliders.from_tensors(
             self.type_t.repeat(B), poses.reshape(-1, 4, 4), self.param_t.repeat(B, 1),
             m["vert_off"].repeat(B), m["vert_len"].repeat(B), m["verts"],
-            graph_off=None if m["graph_off"] is None else m["graph_off"].repeat(B), graph=m["graph"])
+            graph_off=None if m["graph_off"] is None else m["graph_off"].repeat(B), graph=m["graph"],
+            has_boxes=False)
 
     def detect_batch(self, q, chunk=1 << 20):
         """Contact mask for every joint configuration: uint8 device tensor [B, K]

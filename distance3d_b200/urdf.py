@@ -343,8 +343,42 @@ class UrdfTransformManager(TransformManager):
             chain_fixed.extend(merged_fixed)
             chain_joint.extend(merged_joint)
             chain_off.append(len(chain_fixed))
+        # The steps of all chains as a tree (d3d_fk_urdf_tree): two chains share a node when they
+        # agree in every step up to it, so the common prefix of the frames' chains is evaluated
+        # once per configuration.  Nodes are created parents first.
+        node_of = {}
+        node_parent, node_fixed, node_joint, frame_node = [], [], [], []
+        for k in range(len(frames)):
+            parent = -1
+            for s_ in range(chain_off[k], chain_off[k + 1]):
+                key = (parent, np.ascontiguousarray(chain_fixed[s_], dtype=float).tobytes(), int(chain_joint[s_]))
+                if key not in node_of:
+                    node_of[key] = len(node_parent)
+                    node_parent.append(parent)
+                    node_fixed.append(chain_fixed[s_])
+                    node_joint.append(int(chain_joint[s_]))
+                parent = node_of[key]
+            frame_node.append(parent)
+        n_nodes = len(node_parent)
+        has_child = np.zeros(n_nodes, dtype=bool)
+        for p_ in node_parent:
+            if p_ >= 0:
+                has_child[p_] = True
+        node_keep = np.full(n_nodes, -1, dtype=np.int32)
+        node_keep[has_child] = np.arange(int(has_child.sum()), dtype=np.int32)
+        order = np.argsort(np.asarray(frame_node, dtype=np.int64), kind="stable")
+        node_out_off = np.zeros(n_nodes + 1, dtype=np.int32)
+        np.add.at(node_out_off, np.asarray(frame_node, dtype=np.int64) + 1, 1)
+        node_out_off = np.cumsum(node_out_off).astype(np.int32)
         J = len(joint_names)
         return {
+            "node_parent": np.asarray(node_parent, dtype=np.int32),
+            "node_fixed": np.array(node_fixed, dtype=float).reshape(-1, 4, 4),
+            "node_joint": np.asarray(node_joint, dtype=np.int32),
+            "node_keep": node_keep,
+            "node_out_off": node_out_off,
+            "node_out": order.astype(np.int32),
+            "n_keep": int(has_child.sum()),
             "joint_names": joint_names,
             "joint_axis": np.array([self._joints[n][3] for n in joint_names]).reshape(J, 3),
             "joint_limits": np.array([self._joints[n][4] for n in joint_names], dtype=float).reshape(J, 2),

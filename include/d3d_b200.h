@@ -298,6 +298,18 @@ int d3d_fk_urdf(int n_frames, int n_joints, const double *joint_axis, const doub
                 const int32_t *chain_joint, const double *q, int64_t n_cfg, double *out_pose,
                 void *stream);
 
+/* The same poses, bit for bit, with the common prefixes of the frames' chains evaluated once per
+ * configuration (one thread per configuration instead of one per (configuration, frame)).  The
+ * chain steps form a tree: node i = (node_parent[i] or -1 for the base, node_fixed[i], node_joint[i]),
+ * parents before children; node_keep[i] = slot (0 .. n_keep-1, n_keep <= 16) of a node that has
+ * children, -1 otherwise; frames node_out[node_out_off[i] .. node_out_off[i+1]) end at node i.
+ * compile_kinematics emits these arrays next to the flat chains. */
+int d3d_fk_urdf_tree(int n_frames, int n_joints, const double *joint_axis, const double *joint_limits,
+                     const int32_t *joint_type, int n_nodes, int n_keep, const int32_t *node_parent,
+                     const double *node_fixed, const int32_t *node_joint, const int32_t *node_keep,
+                     const int32_t *node_out_off, const int32_t *node_out, const double *q, int64_t n_cfg,
+                     double *out_pose, void *stream);
+
 /* self_collision.py:22-36: candidates of a collider = AABB overlaps minus white-list.  The
  * non-white-listed (frame a, frame b) combinations are a fixed `pattern[n_pattern,2]`; for
  * each of n_groups groups of group_size consecutive boxes the overlapping candidate pairs

@@ -127,6 +127,44 @@ def test_urdf_kinematics_match_reference_poses():
             np.testing.assert_allclose(T, g["poses"][b, k], atol=1e-13)
 
 
+def test_kinematic_tree_is_the_chains_with_shared_prefixes():
+    """compile_kinematics also emits the chain steps as a tree (d3d_fk_urdf_tree): walking from a
+    frame's node to the root gives back exactly that frame's chain, parents come first, and the arm
+    needs one node per joint plus one tail per frame."""
+    for urdf in ("robot_arm.urdf", "robot_branched.urdf"):
+        tm = UrdfTransformManager()
+        with open(os.path.join(DATA, urdf)) as f:
+            tm.load_urdf(f.read(), mesh_path=DATA)
+        tm.add_transform(urdf[:-5], "origin", np.eye(4))
+        frames = [o.frame for o in tm.collision_objects]
+        kin = tm.compile_kinematics(frames, "origin")
+        n = len(kin["node_parent"])
+        assert np.all(kin["node_parent"] < np.arange(n))
+        end = np.empty(len(frames), dtype=int)
+        for node in range(n):
+            end[kin["node_out"][kin["node_out_off"][node]:kin["node_out_off"][node + 1]]] = node
+        steps_flat = steps_tree = 0
+        for k in range(len(frames)):
+            path, node = [], end[k]
+            while node >= 0:
+                path.append(node)
+                node = kin["node_parent"][node]
+            path = path[::-1]
+            lo, hi = kin["chain_off"][k], kin["chain_off"][k + 1]
+            assert len(path) == hi - lo
+            for node, s_ in zip(path, range(lo, hi)):
+                assert np.array_equal(kin["node_fixed"][node], kin["chain_fixed"][s_])
+                assert kin["node_joint"][node] == kin["chain_joint"][s_]
+            steps_flat += hi - lo
+        has_child = np.zeros(n, dtype=bool)
+        has_child[kin["node_parent"][kin["node_parent"] >= 0]] = True
+        assert np.array_equal(kin["node_keep"] >= 0, has_child) and kin["n_keep"] == has_child.sum()
+        assert sorted(kin["node_keep"][has_child]) == list(range(kin["n_keep"]))
+        assert n < steps_flat          # prefixes are shared
+        if urdf == "robot_arm.urdf":
+            assert n == 6 + len(frames) and kin["n_keep"] == 6
+
+
 def test_self_collision_whitelists_match_survey():
     tm = load_robot_tm()
     wl = self_collision_whitelists(tm)

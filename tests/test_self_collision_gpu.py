@@ -65,6 +65,22 @@ def test_batched_fk_and_contact_masks_vs_reference_outputs():
     assert np.array_equal(mask2.cpu().numpy(), np.tile(g["mask"], (3, 1)))
 
 
+@pytest.mark.parametrize("urdf,name", [("robot_arm.urdf", "robot_arm"), ("robot_branched.urdf", "robot_branched")])
+def test_fk_with_shared_chain_prefixes_equals_per_frame_chains(urdf, name):
+    """d3d_fk_urdf_tree (one thread per configuration, common chain prefixes once) performs, for every
+    frame, the operations of d3d_fk_urdf in the same order: poses identical bit for bit."""
+    tm = UrdfTransformManager()
+    tm.load_urdf(open(os.path.join(DATA, urdf)).read(), mesh_path=DATA)
+    b = broad_phase.BoundingVolumeHierarchy(tm, name)
+    b.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
+    model = self_collision.RobotModel(tm, b)
+    q = np.random.RandomState(3).uniform(-3.2, 3.2, size=(5000, model.n_joints))
+    tree = model.forward_kinematics(q).cpu().numpy()
+    flat = model.forward_kinematics(q, shared_prefixes=False).cpu().numpy()
+    assert np.array_equal(tree, flat)
+    assert np.array_equal(tree[:, :, 3], np.broadcast_to([0.0, 0.0, 0.0, 1.0], tree[:, :, 3].shape))
+
+
 def test_branched_robot_asymmetric_whitelists_equal_reference_detect():
     """Torso with two arms and a head: the reference's white-lists are asymmetric there and its
     detect() result depends on the candidate order of its AABB tree; the device replays that
