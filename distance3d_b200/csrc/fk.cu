@@ -13,6 +13,7 @@
 //   k_scatter_hits flags both colliders of every intersecting pair
 // and the narrow phase in between is d3d_gjk_intersection.
 #include "d3d_common.cuh"
+#include "d3d_aabb.cuh"
 
 namespace {
 
@@ -180,6 +181,50 @@ __global__ void k_filter_pairs(const double *__restrict__ aabb, int64_t n_groups
         ov = ov && x.x <= y.y && x.y >= y.x;
     }
     if (ov) append_pair((int)ia, (int)ib, out_pairs, cap, count);
+}
+
+// k_aabb + k_filter_pairs in one pass for the self-collision step: a block takes G groups
+// (configurations) of group_size colliders, one thread per collider computes its box (stored to
+// `aabb` as d3d_aabb would, and to shared memory), then the block tests the G x n_pattern candidate
+// pairs from shared memory.  The boxes are not re-read from global memory and one launch goes away.
+#define FILTER_THREADS 128
+__global__ void __launch_bounds__(FILTER_THREADS)
+k_aabb_filter(d3d_colliders c, int64_t n_groups, int group_size, int groups_per_block,
+              const int32_t *__restrict__ pattern, int n_pattern, double *__restrict__ aabb,
+              int32_t *out_pairs, int64_t cap, unsigned long long *count) {
+    __shared__ double box[FILTER_THREADS * 6];
+    const int64_t g0 = blockIdx.x * (int64_t)groups_per_block;
+    const int n_local = (int)d3d_min64(groups_per_block, n_groups - g0) * group_size;
+    if ((int)threadIdx.x < n_local) {
+        const int64_t i = g0 * group_size + threadIdx.x;
+        double lo[3], hi[3];
+        collider_aabb(c, i, lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            box[6 * threadIdx.x + 2 * k] = lo[k];
+            box[6 * threadIdx.x + 2 * k + 1] = hi[k];
+        }
+        if (aabb) {
+            double2 *o = reinterpret_cast<double2 *>(aabb + 6 * i);
+            o[0] = make_double2(lo[0], hi[0]);
+            o[1] = make_double2(lo[1], hi[1]);
+            o[2] = make_double2(lo[2], hi[2]);
+        }
+    }
+    __syncthreads();
+    const int n_tests = (n_local / group_size) * n_pattern;
+    for (int t0 = 0; t0 < n_tests; t0 += FILTER_THREADS) {  // uniform trip count: append_pair uses __activemask
+        const int t = t0 + threadIdx.x;
+        if (t < n_tests) {
+            const int g = t / n_pattern, p = t % n_pattern;
+            const int a = g * group_size + __ldg(pattern + 2 * p), b = g * group_size + __ldg(pattern + 2 * p + 1);
+            bool ov = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                ov = ov && box[6 * a + 2 * k] <= box[6 * b + 2 * k + 1] && box[6 * a + 2 * k + 1] >= box[6 * b + 2 * k];
+            if (ov) append_pair((int)(g0 * group_size) + a, (int)(g0 * group_size) + b, out_pairs, cap, count);
+        }
+    }
 }
 
 __global__ void k_scatter_hits(const int32_t *__restrict__ pairs, const uint8_t *__restrict__ hit,
@@ -367,6 +412,24 @@ int d3d_filter_pairs(const double *aabb, int64_t n_groups, int group_size, const
     if (!aabb || !pattern || !out_pairs) return d3d_set_error("d3d_filter_pairs: null argument");
     k_filter_pairs<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(aabb, n_groups, group_size, pattern,
                                                                         n_pattern, out_pairs, cap, out_count);
+    D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_aabb_filter_pairs(const d3d_colliders *c, int64_t n_groups, int group_size, const int32_t *pattern,
+                          int n_pattern, double *out_aabb, int32_t *out_pairs, int64_t cap,
+                          unsigned long long *out_count, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!out_count) return d3d_set_error("d3d_aabb_filter_pairs: null argument");
+    D3D_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), stream));
+    if (n_groups == 0) return 0;
+    if (!c || !pattern || !out_pairs) return d3d_set_error("d3d_aabb_filter_pairs: null argument");
+    if (group_size < 1 || group_size > FILTER_THREADS)
+        return d3d_set_error("d3d_aabb_filter_pairs: group_size must be in [1, %d] (use d3d_aabb + d3d_filter_pairs)", FILTER_THREADS);
+    if (c->n != n_groups * group_size) return d3d_set_error("d3d_aabb_filter_pairs: collider count != n_groups * group_size");
+    const int gpb = FILTER_THREADS / group_size;
+    k_aabb_filter<<<(unsigned)((n_groups + gpb - 1) / gpb), FILTER_THREADS, 0, stream>>>(
+        *c, n_groups, group_size, gpb, pattern, n_pattern, out_aabb, out_pairs, cap, out_count);
     D3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

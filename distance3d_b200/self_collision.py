@@ -48,15 +48,25 @@ def _contact_mask(dc, n_groups, group_size, pattern_t, wl_t=None, symmetric=True
     torch = _lib.torch_cuda()
     L = _lib.lib()
     dev = dc.device
-    aabb = torch.empty((dc.n, 3, 2), dtype=torch.float64, device=dev)
-    _lib._check(L.d3d_aabb(ctypes.byref(dc.struct), ptr(aabb), _lib.stream_ptr()))
     n_pattern = int(pattern_t.shape[0])
     cap = max(1, n_groups * n_pattern)
     pairs = torch.empty((cap, 2), dtype=torch.int32, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)
-    _lib._check(L.d3d_filter_pairs(ptr(aabb), c_i64(n_groups), c_int(group_size), ptr(pattern_t),
-                                   c_int(n_pattern), ptr(pairs), c_i64(cap), ptr(count),
-                                   _lib.stream_ptr()))
+    aabb = None
+    if group_size <= 128:
+        # boxes and candidate filter in one pass; the boxes are only written out when the ordered
+        # replay below reads them
+        if not symmetric:
+            aabb = torch.empty((dc.n, 3, 2), dtype=torch.float64, device=dev)
+        _lib._check(L.d3d_aabb_filter_pairs(ctypes.byref(dc.struct), c_i64(n_groups), c_int(group_size),
+                                            ptr(pattern_t), c_int(n_pattern), ptr(aabb), ptr(pairs),
+                                            c_i64(cap), ptr(count), _lib.stream_ptr()))
+    else:
+        aabb = torch.empty((dc.n, 3, 2), dtype=torch.float64, device=dev)
+        _lib._check(L.d3d_aabb(ctypes.byref(dc.struct), ptr(aabb), _lib.stream_ptr()))
+        _lib._check(L.d3d_filter_pairs(ptr(aabb), c_i64(n_groups), c_int(group_size), ptr(pattern_t),
+                                       c_int(n_pattern), ptr(pairs), c_i64(cap), ptr(count),
+                                       _lib.stream_ptr()))
     n_cand = int(count.item())
     mask = torch.zeros(dc.n, dtype=torch.uint8, device=dev)
     hit = status = None

@@ -318,6 +318,13 @@ int d3d_filter_pairs(const double *aabb, int64_t n_groups, int group_size, const
                      int n_pattern, int32_t *out_pairs, int64_t cap, unsigned long long *out_count,
                      void *stream);
 
+/* d3d_aabb + d3d_filter_pairs in one pass (group_size <= 128): the boxes of a group are computed,
+ * stored to out_aabb[n,3,2] (may be NULL when nobody reads them afterwards) and tested from shared
+ * memory.  Same pairs as the two calls, in a different order. */
+int d3d_aabb_filter_pairs(const d3d_colliders *c, int64_t n_groups, int group_size, const int32_t *pattern,
+                          int n_pattern, double *out_aabb, int32_t *out_pairs, int64_t cap,
+                          unsigned long long *out_count, void *stream);
+
 /* self_collision.py:31-35: mask[pairs[t,0]] = mask[pairs[t,1]] = 1 for every t < min(*count, cap)
  * with hit[t] != 0. */
 int d3d_scatter_hits(const int32_t *pairs, const uint8_t *hit, const unsigned long long *count,

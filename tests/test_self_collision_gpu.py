@@ -230,3 +230,40 @@ def test_mesh_robot_reference_pins_0_2_4():
         bvh.update_collider_poses()
         contacts = self_collision.detect(bvh)
         assert [int(contacts[f]) for f in frames] == mb[b].cpu().numpy().tolist()
+
+
+def test_fused_aabb_and_candidate_filter_equals_the_two_calls():
+    """d3d_aabb_filter_pairs = d3d_aabb + d3d_filter_pairs in one pass: same boxes, same pair set."""
+    import ctypes
+    import torch
+    from distance3d_b200 import _lib
+    from distance3d_b200._lib import c_i64, c_int, ptr
+    tm = UrdfTransformManager()
+    tm.load_urdf(open(os.path.join(DATA, "robot_arm.urdf")).read(), mesh_path=DATA)
+    b = broad_phase.BoundingVolumeHierarchy(tm, "robot_arm")
+    b.fill_tree_with_colliders(tm, fill_self_collision_whitelists=True)
+    model = self_collision.RobotModel(tm, b)
+    B = 3001                                          # not a multiple of the groups per block
+    q = np.random.RandomState(8).uniform(-3.0, 3.0, size=(B, model.n_joints))
+    dc = model.colliders_for(model.forward_kinematics(q))
+    L = _lib.lib()
+    n_pattern = int(model.pattern_t.shape[0])
+    cap = B * n_pattern
+    out = {}
+    for fused in (False, True):
+        aabb = torch.zeros((dc.n, 3, 2), dtype=torch.float64, device="cuda")
+        pairs = torch.zeros((cap, 2), dtype=torch.int32, device="cuda")
+        count = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if fused:
+            _lib._check(L.d3d_aabb_filter_pairs(ctypes.byref(dc.struct), c_i64(B), c_int(model.n_frames),
+                                                ptr(model.pattern_t), c_int(n_pattern), ptr(aabb), ptr(pairs),
+                                                c_i64(cap), ptr(count), _lib.stream_ptr()))
+        else:
+            _lib._check(L.d3d_aabb(ctypes.byref(dc.struct), ptr(aabb), _lib.stream_ptr()))
+            _lib._check(L.d3d_filter_pairs(ptr(aabb), c_i64(B), c_int(model.n_frames), ptr(model.pattern_t),
+                                           c_int(n_pattern), ptr(pairs), c_i64(cap), ptr(count), _lib.stream_ptr()))
+        n = int(count.item())
+        p = pairs[:n].cpu().numpy()
+        out[fused] = (aabb.cpu().numpy(), p[np.lexsort((p[:, 1], p[:, 0]))])
+    assert np.array_equal(out[True][0], out[False][0])
+    assert len(out[True][1]) > 1000 and np.array_equal(out[True][1], out[False][1])
