@@ -602,7 +602,10 @@ D3D_DEV void gjk_finish(const PS &s, const SX &S, const GjkParams &prm, bool wri
 #define GJK_BLOCKS_PRIM (GJK_PQ_GLOBAL ? 4 : 3)
 #endif
 #endif
-#define GJK_BLOCKS_FOR(TM) ((TM) == D3D_PRIMITIVE_MASK ? GJK_BLOCKS_PRIM : GJK_BLOCKS_PER_SM)
+#ifndef GJK_BLOCKS_CONVEX
+#define GJK_BLOCKS_CONVEX GJK_BLOCKS_PRIM  // primitives + hulls instance: 126 registers, fits a 4th CTA as well
+#endif
+#define GJK_BLOCKS_FOR(TM) ((TM) == D3D_PRIMITIVE_MASK ? GJK_BLOCKS_PRIM : ((TM) == GJK_CONVEX_MASK ? GJK_BLOCKS_CONVEX : GJK_BLOCKS_PER_SM))
 #ifndef GJK_REFILL_MIN
 #define GJK_REFILL_MIN 8
 #endif
@@ -862,7 +865,8 @@ int launch_gjk(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, co
     int blocks_prim = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_PRIM);
     // ranges are read on the device; an instance whose range is empty exits at once
     k_gjk_thread<MODE, D3D_PRIMITIVE_MASK><<<blocks_prim, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
-    k_gjk_thread<MODE, GJK_CONVEX_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
+    int blocks_convex = (int)d3d_min64((n_pairs + GJK_THREADS - 1) / GJK_THREADS, (int64_t)sms * GJK_BLOCKS_CONVEX);
+    k_gjk_thread<MODE, GJK_CONVEX_MASK><<<blocks_convex, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     k_gjk_thread<MODE, D3D_ALL_TYPES_MASK><<<blocks, GJK_THREADS, smem, stream>>>(*c, pairs, w, prm);
     if (MODE == 0)
         k_gjk_finish<<<(int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8), 256, 0, stream>>>(w, prm);
