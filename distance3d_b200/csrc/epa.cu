@@ -79,10 +79,20 @@ __global__ void k_epa_keys(d3d_colliders c, const int32_t *__restrict__ pairs, c
         if (sh[i]) atomicAdd(&w.hist[i], sh[i]);
 }
 
-__global__ void k_epa_scan(EpaOrder w) {
+// Exclusive scan of the bins; *wide_types = 1 when a pair has a collider that is neither an analytic
+// primitive nor a hull (the thread kernel then runs its all-types instance, see k_epa_thread).
+__global__ void k_epa_scan(EpaOrder w, int *wide_types) {
     if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < EPA_NBINS; ++i) { w.cursor[i] = acc; acc += w.hist[i]; }
+        int acc = 0, wide = 0;
+        const int lean = D3D_PRIMITIVE_MASK | (1 << D3D_HULL);
+        for (int i = 0; i < EPA_NBINS; ++i) {
+            w.cursor[i] = acc;
+            acc += w.hist[i];
+            if (i < EPA_NBINS - 1 && w.hist[i] &&
+                !(((lean >> (i / D3D_NUM_TYPES)) & 1) && ((lean >> (i % D3D_NUM_TYPES)) & 1)))
+                wide = 1;
+        }
+        *wide_types = wide;
     }
 }
 
@@ -429,9 +439,8 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 #define EPAT_MAXV 68  // 4 + max_iter
 #define EPAT_MF 64
 #define EPAT_ML 32
-#ifndef EPAT_TM
 #define EPAT_TM (D3D_ALL_TYPES_MASK & ~(1 << D3D_MESH))
-#endif
+#define EPAT_LEAN_TM (D3D_PRIMITIVE_MASK | (1 << D3D_HULL))
 #ifndef EPAT_MAX_VERTICES
 // Hulls with more vertices go to the warp kernel (cooperative vertex scan).  Measured on C3 (hulls
 // of 64-256 vertices, 4 Mi pairs): warp kernel 243 ms; thread kernel with a serial scan per thread
@@ -474,13 +483,19 @@ struct EpaThreadState {
     int64_t T;
     int *fb_count;
     int *fb_list;
+    const int *wide_types;  // written by k_epa_scan
 };
 
 static __device__ __noinline__ v3 face_normal_call(v3 v0, v3 v1, v3 v2) { return face_normal(v0, v1, v2); }
 
+// Two instances by the types the support switch compiles in (the kernel stalls on instruction
+// fetch: C5 mix 37.6 -> 35.9 ms with the lean one): TM = primitives + hulls runs when the batch has
+// no other type (flag written by k_epa_scan), TM = EPAT_TM otherwise; the other launch exits at once.
+template <int TM>
 __global__ void __launch_bounds__(EPAT_THREADS, EPAT_BLOCKS_PER_SM)
 k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaParams prm, EpaThreadState S) {
     extern __shared__ double smem[];
+    if ((*S.wide_types != 0) != (TM == EPAT_TM)) return;
     const int tid = threadIdx.x;
     // element e of this thread's state sits at [e * T]; rows x threads < 2^31, so the index
     // arithmetic is 32-bit (one IMAD.WIDE per access)
@@ -655,8 +670,8 @@ k_epa_thread(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs
         int pid = 0;
         if (go) {
             v3 sd = FN(closest);
-            p = support_call<1, EPAT_THREADS, EPAT_TM>(A.type, A.nv, A.V, recA, c.graph, sd.x, sd.y, sd.z, 0) -
-                support_call<1, EPAT_THREADS, EPAT_TM>(B.type, B.nv, B.V, recB, c.graph, -sd.x, -sd.y, -sd.z, 0);
+            p = support_call<1, EPAT_THREADS, TM>(A.type, A.nv, A.V, recA, c.graph, sd.x, sd.y, sd.z, 0) -
+                support_call<1, EPAT_THREADS, TM>(B.type, B.nv, B.V, recB, c.graph, -sd.x, -sd.y, -sd.z, 0);
             double proj = dot_blas(p, sd);
             if (proj - min_dist < eps) {
                 finish(sd * proj, true, D3D_INTERSECTION);
@@ -878,7 +893,7 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
     {
         int kb = (int)d3d_min64((n_pairs + 255) / 256, (int64_t)sms * 8);
         k_epa_keys<<<kb, 256, 0, stream>>>(*c, pairs, npoints, n_pairs, ord);
-        k_epa_scan<<<1, 32, 0, stream>>>(ord);
+        k_epa_scan<<<1, 32, 0, stream>>>(ord, reinterpret_cast<int *>(workspace) + 6);
         k_epa_scatter<<<(int)d3d_min64((n_pairs + 2047) / 2048, (int64_t)sms * 8), 256, 0, stream>>>(n_pairs, ord);
     }
     // Thread-per-pair kernel first (reference default limits, no polytope output); what it hands
@@ -901,8 +916,11 @@ int d3d_epa(const d3d_colliders *c, const int32_t *pairs, int64_t n_pairs, const
         S.fnrm = S.vtx + (size_t)EPAT_MAXV * 3 * S.T;
         S.fdist = S.fnrm + (size_t)EPAT_MF * 3 * S.T;
         S.fids = reinterpret_cast<uint32_t *>(S.fdist + (size_t)EPAT_MF * S.T);
-        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPAT_SMEM_BYTES));
-        k_epa_thread<<<(int)(S.T / EPAT_THREADS), EPAT_THREADS, EPAT_SMEM_BYTES, stream>>>(*c, pairs, n_pairs, prm, S);
+        S.wide_types = reinterpret_cast<int *>(p) + 6;
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa_thread<EPAT_LEAN_TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPAT_SMEM_BYTES));
+        D3D_CUDA_CHECK(cudaFuncSetAttribute(k_epa_thread<EPAT_TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPAT_SMEM_BYTES));
+        k_epa_thread<EPAT_LEAN_TM><<<(int)(S.T / EPAT_THREADS), EPAT_THREADS, EPAT_SMEM_BYTES, stream>>>(*c, pairs, n_pairs, prm, S);
+        k_epa_thread<EPAT_TM><<<(int)(S.T / EPAT_THREADS), EPAT_THREADS, EPAT_SMEM_BYTES, stream>>>(*c, pairs, n_pairs, prm, S);
         D3D_CUDA_CHECK(cudaGetLastError());
         prm.perm = S.fb_list;
         prm.n_dev = S.fb_count;
