@@ -111,11 +111,13 @@ def test_scalar_epa_known_answer():
     assert gjk.gjk(c1, c2b)[0] > 0.0
 
 
-def test_undefined_simplices_are_reported_not_run():
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_undefined_simplices_are_reported_not_run(monkeypatch, kernel):
     """GJK may end with fewer than 4 simplex points; the reference's epa() then reads rows of an
     np.empty array (undefined).  With `n_points` those pairs get status 8 and the rest is
     unchanged."""
     import torch
+    monkeypatch.setenv("D3D_EPA_KERNEL", kernel)
     rs = np.random.RandomState(5)
     cs = d3random.random_collider_set(rs, 800, center_scale=0.3)
     pairs = d3random.random_pairs(rs, len(cs), 6000)
@@ -186,3 +188,21 @@ def test_thread_and_warp_kernels_agree_on_a_large_mixed_batch(monkeypatch):
     for key in ("mtv", "success", "n_faces", "iters"):
         assert np.array_equal(thr[key][ok], wrp[key][ok]), key
     assert np.array_equal(thr["iters"], wrp["iters"])
+
+
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_empty_and_single_pair_batches(monkeypatch, kernel):
+    monkeypatch.setenv("D3D_EPA_KERNEL", kernel)
+    rs = np.random.RandomState(2)
+    cs = d3random.random_collider_set(rs, 50, center_scale=0.2)
+    pairs = d3random.random_pairs(rs, len(cs), 200)
+    g = gjk.gjk_distance_batch(cs, pairs).cpu()
+    sel = np.where((g["dist"] == 0.0) & (g["n_points"] == 4))[0]
+    assert len(sel) > 3
+    empty = epa.epa_batch(cs, pairs[:0], g["simplex"][:0]).cpu()
+    assert empty["mtv"].shape == (0, 3) and empty["status"].shape == (0,)
+    one = epa.epa_batch(cs, pairs[sel[:1]], g["simplex"][sel[:1]]).cpu()
+    ref = O.epa(cs, pairs[sel[:1]], g["simplex"][sel[:1]])
+    assert np.array_equal(one["status"], ref["status"])
+    if ref["status"][0] != 7:
+        assert np.array_equal(one["mtv"], ref["mtv"]) and np.array_equal(one["iters"], ref["iters"])
