@@ -70,6 +70,9 @@ def collide(colliders, penetration=True, distance_threshold=None, shard=True, ca
         # come back with status 8
         res.epa_index = hits
         t5 = mark(None)
-        res.epa = _epa.epa_batch(dc, candidates[hits], g.simplex[hits], n_points=g.n_points[hits])
+        # row gathers by index_select (contiguous rows; advanced indexing took 1.6 ms per gather at 7.6 M hits)
+        res.epa = _epa.epa_batch(dc, candidates.index_select(0, hits),
+                                 g.simplex.reshape(-1, 12).index_select(0, hits).reshape(-1, 4, 3),
+                                 n_points=g.n_points.index_select(0, hits))
         mark("epa", t5)
     return res
