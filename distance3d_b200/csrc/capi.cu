@@ -42,6 +42,90 @@ __global__ void k_prepare(d3d_colliders c, double *verts_out) {
     st3(verts_out + 3 * ((int64_t)c.vert_off[i] + v), box_vertex(col, v));
 }
 
+// Offsets of the wire records from their types alone (exclusive scan of the record sizes), so
+// that the 4-byte offset per collider does not have to cross PCIe: tiles of 1024 colliders, tile
+// sums -> one-block scan of the sums -> offsets inside every tile.
+__device__ __forceinline__ int wire_doubles_dev(int t) {
+    // sphere capsule box ellipsoid cylinder hull mesh disk ellipse cone (d3d_pack_wire_host)
+    const unsigned lo = 0x2E7C1C4u;  // 5 bits each, types 0..5:  4 14 16 15 14 1
+    const unsigned hi = 0x72CEDu;                 //              types 6..9: 13  7 11 14
+    return t < 6 ? (int)((lo >> (5 * t)) & 31u) : (int)((hi >> (5 * (t - 6))) & 31u);
+}
+#define WIRE_TILE 1024
+__global__ void __launch_bounds__(256) k_wire_tile_sums(const uint8_t *__restrict__ wtype, int64_t n, int32_t *tile_sum) {
+    __shared__ int warp_sum[8];
+    const int64_t base = blockIdx.x * (int64_t)WIRE_TILE + 4 * threadIdx.x;
+    int s = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (base + u < n) s += wire_doubles_dev(wtype[base + u]);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sum[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) k_wire_scan_sums(int32_t *tile_sum, int64_t n_tiles) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < n_tiles; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        const int v = i < n_tiles ? tile_sum[i] : 0;
+        int incl = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((threadIdx.x & 31) >= off) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_tot[threadIdx.x], wi = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, wi, off);
+                if ((int)threadIdx.x >= off) wi += y;
+            }
+            warp_tot[threadIdx.x] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+        if (i < n_tiles) tile_sum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_wire_offsets(const uint8_t *__restrict__ wtype, int64_t n,
+                                                      const int32_t *__restrict__ tile_base, int32_t *woff) {
+    __shared__ int warp_tot[8];
+    const int64_t base = blockIdx.x * (int64_t)WIRE_TILE + 4 * threadIdx.x;
+    int sz[4], s = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        sz[u] = base + u < n ? wire_doubles_dev(wtype[base + u]) : 0;
+        s += sz[u];
+    }
+    int incl = s;
+    for (int off = 1; off < 32; off <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((threadIdx.x & 31) >= off) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int acc = tile_base[blockIdx.x] + incl - s;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) acc += warp_tot[w];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (base + u < n) woff[base + u] = acc;
+        acc += sz[u];
+    }
+}
+
 // Compact wire records -> the structure-of-arrays collider set (include/d3d_b200.h
 // d3d_unpack_colliders).  One thread per collider; the record is at wire[wire_off[i]].
 __global__ void k_unpack(const uint8_t *__restrict__ wtype, const int32_t *__restrict__ woff,
@@ -177,6 +261,22 @@ int d3d_unpack_colliders(const uint8_t *wire_type, const int32_t *wire_off, cons
     k_unpack<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(wire_type, wire_off, wire, n, type,
                                                                            pose, param, vert_off, vert_len);
     D3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int d3d_wire_offsets(const uint8_t *wire_type, int64_t n, int32_t *wire_off, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return 0;
+    if (!wire_type || !wire_off) return d3d_set_error("d3d_wire_offsets: null argument");
+    const int64_t n_tiles = (n + WIRE_TILE - 1) / WIRE_TILE;
+    int32_t *tile_sum = nullptr;
+    D3D_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&tile_sum), sizeof(int32_t) * (size_t)n_tiles, stream));
+    k_wire_tile_sums<<<(unsigned)n_tiles, 256, 0, stream>>>(wire_type, n, tile_sum);
+    k_wire_scan_sums<<<1, 1024, 0, stream>>>(tile_sum, n_tiles);
+    k_wire_offsets<<<(unsigned)n_tiles, 256, 0, stream>>>(wire_type, n, tile_sum, wire_off);
+    cudaError_t err = cudaGetLastError();
+    cudaFreeAsync(tile_sum, stream);
+    if (err != cudaSuccess) return d3d_set_error("d3d_wire_offsets: %s", cudaGetErrorString(err));
     return 0;
 }
 

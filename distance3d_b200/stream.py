@@ -5,7 +5,8 @@ pose per collider) when every pair brings its own colliders, so a caller that ho
 in HOST memory is PCIe bound.  `pin_batch(..., wire=True)` (the default) therefore ships the
 compact wire records of `ColliderSet.wire()` - a sphere is 4 doubles, a capsule 14, 99 bytes
 per collider on the primitive mix instead of 164 - and `d3d_unpack_colliders` expands them
-into the structure of arrays in HBM.  (The vertex pool travels only when the batch has hull /
+into the structure of arrays in HBM (the record offsets are recomputed on the device from the
+type bytes, `d3d_wire_offsets`, instead of travelling).  (The vertex pool travels only when the batch has hull /
 mesh vertices in it: the 8 vertices of a box are derived data that `d3d_prepare` writes on
 the device.)  This class
 keeps `slots` sets of device buffers and CUDA streams: while the kernels of batch k
@@ -129,7 +130,8 @@ class GjkDistanceStream:
             for k in _ARRAYS + ("pairs",):
                 size = {"verts": m, "pairs": p}.get(k, n)
                 views[k] = slot.dev[k][:size]
-            sent = ("wire_type", "wire_off", "wire", "verts", "pairs") if wire else _ARRAYS + ("pairs",)
+            # the record offsets are recomputed on the device from the types (d3d_wire_offsets)
+            sent = ("wire_type", "wire", "verts", "pairs") if wire else _ARRAYS + ("pairs",)
             for k in sent:
                 if k == "verts" and not host.get("has_vertex_data", True):
                     continue
@@ -137,6 +139,8 @@ class GjkDistanceStream:
                 dst.copy_(host[k].reshape(dst.shape), non_blocking=True)
                 h2d += host[k].numel() * host[k].element_size()
             if wire:   # expand the records into the structure of arrays (HBM to HBM)
+                _lib._check(L.d3d_wire_offsets(ptr(slot.dev["wire_type"]), c_i64(n), ptr(slot.dev["wire_off"]),
+                                               ctypes.c_void_p(slot.stream.cuda_stream)))
                 _lib._check(L.d3d_unpack_colliders(
                     ptr(slot.dev["wire_type"]), ptr(slot.dev["wire_off"]), ptr(slot.dev["wire"]), c_i64(n),
                     ptr(views["type"]), ptr(views["pose"]), ptr(views["param"]), ptr(views["vert_off"]),

@@ -58,6 +58,11 @@ int d3d_prepare(const d3d_colliders *c, double *verts_out, void *stream);
 int d3d_unpack_colliders(const uint8_t *wire_type, const int32_t *wire_off, const double *wire,
                          int64_t n, int32_t *type, double *pose, double *param, int32_t *vert_off,
                          int32_t *vert_len, void *stream);
+
+/* wire_off[i] = sum of the record sizes of colliders 0 .. i-1, computed on the device from the
+ * types alone: the offsets d3d_pack_wire_host wrote on the host do not have to be uploaded
+ * (4 of ~104 bytes per collider on the primitive mix). */
+int d3d_wire_offsets(const uint8_t *wire_type, int64_t n, int32_t *wire_off, void *stream);
 /* HOST functions (no CUDA call): number of doubles the records of `type[n]` take (-1: unknown
  * type), and the packer itself - `c` holds HOST pointers, the three outputs are host buffers
  * (pinned for the upload) with n, n and d3d_wire_size() entries; n_threads host threads. */

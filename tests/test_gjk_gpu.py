@@ -314,6 +314,23 @@ def test_wire_records_of_every_collider_type_unpack_exactly():
     hv = np.isin(cs.type, (P.BOX, P.HULL, P.MESH))
     assert np.array_equal(out["vert_off"].cpu().numpy()[hv], cs.vert_off[hv])
     assert np.array_equal(out["vert_len"].cpu().numpy()[hv], cs.vert_len[hv])
+    # the record offsets recomputed on the device from the type bytes (what the stream does instead of
+    # uploading them): all ten types, set sizes around the 1024-collider tiles of the scan
+    reps = cs
+    for n_rep in (1, 3, 5300):
+        big = P.concat_sets([cs] * n_rep) if n_rep > 1 else reps
+        for cut in (len(big), 1023, 1024, 1025):
+            if cut > len(big):
+                continue
+            sub_t = np.ascontiguousarray(big.type[:cut].astype(np.uint8))
+            sizes = np.array([4, 14, 16, 15, 14, 1, 13, 7, 11, 14])[sub_t]
+            expect = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+            d_t = t(sub_t)
+            d_o = torch.full((cut,), -1, dtype=torch.int32, device=dev)
+            _lib._check(_lib.lib().d3d_wire_offsets(_lib.ptr(d_t), ctypes.c_int64(cut), _lib.ptr(d_o), _lib.stream_ptr()))
+            assert np.array_equal(d_o.cpu().numpy(), expect), (n_rep, cut)
+    sizes0 = np.array([4, 14, 16, 15, 14, 1, 13, 7, 11, 14])[cs.type]
+    assert np.array_equal(np.concatenate(([0], np.cumsum(sizes0)[:-1])).astype(np.int32), wo)
 
 
 def test_fp32_mode_stated_tolerance():
