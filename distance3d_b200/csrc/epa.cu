@@ -414,23 +414,30 @@ k_epa(d3d_colliders c, const int32_t *__restrict__ pairs, int64_t n_pairs, EpaPa
 //
 // The warp kernel above spends most of its issue slots on work that one lane could do: the two
 // support calls, the convergence test and the edge bookkeeping are replicated on 32 lanes
-// (profiles/r02_epa_phases.txt: ~2000 warp instructions per expanding iteration).  Here a thread
-// owns a pair and replays epa.py:9-202 sequentially, 32 pairs per warp instruction:
+// (profiles/r02_epa_warp_kernel_phases.txt: ~2000 warp instructions per expanding iteration).
+// Here a thread owns a pair and replays epa.py:9-202 sequentially, 32 pairs per warp instruction:
 //   * polytope vertices get small integer ids (table of <= 4 + max_iter points); a face is three
 //     ids, its normal and its cached distance np.sum(v0 * n) (the value find_face_closest_to_origin
 //     recomputes every iteration from the same two vectors); a loose edge is two ids.
 //   * the reference matches edges by COORDINATES with a tolerance (epa.py:189-191).  A new vertex
 //     is compared with every vertex of the table: bit-equal -> it re-uses that id; closer than
-//     epsilon but not equal -> the pair is handed to the warp kernel.  So distinct ids are at
-//     least epsilon apart and "ids equal" is exactly the reference's test.
+//     epsilon but not equal -> the two ids are remembered as a "near pair" (up to four per
+//     polytope) which the edge match treats as equal, exactly like the reference's distance test.
+//     Without near pairs - nearly always - "ids equal" is the whole test.
+//   * visibility is decided by dot(n, p) - dist with an error bound, the reference's expression
+//     (which needs the face's first vertex) only inside the rounding band; the closest face of the
+//     next iteration is collected on the way (see the comments in the loop).
 //   * state lives in global memory, element e of thread t at [e * T + t]: the threads of a warp
-//     walk their face lists in step, so the accesses coalesce, and L1 / L2 hold the working set
-//     (~2.5 KB per pair in use).  Collider records and the loose-edge list are in shared memory.
-//   * pairs the thread kernel does not finish (MeshGraph colliders, near-duplicate vertices,
-//     max_iter reached - the reference then reads a face slot as it looks at that time) go to a
-//     list that the warp kernel processes afterwards from scratch.
-// A thread runs one iteration per trip of a flat loop and fetches its next pair at the loop head,
-// so the lanes of a warp stay converged on the iteration body whatever their pairs' lengths.
+//     walk their face lists in step, so the accesses coalesce (256-byte rows); the kernel is bound
+//     by the DRAM traffic of that state (profiles/r02_ncu_k_epa_thread_v4.txt,
+//     r02_epa_thread_kernel_phases.txt).  Collider records and the loose-edge list are in shared
+//     memory.
+//   * pairs the thread kernel does not finish (MeshGraph colliders, hulls above
+//     EPAT_MAX_VERTICES, a fifth near pair, max_iter reached - the reference then reads a face
+//     slot as it looks at that time) go to a list that the warp kernel processes afterwards from
+//     scratch.
+// One trip of the kernel's loop is one EPA iteration of every lane that owns a pair; the loop is
+// warp-uniform and a warp takes its 32 pairs together (EPAT_REFILL_MIN), see below.
 #define EPAT_THREADS 128
 #ifndef EPAT_BLOCKS_PER_SM
 #define EPAT_BLOCKS_PER_SM 4
