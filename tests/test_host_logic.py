@@ -295,3 +295,51 @@ def test_mesh_io_round_trips_and_urdf_mesh_colliders(tmp_path):
     np.testing.assert_allclose(arm.mesh2origin[:3, 3], [0.0, 0.0, 1.0])
     packed = pack.pack_colliders([base, arm])
     assert packed.type.tolist() == [pack.MESH, pack.MESH] and packed.vert_len.tolist() == [len(used)] * 2
+
+
+def test_host_wire_packer_records_and_sizes():
+    """d3d_wire_size / d3d_pack_wire_host are host code (no GPU): offsets are the exclusive scan of
+    the record sizes, the records hold the pose / parameter / vertex-range fields of their type, and
+    the result does not depend on the number of packing threads."""
+    import ctypes
+    from distance3d_b200 import _lib, colliders as C, pack as P, random as R
+    rs = np.random.RandomState(4)
+    cs = R.random_collider_set(rs, 3000, names=R.PRIMITIVES + ("mesh", "cone"), hull_vertices=(4, 12))
+    extra = P.pack_colliders([C.Disk(rs.randn(3), 0.7, np.array([0.0, 0.6, 0.8])),
+                              C.Ellipse(rs.randn(3), np.eye(3)[:2], np.array([0.4, 0.9]))])
+    cs = P.concat_sets([cs, extra])
+    sizes = np.array([4, 14, 16, 15, 14, 1, 13, 7, 11, 14])[cs.type]
+    wt, wo, w = cs.wire(n_threads=1)
+    assert np.array_equal(wt, cs.type.astype(np.uint8))
+    assert np.array_equal(wo, np.concatenate(([0], np.cumsum(sizes)[:-1])))
+    assert len(w) == sizes.sum()
+    wt8, wo8, w8 = cs.wire(n_threads=8)
+    assert np.array_equal(wt8, wt) and np.array_equal(wo8, wo) and np.array_equal(w8.view(np.uint64), w.view(np.uint64))
+    for i in range(len(cs)):
+        r = w[wo[i]:wo[i] + sizes[i]]
+        t, T, p = cs.type[i], cs.pose[i], cs.param[i]
+        rng = np.array([cs.vert_off[i], cs.vert_len[i]], dtype=np.int32).view(np.float64)[0]
+        if t == P.SPHERE:
+            expect = [T[0, 3], T[1, 3], T[2, 3], p[0]]
+        elif t in (P.CAPSULE, P.CYLINDER, P.CONE):
+            expect = list(T[:3].ravel()) + [p[0], p[1]]
+        elif t == P.ELLIPSOID:
+            expect = list(T[:3].ravel()) + list(p)
+        elif t == P.BOX:
+            expect = list(T[:3].ravel()) + list(p) + [rng]
+        elif t == P.HULL:
+            expect = [rng]
+        elif t == P.DISK:
+            expect = [T[0, 3], T[1, 3], T[2, 3], T[0, 2], T[1, 2], T[2, 2], p[0]]
+        else:   # ellipse
+            expect = [T[0, 3], T[1, 3], T[2, 3], T[0, 0], T[1, 0], T[2, 0], T[0, 1], T[1, 1], T[2, 1], p[0], p[1]]
+        assert np.array_equal(np.asarray(expect).view(np.uint64), r.view(np.uint64)), (i, t)
+    # the size pass is shared by the host threads above 256 k colliders
+    big = np.ascontiguousarray(rs.randint(0, 10, size=1_300_001), dtype=np.int32)
+    L = _lib.lib()
+    L.d3d_wire_size.restype = ctypes.c_int64
+    assert L.d3d_wire_size(ctypes.c_void_p(big.ctypes.data), ctypes.c_int64(len(big))) == \
+        int(np.array([4, 14, 16, 15, 14, 1, 13, 7, 11, 14])[big].sum())
+    big[777_777] = 12
+    assert L.d3d_wire_size(ctypes.c_void_p(big.ctypes.data), ctypes.c_int64(len(big))) == -1
+    assert b"unknown collider type 12 at 777777" in L.d3d_last_error_string()
