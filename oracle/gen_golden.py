@@ -10,6 +10,7 @@ and the outputs of the reference's own functions:
   aabb.npz     collider.aabb(), AabbTree.overlaps_aabb_tree, all_aabbs_overlap
   support.npz  collider.support_function on random directions
   hulls.npz    ConvexHullVertices with 64-256 vertices (config C3 shape)
+  epa_degenerate.npz  epa.epa on simplices with duplicated / 1e-9-apart points (--only-epa-degenerate)
 
 Usage: python oracle/gen_golden.py
 """
@@ -295,8 +296,43 @@ def libccd_fixture():
     np.savez_compressed(os.path.join(OUT, "libccd.npz"), **out)
 
 
+def epa_degenerate_fixture():
+    """epa_degenerate.npz: the real reference's epa.epa on GJK simplices with a duplicated point or two
+    points 1e-9 apart (closer than the edge-matching epsilon of epa.py:189-191): the region where
+    matching loose edges by coordinates differs from matching them by identity."""
+    rs = np.random.RandomState(909)
+    names = ["sphere", "ellipsoid", "capsule", "cylinder", "box", "mesh", "cone"]
+    cols = refbridge.random_reference_colliders(rs, 200, names, **{n: dict(center_scale=0.3) for n in names})
+    cs = refbridge.to_set(cols)
+    pairs = rs.randint(0, len(cols), size=(900, 2)).astype(np.int32)
+    g = run_gjk(cols, pairs)
+    sel = np.where((g["dist"] == 0.0) & (g["status"] == 1))[0]
+    pairs, Y = pairs[sel], g["Y"][sel].copy()
+    kind = np.zeros(len(sel), dtype=np.int32)          # 0 untouched, 1 duplicated point, 2 near-duplicate
+    Y[::3, 1] = Y[::3, 0]; kind[::3] = 1
+    Y[1::3, 2] = Y[1::3, 3] + 1e-9; kind[1::3] = 2
+    n = len(sel)
+    mtv = np.zeros((n, 3)); success = np.zeros(n, dtype=np.uint8); nfaces = np.zeros(n, dtype=np.int32)
+    status = np.ones(n, dtype=np.int32)
+    faces_all = np.zeros((n, 64, 4, 3))
+    for k, (i, j) in enumerate(pairs):
+        try:
+            with np.errstate(all="ignore"):
+                m, faces, ok = epa.epa(Y[k].copy(), cols[i], cols[j])
+        except AssertionError:
+            status[k] = 7
+            continue
+        mtv[k] = m; success[k] = ok; nfaces[k] = len(faces); faces_all[k, :len(faces)] = faces
+    print("epa_degenerate: %d simplices, %d max_faces assertions, %d converged" % (n, int((status == 7).sum()), int(success.sum())))
+    np.savez_compressed(os.path.join(OUT, "epa_degenerate.npz"), pairs=pairs, Y=Y, kind=kind, mtv=mtv,
+                        success=success, n_faces=nfaces, status=status, faces=faces_all, **set_arrays(cs))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-epa-degenerate" in sys.argv:
+        epa_degenerate_fixture()
+        return
     if "--only-libccd" in sys.argv:
         libccd_fixture()
         return

@@ -47,6 +47,24 @@ def test_golden_epa_thread_kernel(monkeypatch):
     assert int(res["deferred"][0]) < 0.2 * len(sel)
 
 
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_golden_degenerate_simplices_vs_reference_outputs(monkeypatch, kernel):
+    """epa_degenerate.npz: outputs of the real reference for simplices with a duplicated point or two
+    points 1e-9 apart - shared vertex ids and near pairs in the thread kernel, coordinate matching in
+    the warp kernel."""
+    monkeypatch.setenv("D3D_EPA_KERNEL", kernel)
+    cs, g = load_golden("epa_degenerate.npz")
+    res = epa.epa_batch(cs, g["pairs"], g["Y"]).cpu()
+    asserted = g["status"] == 7
+    assert np.array_equal(res["status"] == 7, asserted)
+    m = ~asserted
+    assert np.array_equal(res["mtv"][m], g["mtv"][m])
+    assert np.array_equal(res["success"][m], g["success"][m])
+    assert np.array_equal(res["n_faces"][m], g["n_faces"][m])
+    if kernel == "thread":
+        assert int(res["deferred"][0]) < 0.1 * len(m)
+
+
 def test_golden_wide_hulls():
     cs, g = load_golden("hulls.npz")
     sel = np.where(g["epa_status"] >= 0)[0]

@@ -70,6 +70,24 @@ def test_epa_bit_exact_including_max_faces_assert():
     assert asserted.sum() > 0 and m.sum() > 50
 
 
+def test_epa_on_degenerate_simplices_bit_exact():
+    """Real-reference outputs for simplices with a duplicated point or two points 1e-9 apart (closer
+    than the edge-matching epsilon, epa.py:189-191)."""
+    cs, g = load_golden("epa_degenerate.npz")
+    res = O.epa(cs, g["pairs"], g["Y"], return_faces=True)
+    asserted = g["status"] == 7
+    np.testing.assert_array_equal(res["status"] == 7, asserted)
+    m = ~asserted
+    np.testing.assert_array_equal(res["mtv"][m], g["mtv"][m])
+    np.testing.assert_array_equal(res["success"][m], g["success"][m])
+    np.testing.assert_array_equal(res["n_faces"][m], g["n_faces"][m])
+    for q in np.where(m)[0]:
+        n = res["n_faces"][q]
+        np.testing.assert_array_equal(res["faces"][q, :n], g["faces"][q, :n])
+    for kind in (0, 1, 2):
+        assert (m & (g["kind"] == kind)).sum() > 100
+
+
 def test_epa_on_wide_hulls_bit_exact():
     cs, g = load_golden("hulls.npz")
     sel = np.where(g["epa_status"] >= 0)[0]
